@@ -1,0 +1,50 @@
+// Shared helpers for the slide_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/slide_b200.h"
+
+namespace slide {
+
+extern long long g_launch_count;
+void set_cuda_error(cudaError_t e);
+
+// Record the launch and surface launch errors as a return code (the reference exits the process instead).
+inline int after_launch() {
+  ++g_launch_count;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_cuda_error(e);
+    return SLIDE_ERR_CUDA;
+  }
+  return SLIDE_OK;
+}
+
+inline int cuda_rc(cudaError_t e) {
+  if (e != cudaSuccess) {
+    set_cuda_error(e);
+    return SLIDE_ERR_CUDA;
+  }
+  return SLIDE_OK;
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// a*a + b*b + c*c in the order the reference's sm_100a SASS evaluates it (see oracle/slide_oracle.c):
+// FMUL t=b*b ; FFMA t=a*a+t ; FFMA t=c*c+t.  Explicit intrinsics so the compiler cannot re-associate.
+__device__ __forceinline__ float sumsq3_ref(float a, float b, float c) {
+  float t = __fmul_rn(b, b);
+  t = __fmaf_rn(a, a, t);
+  return __fmaf_rn(c, c, t);
+}
+
+// pytorch3d's `dist += diff*diff` over x,y,z as nvcc contracts it.
+__device__ __forceinline__ float sumsq3_p3d(float a, float b, float c) {
+  float t = __fmul_rn(a, a);
+  t = __fmaf_rn(b, b, t);
+  return __fmaf_rn(c, c, t);
+}
+
+}  // namespace slide
