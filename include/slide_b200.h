@@ -123,9 +123,15 @@ void *slide_program_arena(slide_program *p);
 void *slide_program_weights(slide_program *p);
 /* Enqueue ops [first, first+count) on `stream`. */
 int slide_program_run(slide_program *p, int first, int count, slide_stream_t stream);
-/* Capture ops [first, first+count) into a CUDA graph (slot 0..7), then replay it `times` times. */
-int slide_program_capture(slide_program *p, int slot, int first, int count, slide_stream_t stream);
+/* Capture `repeat` back-to-back passes over ops [first, first+count) into one CUDA graph (slot 0..7); replay
+ * launches that graph `times` times (so one replay = `repeat` diffusion steps). */
+int slide_program_capture(slide_program *p, int slot, int first, int count, int repeat, slide_stream_t stream);
 int slide_program_replay(slide_program *p, int slot, int times, slide_stream_t stream);
+/* GEMM kernel selection: 0 = tcgen05 (TF32 operands, fp32 accumulate in TMEM) where the contraction is dense
+ * and aligned, fp32 FFMA otherwise; 1 = fp32 FFMA everywhere.  Env SLIDE_GEMM_BACKEND=simt sets 1 at creation. */
+int slide_program_set_gemm_backend(slide_program *p, int backend);
+/* Non-zero if a tcgen05 pipeline wait ever timed out in this process (a bug guard; results are then invalid). */
+int slide_tc_error(void);
 /* Kernels launched by one pass over ops [first, first+count). */
 int slide_program_launches(slide_program *p, int first, int count);
 

@@ -1,0 +1,463 @@
+// tcgen05 GEMM for sm_100a: C = act( xfA(A) W^T + bias + ev + xfR(resid) ) with TF32 operands, fp32 accumulation
+// in tensor memory, and the fused GroupNorm prologue / statistics epilogue of SLIDE_OP_GEMM.
+//
+// Why not TMA for the operands: the A operand is not stored in the form the tensor core consumes -- the
+// producing layer's GroupNorm + ReLU + timestep/condition vector are applied WHILE loading (that is what
+// removes the separate normalisation pass over HBM), so operand tiles go global -> registers (transform,
+// round-to-nearest TF32) -> shared memory in the canonical K-major SWIZZLE_128B layout, and are handed to the
+// tensor core through the async proxy.  One elected thread issues tcgen05.mma (M=128, N=BN, K=8 per
+// instruction); accumulators live in TMEM and are drained by four warps with tcgen05.ld, transposed through
+// shared memory so that every global store / residual load is a coalesced 128-byte row segment.
+//
+// CTA = 160 threads: warps 0-3 load operand stages, then run the epilogue (warp w owns TMEM lanes 32w..32w+31);
+// warp 4 allocates TMEM and issues the MMAs.  Two CTAs fit per SM (<= 113 KB shared memory, <= 256 TMEM
+// columns each), so one CTA's epilogue overlaps the other's main loop.
+#include "common.cuh"
+#include "program.cuh"
+
+namespace slide {
+
+constexpr int TBM = 128;      // rows per CTA tile (UMMA M)
+constexpr int TBK = 32;       // fp32 elements per K block = one 128-byte swizzle row
+constexpr int TC_THREADS = 160;
+constexpr int TC_PRODUCERS = 128;
+constexpr int TC_TABLE_BUDGET = 48 * 1024;  // bytes of shared memory for the A transform table
+
+__device__ int g_tc_error = 0;  // set when a barrier wait times out (never in a correct run)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU.  After ~2 s (or once any thread has given up) the wait
+// returns false and the kernel drains without touching tensor memory results.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((it & 255u) == 0u) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (*(volatile int *)&g_tc_error != 0 || t1 - t0 > 2000000000ull) {
+        atomicExch(&g_tc_error, 1);
+        return false;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// leading byte offset 1 (unused for swizzled K-major), stride byte offset 1024 B (8 rows x 128 B), version 1,
+// layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, TF32 x TF32, both K-major, M=128, N=bn.
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+}
+
+struct TcSmemLayout {
+  int stage_bytes, stages_bytes, table_off, table_bytes, bar_off, total;
+};
+
+__host__ __device__ inline TcSmemLayout tc_layout(int BN, int STAGES, int table_entries) {
+  TcSmemLayout L;
+  L.stage_bytes = (TBM + BN) * TBK * 4;
+  const int epi_bytes = 4 * 32 * 33 * 4 + XF_MAXS * BN * 16;  // transpose buffers + resid transform table
+  L.stages_bytes = STAGES * L.stage_bytes > epi_bytes ? STAGES * L.stage_bytes : epi_bytes;
+  L.table_off = L.stages_bytes;
+  L.table_bytes = table_entries * 16;
+  L.bar_off = L.table_off + ((L.table_bytes + 15) / 16) * 16;
+  L.total = L.bar_off + 256 + XF_MAXS * XF_MAXG * 2 * 4 + 1024 /* alignment slack */;
+  return L;
+}
+
+// Fill a transform table: entry (sl, k) = (scale, shift, add, 0) so that y = relu?(x*scale + shift) + add.
+__device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, int s0, int ns, int ncols, int col0,
+                                              int stride, int step, int tid, int nthreads) {
+  const int G = x.stats ? x.nnorm / x.cg : 1;
+  for (int e = tid; e < ns * ncols; e += nthreads) {
+    const int sl = e / ncols, kk = e - sl * ncols;
+    const int k = col0 + kk;
+    float scale = 1.f, shift = 0.f, add = 0.f;
+    if (x.stats) {
+      const int ch = x.choff + k;
+      if (ch < x.nnorm) {
+        const double *st = x.stats + ((size_t)(s0 + sl) * G + ch / x.cg) * 2;
+        const double m = st[0] * (double)x.inv_count;
+        double var = st[1] * (double)x.inv_count - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        const float rstd = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS));
+        scale = rstd * __ldg(x.gamma + ch);
+        shift = __ldg(x.beta + ch) - (float)m * scale;
+      }
+    }
+    if (x.addvec) {
+      const long long arow = x.addmode == 0 ? (s0 + sl) : (x.addmode == 1 ? step : 0);
+      add = __ldg(x.addvec + arow * x.addld + k);
+    }
+    tab[sl * stride + kk] = make_float4(scale, shift, add, 0.f);
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, int table_stride, int table_rows) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const TcSmemLayout L = tc_layout(BN, STAGES, 0);
+  const bool has_xfa = a.xfa.stats != nullptr || a.xfa.addvec != nullptr || a.xfa.relu != 0;
+  float4 *tabA = reinterpret_cast<float4 *>(smem + L.table_off);
+  const int tabA_bytes = has_xfa ? table_rows * table_stride * 16 : 0;
+  uint8_t *ctrl = smem + L.table_off + ((tabA_bytes + 15) / 16) * 16;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(ctrl);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *accum_bar = empty_bar + STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+  float *stacc = reinterpret_cast<float *>(ctrl + 256);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
+  const int mlast = min(m0 + TBM, a.M) - 1;
+  const int step = a.step ? *a.step : 0;
+  const int num_kb = (a.K + TBK - 1) / TBK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full_bar + s), TC_PRODUCERS);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    mbar_init(smem_u32(accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  const int sA0 = m0 / a.xfa.R;
+  if (has_xfa)
+    fill_xf_table(a.xfa, tabA, sA0, mlast / a.xfa.R - sA0 + 1, a.K, 0, table_stride, step, tid, TC_THREADS);
+  if (a.st_stats)
+    for (int e = tid; e < XF_MAXS * XF_MAXG * 2; e += TC_THREADS) stacc[e] = 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  bool ok = true;
+  if (warp < 4) {
+    // ------------------------------------------------------------------------------------- producers
+    const int chunk = tid & 7;   // 16-byte chunk within the 128-byte K row
+    const int rbase = tid >> 3;  // 0..15
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      if (ok) ok = mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
+      uint8_t *sa = smem + (size_t)s * L.stage_bytes;
+      uint8_t *sb = sa + TBM * TBK * 4;
+      const int k = kb * TBK + chunk * 4;
+      // A tile: 128 rows, 8 rows in flight per thread
+      float4 va[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + rbase + 16 * i;
+        va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < a.M && k < a.K) va[i] = *reinterpret_cast<const float4 *>(a.A + (size_t)m * a.lda + k);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rbase + 16 * i;
+        const int m = m0 + r;
+        float v[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
+        if (has_xfa && m < a.M) {
+          const float4 *t = tabA + (m / a.xfa.R - sA0) * table_stride + k;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (k + u < a.K) {
+              const float4 c = t[u];
+              float y = fmaf(v[u], c.x, c.y);
+              if (a.xfa.relu) y = fmaxf(y, 0.f);
+              v[u] = y + c.z;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (k + u >= a.K) v[u] = 0.f;
+        const uint4 o = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+        *reinterpret_cast<uint4 *>(sa + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
+      }
+      // W tile: BN rows
+#pragma unroll
+      for (int i0 = 0; i0 < BN / 16; i0 += 8) {
+        float4 vw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = n0 + rbase + 16 * (i0 + i);
+          vw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i0 + i < BN / 16 && n < a.N && k < a.K)
+            vw[i] = __ldg(reinterpret_cast<const float4 *>(a.W + (size_t)n * a.ldw + k));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i0 + i < BN / 16) {
+            const int r = rbase + 16 * (i0 + i);
+            float v[4] = {vw[i].x, vw[i].y, vw[i].z, vw[i].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (k + u >= a.K) v[u] = 0.f;
+            const uint4 o = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+            *reinterpret_cast<uint4 *>(sb + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
+          }
+        }
+      }
+      // make the generic-proxy writes visible to the tensor core (async proxy), then signal
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(smem_u32(full_bar + s));
+    }
+  } else {
+    // ------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        if (ok) ok = mbar_wait(smem_u32(full_bar + s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + (size_t)s * L.stage_bytes);
+        const uint64_t da = make_smem_desc(sa);
+        const uint64_t db = make_smem_desc(sa + TBM * TBK * 4);
+        if (ok) {
+#pragma unroll
+          for (int kk = 0; kk < TBK / 8; ++kk) {
+            const uint32_t accum = (kb > 0 || kk > 0) ? 1u : 0u;
+            // advance 8 TF32 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "setp.ne.b32 p, %4, 0;\n"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+                "}\n" ::"r"(tmem_base),
+                "l"(da + (uint64_t)(kk * 2)), "l"(db + (uint64_t)(kk * 2)), "r"(idesc), "r"(accum)
+                : "memory");
+          }
+        }
+        // release the stage to the producers once the MMAs that read it have completed
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(empty_bar + s))
+                     : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(accum_bar))
+                   : "memory");
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------------------------------- epilogue
+  if (warp < 4) {
+    if (ok) ok = mbar_wait(smem_u32(accum_bar), 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  // every stage buffer is dead now (all MMAs completed before accum_bar fired): reuse it
+  float *tbuf = reinterpret_cast<float *>(smem) + warp * (32 * 33);
+  float4 *tabR = reinterpret_cast<float4 *>(smem + 4 * 32 * 33 * 4);
+  const bool has_xfr = a.res && (a.xfr.stats != nullptr || a.xfr.addvec != nullptr || a.xfr.relu != 0);
+  const int sR0 = m0 / a.xfr.R;
+  // all 160 threads reach this barrier: producers are past their last smem write, warp 4 is past its issue loop
+  __syncthreads();
+  if (has_xfr) {
+    const int ncols = min(BN, a.N - n0);
+    fill_xf_table(a.xfr, tabR, sR0, mlast / a.xfr.R - sR0 + 1, ncols, n0, BN, step, tid, TC_THREADS);
+  }
+  __syncthreads();
+
+  if (warp < 4) {
+    const int sS0 = m0 / a.st_R;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= a.N) break;
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      if (ok) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+              "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+              "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      // transpose: thread (= row) writes its 32 columns; then lane = column
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      const int n = n0 + c0 + lane;
+      const bool ncol = n < a.N;
+      const float bias = (ncol && a.bias) ? __ldg(a.bias + n) : 0.f;
+      const int stch = a.st_choff + n;
+      const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
+      float ssum = 0.f, ssq = 0.f;
+      int scur = -1;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = m0 + warp * 32 + rr;
+        if (m >= a.M) break;
+        if (ncol) {
+          float v = tbuf[rr * 33 + lane] + bias;
+          if (a.ev) v += a.ev[(size_t)(m / a.evdiv) * a.evld + n];
+          if (a.res) {
+            float x = a.res[(size_t)m * a.ldr + n];
+            if (has_xfr) {
+              const float4 c = tabR[(m / a.xfr.R - sR0) * BN + c0 + lane];
+              x = fmaf(x, c.x, c.y);
+              if (a.xfr.relu) x = fmaxf(x, 0.f);
+              x += c.z;
+            }
+            v += x;
+          }
+          v = act_apply(a.act, v);
+          a.C[(size_t)m * a.ldc + n] = v;
+          if (dost) {
+            const int sm = m / a.st_R;
+            if (sm != scur) {
+              if (scur >= 0) {
+                float *slot = stacc + ((scur - sS0) * XF_MAXG + stch / a.st_cg) * 2;
+                atomicAdd(slot, ssum);
+                atomicAdd(slot + 1, ssq);
+              }
+              scur = sm;
+              ssum = 0.f;
+              ssq = 0.f;
+            }
+            ssum += v;
+            ssq = fmaf(v, v, ssq);
+          }
+        }
+      }
+      if (dost && scur >= 0) {
+        float *slot = stacc + ((scur - sS0) * XF_MAXG + stch / a.st_cg) * 2;
+        atomicAdd(slot, ssum);
+        atomicAdd(slot + 1, ssq);
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (a.st_stats) {
+    const int G = a.st_nnorm / a.st_cg;
+    const int sS0 = m0 / a.st_R;
+    const int ns = mlast / a.st_R - sS0 + 1;
+    for (int e = tid; e < ns * G * 2; e += TC_THREADS) {
+      const int sl = e / (G * 2), rem = e - sl * G * 2;
+      const float v = stacc[(sl * XF_MAXG + (rem >> 1)) * 2 + (rem & 1)];
+      if (v != 0.f) atomicAdd(a.st_stats + ((size_t)(sS0 + sl) * G) * 2 + rem, (double)v * (double)a.st_weight);
+    }
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+  }
+}
+
+// A row tile must map onto whole samples (or lie inside one): then it touches at most XF_MAXS of them.
+static bool spans_ok_tc(int R) { return R % TBM == 0 || (TBM % R == 0 && TBM / R <= XF_MAXS); }
+static int tc_rows_per_tile(int R) { return R % TBM == 0 ? 1 : TBM / R; }
+static int tc_table_stride(const GemmArgs &a) { return ((a.K + 3) / 4) * 4; }
+static bool has_xf(const XFd &x) { return x.stats || x.addvec || x.relu; }
+
+bool gemm_tc_eligible(const GemmArgs &a) {
+  if (a.M < TBM || a.K < 48 || a.N < 32) return false;
+  if (((uintptr_t)a.A & 15) || (a.lda & 3) || ((uintptr_t)a.W & 15) || (a.ldw & 3)) return false;
+  if (has_xf(a.xfa)) {
+    if (!spans_ok_tc(a.xfa.R)) return false;
+    if (tc_rows_per_tile(a.xfa.R) * tc_table_stride(a) * 16 > TC_TABLE_BUDGET) return false;
+    if (a.xfa.stats && a.xfa.nnorm / a.xfa.cg > XF_MAXG) return false;
+  }
+  if (a.res && has_xf(a.xfr)) {
+    if (!spans_ok_tc(a.xfr.R)) return false;
+    if (a.xfr.stats && a.xfr.nnorm / a.xfr.cg > XF_MAXG) return false;
+  }
+  if (a.st_stats && (!spans_ok_tc(a.st_R) || a.st_nnorm / a.st_cg > XF_MAXG)) return false;
+  return true;
+}
+
+constexpr int TC_MAX_DYN_SMEM = 227 * 1024;
+
+template <int BN, int STAGES>
+static int launch_tc(const GemmArgs &a, cudaStream_t st) {
+  const int stride = tc_table_stride(a);
+  const int rows = has_xf(a.xfa) ? tc_rows_per_tile(a.xfa.R) : 0;
+  const TcSmemLayout L = tc_layout(BN, STAGES, 0);
+  const int table_bytes = rows * stride * 16;
+  const int total = L.table_off + ((table_bytes + 15) / 16) * 16 + 256 + XF_MAXS * XF_MAXG * 2 * 4 + 1024;
+  if (total > TC_MAX_DYN_SMEM) return SLIDE_ERR_UNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TC_MAX_DYN_SMEM);
+    if (e != cudaSuccess) return cuda_rc(e);
+    configured = true;
+  }
+  dim3 grid(ceil_div(a.M, TBM), ceil_div(a.N, BN));
+  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, total, st>>>(a, stride, rows);
+  return after_launch();
+}
+
+int launch_gemm_tc(const GemmArgs &a, cudaStream_t st) {
+  if (a.N > 128) return launch_tc<256, 2>(a, st);
+  if (a.N > 64) return launch_tc<128, 3>(a, st);
+  if (a.N > 32) return launch_tc<64, 4>(a, st);
+  return launch_tc<32, 4>(a, st);
+}
+
+int tc_error_flag() {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int));
+  return v;
+}
+
+}  // namespace slide

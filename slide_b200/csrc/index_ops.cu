@@ -27,17 +27,20 @@ namespace slide {
 //
 // MODE 0: pointnet2_ops._ext semantics (start 0, |p|^2 <= 1e-3 skipped, init 1e10, i32 output).
 // MODE 1: pytorch3d semantics (start index given, init +inf, lowest index wins ties, i64 output, -1 pad).
+// MODE 2: MODE 1 with i32 start indices / output and no per-cloud lengths (used inside slide programs).
+// `ldx` is the row stride of xyz in floats (3 for a packed cloud).
 template <int PPT, int MODE>
-__global__ void __launch_bounds__(1024) fps_kernel(const float *__restrict__ xyz, int N, int m, int s_log2,
+__global__ void __launch_bounds__(1024) fps_kernel(const float *__restrict__ xyz, int ldx, int N, int m, int s_log2,
                                                    int nb_log2, const int64_t *__restrict__ lengths,
                                                    const int64_t *__restrict__ Ks,
-                                                   const int64_t *__restrict__ start_idx, void *out_raw) {
+                                                   const void *__restrict__ start_raw, void *out_raw) {
   __shared__ uint2 slots[2][32];
   const int b = blockIdx.x;
   const int T = blockDim.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-  const float *p = xyz + (size_t)b * N * 3;
+  const float *p = xyz + (size_t)b * N * ldx;
+  const int64_t *start_idx = (const int64_t *)start_raw;
 
   int len = N, kn = m;
   if (MODE == 1) {
@@ -54,9 +57,9 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float *__restrict__ xyz
   for (int i = 0; i < PPT; ++i) {
     const int k = tid + i * T;
     const bool in = k < len;
-    px[i] = in ? p[k * 3 + 0] : 0.f;
-    py[i] = in ? p[k * 3 + 1] : 0.f;
-    pz[i] = in ? p[k * 3 + 2] : 0.f;
+    px[i] = in ? p[(size_t)k * ldx + 0] : 0.f;
+    py[i] = in ? p[(size_t)k * ldx + 1] : 0.f;
+    pz[i] = in ? p[(size_t)k * ldx + 2] : 0.f;
     if (MODE == 0) {
       const float mag = sumsq3_ref(px[i], py[i], pz[i]);
       ok[i] = in && !((double)mag <= 1e-3);
@@ -73,11 +76,14 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float *__restrict__ xyz
 
   int old = 0;
   if (MODE == 1 && start_idx) old = (int)start_idx[b];
+  if (MODE == 2 && start_raw) old = ((const int *)start_raw)[b];
   int *out32 = (int *)out_raw + (size_t)b * m;
   long long *out64 = (long long *)out_raw + (size_t)b * m;
   if (tid == 0) {
     if (MODE == 0) {
       if (m > 0) out32[0] = 0;
+    } else if (MODE == 2) {
+      if (m > 0) out32[0] = old;
     } else {
       for (int j = kn > 0 ? kn : 0; j < m; ++j) out64[j] = -1;
       if (kn > 0) out64[0] = old;
@@ -85,7 +91,8 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float *__restrict__ xyz
   }
 
   for (int j = 1; j < kn; ++j) {
-    const float x1 = __ldg(p + old * 3 + 0), y1 = __ldg(p + old * 3 + 1), z1 = __ldg(p + old * 3 + 2);
+    const float x1 = __ldg(p + (size_t)old * ldx + 0), y1 = __ldg(p + (size_t)old * ldx + 1),
+                z1 = __ldg(p + (size_t)old * ldx + 2);
     uint32_t bhi = 0, brk = 0xffffffffu;
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
@@ -121,10 +128,10 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float *__restrict__ xyz
       old = (int)mr;
     }
     if (tid == 0) {
-      if (MODE == 0)
-        out32[j] = old;
-      else
+      if (MODE == 1)
         out64[j] = old;
+      else
+        out32[j] = old;
     }
   }
 }
@@ -145,8 +152,8 @@ static int ilog2_ceil(int v) {
 }
 
 template <int MODE>
-static int launch_fps(const float *xyz, int B, int N, int m, const int64_t *lengths, const int64_t *Ks,
-                      const int64_t *start, void *out, cudaStream_t st) {
+static int launch_fps(const float *xyz, int ldx, int B, int N, int m, const int64_t *lengths, const int64_t *Ks,
+                      const void *start, void *out, cudaStream_t st) {
   if (B == 0 || m == 0) return SLIDE_OK;
   if (N > 16384) return SLIDE_ERR_UNSUPPORTED;
   int T = ((N + 31) / 32) * 32;
@@ -157,7 +164,7 @@ static int launch_fps(const float *xyz, int B, int N, int m, const int64_t *leng
   const int nb_log2 = ilog2_ceil(ceil_div(N, S));
   if (s_log2 + nb_log2 > 31) return SLIDE_ERR_UNSUPPORTED;
 #define FPS_CASE(P)                                                                                      \
-  fps_kernel<P, MODE><<<B, T, 0, st>>>(xyz, N, m, s_log2, nb_log2, lengths, Ks, start, out);             \
+  fps_kernel<P, MODE><<<B, T, 0, st>>>(xyz, ldx, N, m, s_log2, nb_log2, lengths, Ks, start, out);        \
   break;
   switch (ppt <= 1 ? 1 : ppt <= 2 ? 2 : ppt <= 4 ? 4 : ppt <= 8 ? 8 : 16) {
     case 1: FPS_CASE(1)
@@ -427,6 +434,12 @@ __global__ void __launch_bounds__(128) knn_kernel(const float *__restrict__ p1, 
   }
 }
 
+// entry points for the program executor (program.cu)
+int program_fps(int mode, const float *xyz, int ldx, int B, int N, int m, const int *start, int *out, cudaStream_t st) {
+  if (mode == 0) return launch_fps<0>(xyz, ldx, B, N, m, nullptr, nullptr, nullptr, out, st);
+  return launch_fps<2>(xyz, ldx, B, N, m, nullptr, nullptr, start, out, st);
+}
+
 long long g_launch_count = 0;
 static thread_local cudaError_t g_last_error = cudaSuccess;
 void set_cuda_error(cudaError_t e) { g_last_error = e; }
@@ -444,7 +457,7 @@ void slide_reset_launch_count(void) { g_launch_count = 0; }
 
 int slide_furthest_point_sampling(const float *xyz, int B, int N, int m, int *idx, slide_stream_t stream) {
   if (!xyz || !idx || B < 0 || N <= 0 || m < 0) return SLIDE_ERR_INVALID;
-  return launch_fps<0>(xyz, B, N, m, nullptr, nullptr, nullptr, idx, (cudaStream_t)stream);
+  return launch_fps<0>(xyz, 3, B, N, m, nullptr, nullptr, nullptr, idx, (cudaStream_t)stream);
 }
 
 int slide_sample_farthest_points(const float *points, int B, int P, int D, const int64_t *lengths,
@@ -452,7 +465,7 @@ int slide_sample_farthest_points(const float *points, int B, int P, int D, const
                                  slide_stream_t stream) {
   if (!points || !idx || B < 0 || P <= 0 || maxK < 0) return SLIDE_ERR_INVALID;
   if (D != 3) return SLIDE_ERR_UNSUPPORTED;
-  return launch_fps<1>(points, B, P, maxK, lengths, K, start_idx, idx, (cudaStream_t)stream);
+  return launch_fps<1>(points, 3, B, P, maxK, lengths, K, start_idx, idx, (cudaStream_t)stream);
 }
 
 int slide_gather_points(const float *points, const int *idx, int B, int C, int N, int m, float *out,

@@ -1,0 +1,558 @@
+// Executor of slide programs (include/slide_program.h): one kernel per record, optional CUDA-graph replay.
+//
+// This file holds the memory-bound "glue" kernels of the fused networks (grouping, soft-max aggregation,
+// DDPM update, up-sampling, copies) and the program object; the GEMM kernels live in gemm_simt.cu (fp32 FFMA,
+// any shape) and gemm_tc.cu (tcgen05 / TMEM, TF32 operands, fp32 accumulate).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "program.cuh"
+
+namespace slide {
+
+// =====================================================================================================
+// STEP_BEGIN: zero the statistics region, decrement the step counter
+// =====================================================================================================
+__global__ void step_begin_kernel(uint4 *__restrict__ zero, size_t n16, int *__restrict__ step) {
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = i0; i < n16; i += stride) zero[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (i0 == 0 && step) *step -= 1;
+}
+
+// =====================================================================================================
+// kNN inside programs: strided point rows, i32 indices, optional squared distances
+// =====================================================================================================
+// One thread per query; the reference cloud streams through shared memory.  Same insertion rule as
+// knn_kernel in index_ops.cu (strict <, ascending index on ties).
+constexpr int PK_TILE = 1024;
+
+template <int KCAP>
+__global__ void __launch_bounds__(128) knn_prog_kernel(const float *__restrict__ q, int ldq, int P1,
+                                                       const float *__restrict__ ref, int ldr, int P2, int K,
+                                                       int *__restrict__ idx, float *__restrict__ d2) {
+  __shared__ float tile[PK_TILE * 3];
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < P1;
+  const float *qq = q + ((size_t)b * P1 + (active ? i : 0)) * ldq;
+  const float qx = qq[0], qy = qq[1], qz = qq[2];
+  const float *r = ref + (size_t)b * P2 * ldr;
+  float bd[KCAP];
+  int bi[KCAP];
+#pragma unroll
+  for (int k = 0; k < KCAP; ++k) {
+    bd[k] = INFINITY;
+    bi[k] = 0;
+  }
+  for (int base = 0; base < P2; base += PK_TILE) {
+    const int tn = min(PK_TILE, P2 - base);
+    __syncthreads();
+    for (int t = threadIdx.x; t < tn; t += blockDim.x) {
+      const float *s = r + (size_t)(base + t) * ldr;
+      tile[t * 3 + 0] = s[0];
+      tile[t * 3 + 1] = s[1];
+      tile[t * 3 + 2] = s[2];
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int k = 0; k < tn; ++k) {
+      const float d = sumsq3_p3d(qx - tile[k * 3 + 0], qy - tile[k * 3 + 1], qz - tile[k * 3 + 2]);
+      if (d < bd[KCAP - 1]) {
+        // branch-free sorted insertion over a fully unrolled register array
+        float cd = d;
+        int ci = base + k;
+#pragma unroll
+        for (int s = 0; s < KCAP; ++s) {
+          const bool sw = cd < bd[s];
+          const float td = bd[s];
+          const int ti = bi[s];
+          bd[s] = sw ? cd : td;
+          bi[s] = sw ? ci : ti;
+          cd = sw ? td : cd;
+          ci = sw ? ti : ci;
+        }
+      }
+    }
+  }
+  if (active) {
+    int *ii = idx + ((size_t)b * P1 + i) * K;
+    float *dd = d2 ? d2 + ((size_t)b * P1 + i) * K : nullptr;
+#pragma unroll
+    for (int k = 0; k < KCAP; ++k) {
+      if (k < K) {
+        ii[k] = bi[k];
+        if (dd) dd[k] = bd[k];
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// GROUP: one warp per grouped row; channels-last makes the feature part a contiguous row copy
+// =====================================================================================================
+__global__ void __launch_bounds__(256) group_kernel(int mode, const float *__restrict__ F, int ldf, int C,
+                                                    const float *__restrict__ xyz, int ldx, int N,
+                                                    const float *__restrict__ ctr, int ldc, int np,
+                                                    const int *__restrict__ idx, int K, const float *__restrict__ d2,
+                                                    float *__restrict__ out, int ldo, int inc_abs, int inc_ctr,
+                                                    long long rows) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const long long pi = row / K;  // (sample, point)
+    const int s = (int)(pi / np);
+    const int j = idx[row];
+    float *o = out + row * ldo;
+    if (C > 0) {
+      const float *f = F + ((size_t)s * N + j) * ldf;
+      for (int c = lane; c < C; c += 32) o[c] = __ldg(f + c);
+    }
+    const float *xj = xyz + ((size_t)s * N + j) * ldx;
+    const float *ci = ctr + (size_t)pi * ldc;
+    if (mode == 0) {
+      // [x_j - c_i | x_j | c_i]
+      if (lane < 3) {
+        const float a = __ldg(xj + lane), c = __ldg(ci + lane);
+        int pos = C;
+        o[pos + lane] = __fsub_rn(a, c);
+        pos += 3;
+        if (inc_abs) {
+          o[pos + lane] = a;
+          pos += 3;
+        }
+        if (inc_ctr) o[pos + lane] = c;
+      }
+    } else {
+      // [d2 | w | x_j | x_j - c_i | c_i],  w = (1/(d2+1e-8)) / sum_k (1/(d2+1e-8))  (sum in ascending k like torch.sum)
+      if (lane < 3) {
+        const float a = __ldg(xj + lane), c = __ldg(ci + lane);
+        o[C + 2 + lane] = a;
+        o[C + 5 + lane] = __fsub_rn(a, c);
+        o[C + 8 + lane] = c;
+      } else if (lane == 3) {
+        const float *dr = d2 + pi * K;
+        float sum = 0.f;
+        for (int k = 0; k < K; ++k) sum = __fadd_rn(sum, __fdiv_rn(1.0f, __fadd_rn(dr[k], 1e-8f)));
+        const float dk = d2[row];
+        o[C] = dk;
+        o[C + 1] = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(dk, 1e-8f)), sum);
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// SOFTMAX_WSUM: out[i,c] = sum_k xf(V)[i,k,c] * softmax_k(S[i,k,c])   (one thread per (i,c), coalesced in c)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) softmax_wsum_kernel(const float *__restrict__ S, int lds,
+                                                           const float *__restrict__ Vt, int ldv, XFd xf,
+                                                           const int *__restrict__ step_ptr, float *__restrict__ out,
+                                                           int ldo, long long rows, int K, int C) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * C) return;
+  const long long i = e / C;
+  const int c = (int)(e - i * C);
+  const long long r0 = i * K;
+  const int step = step_ptr ? *step_ptr : 0;
+  // all K rows of one point belong to one sample
+  const int s = xf.R > 0 ? (int)(r0 / xf.R) : 0;
+  float mean = 0.f, rstd = 1.f, gam = 1.f, bet = 0.f;
+  bool norm = false;
+  if (xf.stats) {
+    const int ch = xf.choff + c;
+    if (ch < xf.nnorm) {
+      norm = true;
+      const int G = xf.nnorm / xf.cg;
+      const double *st = xf.stats + ((size_t)s * G + ch / xf.cg) * 2;
+      const double m = st[0] * (double)xf.inv_count;
+      double var = st[1] * (double)xf.inv_count - m * m;
+      var = var < 0.0 ? 0.0 : var;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS));
+      gam = __ldg(xf.gamma + ch);
+      bet = __ldg(xf.beta + ch);
+    }
+  }
+  float add = 0.f;
+  if (xf.addvec) {
+    const long long arow = xf.addmode == 0 ? s : (xf.addmode == 1 ? step : 0);
+    add = xf.addvec[arow * xf.addld + c];
+  }
+  float mx = -INFINITY;
+  for (int k = 0; k < K; ++k) mx = fmaxf(mx, S[(r0 + k) * lds + c]);
+  float den = 0.f, acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float w = expf(S[(r0 + k) * lds + c] - mx);
+    float v = Vt[(r0 + k) * ldv + c];
+    if (norm) v = (v - mean) * rstd * gam + bet;
+    if (xf.relu) v = fmaxf(v, 0.f);
+    v += add;
+    den += w;
+    acc = fmaf(v, w, acc);
+  }
+  out[i * ldo + c] = acc / den;
+}
+
+// =====================================================================================================
+// element-wise helpers
+// =====================================================================================================
+__global__ void copy_cols_kernel(const float *__restrict__ src, int lds, float *__restrict__ dst, int ldd,
+                                 long long rows, int n) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * n) return;
+  const long long r = e / n;
+  const int c = (int)(e - r * n);
+  dst[r * ldd + c] = src[r * lds + c];
+}
+
+// DDPM ancestral update; every multiply / add is a separate IEEE operation in the reference's order (torch
+// evaluates the expression op by op), so given the same eps the update is bit-exact.
+__global__ void ddpm_update_kernel(int mode, float *__restrict__ x, int ldx, const float *__restrict__ eps, int lde,
+                                   const float *__restrict__ noise, long long rows, int ncols, int col0,
+                                   const float *__restrict__ table, const int *__restrict__ step_ptr, float clamp) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * ncols) return;
+  const long long r = e / ncols;
+  const int c = (int)(e - r * ncols);
+  if (c < col0) return;
+  const int t = *step_ptr;
+  const float *tab = table + (size_t)t * 8;
+  const float xv = x[r * ldx + c], ev = eps[r * lde + c];
+  const float nz = noise[((size_t)t * rows + r) * ncols + c];
+  float res;
+  if (mode == 0) {
+    // x = (x - k1*eps) / sqrt_alpha ; if t > 0: x += sigma * z          (pointnet2/util.py:247-253)
+    res = __fdiv_rn(__fsub_rn(xv, __fmul_rn(tab[0], ev)), tab[1]);
+    if (t > 0) res = __fadd_rn(res, __fmul_rn(tab[2], nz));
+  } else {
+    // x0 = c1*x - c2*eps ; clamp ; mean = pm1*x0 + pm2*x ; x = mean + (t != 0) * sig * z   (diffusion.py:71-92)
+    float x0 = __fsub_rn(__fmul_rn(tab[0], xv), __fmul_rn(tab[1], ev));
+    if (clamp > 0.f) x0 = fminf(fmaxf(x0, -clamp), clamp);
+    const float mean = __fadd_rn(__fmul_rn(tab[2], x0), __fmul_rn(tab[3], xv));
+    const float m = t == 0 ? 0.f : 1.f;
+    res = __fadd_rn(mean, __fmul_rn(__fmul_rn(m, tab[4]), nz));
+  }
+  x[r * ldx + c] = res;
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ src, int lds, int N, const int *__restrict__ idx, int m,
+                                   float *__restrict__ dst, int ldd, int ncols, long long total_rows) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total_rows * ncols) return;
+  const long long r = e / ncols;  // (sample, j)
+  const int c = (int)(e - r * ncols);
+  const long long s = r / m;
+  const int j = idx[r];
+  dst[r * ldd + c] = src[((size_t)s * N + j) * lds + c];
+}
+
+__global__ void upsample_kernel(const float *__restrict__ coarse, int ldc, int coarse_c,
+                                const float *__restrict__ disp, int ldd, float *__restrict__ out, int ldo,
+                                long long rows, int factor, int Fd, float inv_sqrt_f, float scale) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * factor * Fd) return;
+  const long long orow = e / Fd;
+  const int c = (int)(e - orow * Fd);
+  const long long n = orow / factor;
+  const int q = (int)(orow - n * factor);
+  const float base = c < coarse_c ? coarse[n * ldc + c] : 0.f;
+  const float d = disp[n * ldd + q * Fd + c];
+  out[orow * ldo + c] = __fadd_rn(base, __fmul_rn(__fmul_rn(d, inv_sqrt_f), scale));
+}
+
+__global__ void temb_kernel(const float *__restrict__ ts, const float *__restrict__ freq, int half,
+                            float *__restrict__ out, int ldo, int rows) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * half) return;
+  const int r = e / half, j = e - r * half;
+  const float arg = __fmul_rn(ts[r], freq[j]);
+  out[(size_t)r * ldo + j] = sinf(arg);
+  out[(size_t)r * ldo + half + j] = cosf(arg);
+}
+
+}  // namespace slide
+
+using namespace slide;
+
+// =====================================================================================================
+// program object
+// =====================================================================================================
+struct slide_program {
+  std::vector<slide_op> ops;
+  char *arena = nullptr;
+  char *weights = nullptr;
+  size_t arena_bytes = 0, weights_bytes = 0;
+  cudaGraphExec_t graphs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int graph_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int gemm_backend = 0;  // 0 = auto (tcgen05 where eligible), 1 = fp32 FFMA everywhere
+};
+
+namespace {
+
+template <typename T>
+inline T *AP(slide_program *p, int64_t off) {
+  return off < 0 ? nullptr : reinterpret_cast<T *>(p->arena + off);
+}
+template <typename T>
+inline const T *WP(slide_program *p, int64_t off) {
+  return off < 0 ? nullptr : reinterpret_cast<const T *>(p->weights + off);
+}
+
+inline unsigned grid_for(long long n, int threads) {
+  long long g = (n + threads - 1) / threads;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+XFd make_xf(slide_program *p, const int64_t *f) {
+  XFd x;
+  x.stats = AP<double>(p, f[XF_STATS]);
+  x.cg = (int)f[XF_CG];
+  x.nnorm = (int)f[XF_NNORM];
+  x.choff = (int)f[XF_CHOFF];
+  x.gamma = WP<float>(p, f[XF_GAMMA_W]);
+  x.beta = WP<float>(p, f[XF_BETA_W]);
+  x.R = (int)f[XF_R];
+  x.inv_count = f[XF_COUNT] > 0 ? 1.0f / (float)f[XF_COUNT] : 1.0f;
+  x.relu = (int)f[XF_RELU];
+  x.addvec = AP<float>(p, f[XF_ADDVEC]);
+  x.addld = (int)f[XF_ADDLD];
+  x.addmode = (int)f[XF_ADDMODE];
+  return x;
+}
+
+int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
+  const int64_t *q = op.p;
+  switch (op.kind) {
+    case SLIDE_OP_NOP:
+      return SLIDE_OK;
+    case SLIDE_OP_STEP_BEGIN: {
+      const size_t n16 = (size_t)q[SB_ZERO_BYTES] / 16;
+      unsigned g = grid_for((long long)n16, 256);
+      if (g > 1184) g = 1184;
+      step_begin_kernel<<<g, 256, 0, st>>>(AP<uint4>(p, q[SB_ZERO_OFF]), n16, AP<int>(p, q[SB_STEP]));
+      return after_launch();
+    }
+    case SLIDE_OP_KNN: {
+      const int B = (int)q[KNN_B], P1 = (int)q[KNN_P1], P2 = (int)q[KNN_P2], K = (int)q[KNN_K];
+      if (K > 32 || K > P2 || B > 65535) return SLIDE_ERR_UNSUPPORTED;
+      const int threads = P1 >= 128 ? 128 : ((P1 + 31) / 32) * 32;
+      dim3 grid(ceil_div(P1, threads), B);
+      const float *qq = AP<float>(p, q[KNN_Q]), *rr = AP<float>(p, q[KNN_REF]);
+      int *idx = AP<int>(p, q[KNN_IDX]);
+      float *d2 = AP<float>(p, q[KNN_D2]);
+      const int ldq = (int)q[KNN_LDQ], ldr = (int)q[KNN_LDR];
+      if (K <= 4)
+        knn_prog_kernel<4><<<grid, threads, 0, st>>>(qq, ldq, P1, rr, ldr, P2, K, idx, d2);
+      else if (K <= 8)
+        knn_prog_kernel<8><<<grid, threads, 0, st>>>(qq, ldq, P1, rr, ldr, P2, K, idx, d2);
+      else if (K <= 16)
+        knn_prog_kernel<16><<<grid, threads, 0, st>>>(qq, ldq, P1, rr, ldr, P2, K, idx, d2);
+      else
+        knn_prog_kernel<32><<<grid, threads, 0, st>>>(qq, ldq, P1, rr, ldr, P2, K, idx, d2);
+      return after_launch();
+    }
+    case SLIDE_OP_GROUP: {
+      const long long rows = (long long)q[GRP_B] * q[GRP_NP] * q[GRP_K];
+      unsigned g = grid_for(rows * 32, 256);
+      if (g > 148 * 16) g = 148 * 16;
+      group_kernel<<<g, 256, 0, st>>>((int)q[GRP_MODE], AP<float>(p, q[GRP_F]), (int)q[GRP_LDF], (int)q[GRP_C],
+                                      AP<float>(p, q[GRP_XYZ]), (int)q[GRP_LDX], (int)q[GRP_N],
+                                      AP<float>(p, q[GRP_CTR]), (int)q[GRP_LDCTR], (int)q[GRP_NP],
+                                      AP<int>(p, q[GRP_IDX]), (int)q[GRP_K], AP<float>(p, q[GRP_D2]),
+                                      AP<float>(p, q[GRP_OUT]), (int)q[GRP_LDO], (int)q[GRP_ABS],
+                                      (int)q[GRP_CENTER], rows);
+      return after_launch();
+    }
+    case SLIDE_OP_GEMM: {
+      GemmArgs a;
+      a.A = AP<float>(p, q[GEMM_A]);
+      a.lda = (int)q[GEMM_LDA];
+      a.M = (int)q[GEMM_M];
+      a.K = (int)q[GEMM_K];
+      a.W = WP<float>(p, q[GEMM_W_W]);
+      a.ldw = (int)q[GEMM_LDW];
+      a.N = (int)q[GEMM_N];
+      a.C = AP<float>(p, q[GEMM_C]);
+      a.ldc = (int)q[GEMM_LDC];
+      a.bias = WP<float>(p, q[GEMM_BIAS_W]);
+      a.act = (int)q[GEMM_ACT];
+      a.ev = AP<float>(p, q[GEMM_EV]);
+      a.evld = (int)q[GEMM_EVLD];
+      a.evdiv = (int)q[GEMM_EVDIV] > 0 ? (int)q[GEMM_EVDIV] : 1;
+      a.res = AP<float>(p, q[GEMM_RES]);
+      a.ldr = (int)q[GEMM_LDR];
+      a.st_stats = AP<double>(p, q[GEMM_ST_STATS]);
+      a.st_cg = (int)q[GEMM_ST_CG] > 0 ? (int)q[GEMM_ST_CG] : 1;
+      a.st_nnorm = (int)q[GEMM_ST_NNORM];
+      a.st_choff = (int)q[GEMM_ST_CHOFF];
+      a.st_R = (int)q[GEMM_ST_R] > 0 ? (int)q[GEMM_ST_R] : 1;
+      a.st_weight = (float)q[GEMM_ST_WEIGHT];
+      a.xfa = make_xf(p, q + GEMM_XFA);
+      a.xfr = make_xf(p, q + GEMM_XFR);
+      a.step = AP<int>(p, q[GEMM_STEP]);
+      if (p->gemm_backend == 0 && gemm_tc_eligible(a)) return launch_gemm_tc(a, st);
+      return launch_gemm_simt(a, st);
+    }
+    case SLIDE_OP_SOFTMAX_WSUM: {
+      const long long rows = q[SM_ROWS];
+      const int C = (int)q[SM_C];
+      softmax_wsum_kernel<<<grid_for(rows * C, 256), 256, 0, st>>>(
+          AP<float>(p, q[SM_S]), (int)q[SM_LDS], AP<float>(p, q[SM_V]), (int)q[SM_LDV], make_xf(p, q + SM_XFV),
+          AP<int>(p, q[SM_STEP]), AP<float>(p, q[SM_OUT]), (int)q[SM_LDO], rows, (int)q[SM_K], C);
+      return after_launch();
+    }
+    case SLIDE_OP_COPY_COLS: {
+      const long long rows = q[CP_ROWS];
+      const int n = (int)q[CP_NCOLS];
+      copy_cols_kernel<<<grid_for(rows * n, 256), 256, 0, st>>>(AP<float>(p, q[CP_SRC]), (int)q[CP_LDS],
+                                                               AP<float>(p, q[CP_DST]), (int)q[CP_LDD], rows, n);
+      return after_launch();
+    }
+    case SLIDE_OP_DDPM_UPDATE: {
+      const long long rows = q[DD_ROWS];
+      const int n = (int)q[DD_NCOLS];
+      ddpm_update_kernel<<<grid_for(rows * n, 256), 256, 0, st>>>(
+          (int)q[DD_MODE], AP<float>(p, q[DD_X]), (int)q[DD_LDX], AP<float>(p, q[DD_EPS]), (int)q[DD_LDE],
+          AP<float>(p, q[DD_NOISE]), rows, n, (int)q[DD_COL0], WP<float>(p, q[DD_TABLE_W]), AP<int>(p, q[DD_STEP]),
+          op.f[0]);
+      return after_launch();
+    }
+    case SLIDE_OP_FPS:
+      return program_fps((int)q[FPS_MODE], AP<float>(p, q[FPS_XYZ]), (int)q[FPS_LDX], (int)q[FPS_B], (int)q[FPS_N],
+                         (int)q[FPS_M], AP<int>(p, q[FPS_START]), AP<int>(p, q[FPS_OUT]), st);
+    case SLIDE_OP_GATHER_ROWS: {
+      const long long total = (long long)q[GA_B] * q[GA_M];
+      const int n = (int)q[GA_NCOLS];
+      gather_rows_kernel<<<grid_for(total * n, 256), 256, 0, st>>>(AP<float>(p, q[GA_SRC]), (int)q[GA_LDS],
+                                                                  (int)q[GA_N], AP<int>(p, q[GA_IDX]), (int)q[GA_M],
+                                                                  AP<float>(p, q[GA_DST]), (int)q[GA_LDD], n, total);
+      return after_launch();
+    }
+    case SLIDE_OP_UPSAMPLE: {
+      const long long rows = q[UP_ROWS];
+      const int factor = (int)q[UP_FACTOR], Fd = (int)q[UP_F];
+      upsample_kernel<<<grid_for(rows * factor * Fd, 256), 256, 0, st>>>(
+          AP<float>(p, q[UP_COARSE]), (int)q[UP_LDC], (int)q[UP_COARSE_C], AP<float>(p, q[UP_DISP]), (int)q[UP_LDD],
+          AP<float>(p, q[UP_OUT]), (int)q[UP_LDO], rows, factor, Fd, op.f[0], op.f[1]);
+      return after_launch();
+    }
+    case SLIDE_OP_TEMB: {
+      const int rows = (int)q[TE_ROWS], half = (int)q[TE_HALF];
+      temb_kernel<<<grid_for((long long)rows * half, 256), 256, 0, st>>>(
+          AP<float>(p, q[TE_TS]), WP<float>(p, q[TE_FREQ_W]), half, AP<float>(p, q[TE_OUT]), (int)q[TE_LDO], rows);
+      return after_launch();
+    }
+    default:
+      return SLIDE_ERR_INVALID;
+  }
+}
+
+int run_range(slide_program *p, int first, int count, cudaStream_t st) {
+  if (!p || first < 0 || count < 0 || (size_t)(first + count) > p->ops.size()) return SLIDE_ERR_INVALID;
+  for (int i = first; i < first + count; ++i) {
+    const int rc = run_op(p, p->ops[i], st);
+    if (rc != SLIDE_OK) return rc;
+  }
+  return SLIDE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int slide_program_create(const struct slide_op *ops, int n_ops, size_t arena_bytes, const void *weights,
+                         size_t weights_bytes, slide_program **out) {
+  if (!ops || n_ops < 0 || !out) return SLIDE_ERR_INVALID;
+  slide_program *p = new slide_program();
+  p->ops.assign(ops, ops + n_ops);
+  p->arena_bytes = arena_bytes;
+  p->weights_bytes = weights_bytes;
+  const char *be = getenv("SLIDE_GEMM_BACKEND");
+  if (be && strcmp(be, "simt") == 0) p->gemm_backend = 1;
+  int rc = cuda_rc(cudaMalloc((void **)&p->arena, arena_bytes > 0 ? arena_bytes : 256));
+  if (rc == SLIDE_OK) rc = cuda_rc(cudaMemset(p->arena, 0, arena_bytes));
+  if (rc == SLIDE_OK) rc = cuda_rc(cudaMalloc((void **)&p->weights, weights_bytes > 0 ? weights_bytes : 256));
+  if (rc == SLIDE_OK && weights && weights_bytes)
+    rc = cuda_rc(cudaMemcpy(p->weights, weights, weights_bytes, cudaMemcpyHostToDevice));
+  if (rc != SLIDE_OK) {
+    slide_program_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return SLIDE_OK;
+}
+
+void slide_program_destroy(slide_program *p) {
+  if (!p) return;
+  for (int i = 0; i < 8; ++i)
+    if (p->graphs[i]) cudaGraphExecDestroy(p->graphs[i]);
+  if (p->arena) cudaFree(p->arena);
+  if (p->weights) cudaFree(p->weights);
+  delete p;
+}
+
+void *slide_program_arena(slide_program *p) { return p ? p->arena : nullptr; }
+void *slide_program_weights(slide_program *p) { return p ? p->weights : nullptr; }
+
+int slide_program_set_gemm_backend(slide_program *p, int backend) {
+  if (!p || backend < 0 || backend > 1) return SLIDE_ERR_INVALID;
+  p->gemm_backend = backend;
+  return SLIDE_OK;
+}
+
+int slide_program_run(slide_program *p, int first, int count, slide_stream_t stream) {
+  return run_range(p, first, count, (cudaStream_t)stream);
+}
+
+int slide_program_capture(slide_program *p, int slot, int first, int count, int repeat, slide_stream_t stream) {
+  if (!p || slot < 0 || slot >= 8 || repeat < 1) return SLIDE_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->graphs[slot]) {
+    cudaGraphExecDestroy(p->graphs[slot]);
+    p->graphs[slot] = nullptr;
+  }
+  const long long before = g_launch_count;
+  int rc = cuda_rc(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  if (rc != SLIDE_OK) return rc;
+  int run_rc = SLIDE_OK;
+  for (int r = 0; r < repeat && run_rc == SLIDE_OK; ++r) run_rc = run_range(p, first, count, st);
+  cudaGraph_t graph = nullptr;
+  rc = cuda_rc(cudaStreamEndCapture(st, &graph));
+  p->graph_launches[slot] = (int)(g_launch_count - before);
+  g_launch_count = before;  // captured, not launched
+  if (run_rc != SLIDE_OK || rc != SLIDE_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return run_rc != SLIDE_OK ? run_rc : rc;
+  }
+  rc = cuda_rc(cudaGraphInstantiate(&p->graphs[slot], graph, 0));
+  cudaGraphDestroy(graph);
+  return rc;
+}
+
+int slide_program_replay(slide_program *p, int slot, int times, slide_stream_t stream) {
+  if (!p || slot < 0 || slot >= 8 || !p->graphs[slot] || times < 0) return SLIDE_ERR_INVALID;
+  for (int i = 0; i < times; ++i) {
+    const int rc = cuda_rc(cudaGraphLaunch(p->graphs[slot], (cudaStream_t)stream));
+    if (rc != SLIDE_OK) return rc;
+    g_launch_count += p->graph_launches[slot];
+  }
+  return SLIDE_OK;
+}
+
+int slide_tc_error(void) { return tc_error_flag(); }
+
+int slide_program_launches(slide_program *p, int first, int count) {
+  if (!p || first < 0 || count < 0 || (size_t)(first + count) > p->ops.size()) return SLIDE_ERR_INVALID;
+  int n = 0;
+  for (int i = first; i < first + count; ++i)
+    if (p->ops[i].kind != SLIDE_OP_NOP) ++n;
+  return n;
+}
+
+}  // extern "C"

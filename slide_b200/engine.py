@@ -1,0 +1,126 @@
+"""Program assembly for the sampling path: DDPM loops (position / latent) and the autoencoder decode.
+
+build_* functions only need numpy (they return a Builder plus named handles) so that tests can interpret the
+records on CPU; the *Sampler classes run them on the GPU through slide_b200.program.Program.
+
+Reference behaviour reproduced here:
+  position DDPM   pointnet2/util.py:167-259 (calc_diffusion_hyperparams, sampling)
+  latent DDPM     pointnet2/diffusion_utils/diffusion.py:12-39,58-95,158-208,346-404
+  decode          pointnet2/models/autoencoder.py:42-45
+"""
+import numpy as np
+
+from . import nets
+from .program import Builder
+
+
+# ---------------------------------------------------------------------------------------------------
+# schedules -> per-timestep coefficient tables (fp32 [T, 8])
+# ---------------------------------------------------------------------------------------------------
+def position_table(T, beta_0, beta_T):
+    """util.calc_diffusion_hyperparams in fp32 torch (sequential in-place products, util.py:182-189) and the
+    scalars sampling() derives from it (util.py:247-253): [k1 = (1-a)/sqrt(1-abar), sqrt(a), sigma]."""
+    import torch
+    Beta = torch.linspace(beta_0, beta_T, T)
+    Alpha = 1 - Beta
+    Alpha_bar = Alpha + 0
+    Beta_tilde = Beta + 0
+    for t in range(1, T):
+        Alpha_bar[t] *= Alpha_bar[t - 1]
+        Beta_tilde[t] *= (1 - Alpha_bar[t - 1]) / (1 - Alpha_bar[t])
+    Sigma = torch.sqrt(Beta_tilde)
+    tab = torch.zeros(T, 8)
+    for t in range(T):
+        tab[t, 0] = (1 - Alpha[t]) / torch.sqrt(1 - Alpha_bar[t])
+        tab[t, 1] = torch.sqrt(Alpha[t])
+        tab[t, 2] = Sigma[t]
+    return tab.numpy()
+
+
+def latent_table(dcfg):
+    """Diffusion.init_diffusion_parameters (float64 numpy, diffusion.py:158-208) then the fp32 casts of
+    extract() (diffusion.py:31-39) and exp(0.5*logvar) evaluated in fp32 like denoising_step (:88-92):
+    [sqrt_recip_acp, sqrt_recipm1_acp, post_mean_coef1, post_mean_coef2, exp(0.5*logvar)]."""
+    import torch
+    if dcfg["beta_schedule"] != "linear" or dcfg.get("model_var_type", "fixedsmall") != "fixedsmall":
+        raise NotImplementedError("only the linear / fixedsmall schedule of the shipped configs")
+    T = dcfg["num_diffusion_timesteps"]
+    betas = np.linspace(dcfg["beta_start"], dcfg["beta_end"], T, dtype=np.float64)
+    alphas = 1.0 - betas
+    acp = np.cumprod(alphas, axis=0)
+    acp_prev = np.append(1.0, acp[:-1])
+    post_var = betas * (1.0 - acp_prev) / (1.0 - acp)
+    logvar = np.log(np.maximum(post_var, 1e-20))
+    tab = torch.zeros(T, 8)
+    tab[:, 0] = torch.tensor(np.sqrt(1.0 / acp)).float()
+    tab[:, 1] = torch.tensor(np.sqrt(1.0 / acp - 1)).float()
+    tab[:, 2] = torch.tensor(betas * np.sqrt(acp_prev) / (1.0 - acp)).float()
+    tab[:, 3] = torch.tensor((1.0 - acp_prev) * np.sqrt(alphas) / (1.0 - acp)).float()
+    tab[:, 4] = torch.exp(0.5 * torch.tensor(logvar).float())
+    return tab.numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# builders
+# ---------------------------------------------------------------------------------------------------
+def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0, with_noise=True):
+    """One program = setup segment + step segment (+ forward-only segment) for a DDPM denoiser.
+
+    mode 0: position sampler (util.sampling), mode 1: latent sampler (denoising_step).
+    keep_cols: leading columns of x the update must not touch (3 for keypoint-conditional sampling).
+    Handles: x, eps, labels, noise [T*B*n, C], ts_table, class_emb.
+    """
+    b = Builder(B)
+    C = 3 + cfg["in_fea_dim"]
+    assert cfg["out_dim"] == C
+    X = b.tensor("x", n_points, C)
+    labels = b.tensor("labels", 1, B, B=1, dtype="i32")
+    noise = b.tensor("noise", T * B * n_points if with_noise else 1, C, B=1, ld=C)
+    table_off = b.weight(np.asarray(table, dtype=np.float32).reshape(T, 8))
+    P = nets.Params(sd)
+    b.begin_segment("step")
+    b.step_begin()
+    net = nets.lower_cloud_net(b, P, cfg, X, n_points, "net", T=T, labels=labels)
+    fwd_count = len(b.ops) - b._seg_open[1]
+    b.ddpm_update(mode, X, net["out"], noise, table_off, col0=keep_cols, clamp=clamp, note="ddpm_update")
+    b.end_segment()
+    first = b.segments["step"][0]
+    b.segments["forward"] = (first, fwd_count)
+    b.begin_segment("setup")
+    net["emit_setup"]()
+    b.end_segment()
+    h = dict(x=X, eps=net["out"], labels=labels, noise=noise, T=T, C=C, n_points=n_points)
+    h.update(net["inputs"])
+    return b, h
+
+
+def build_decode(decoder_cfgs, sd, B):
+    b = Builder(B)
+    kp = b.tensor("keypoint", 16, 3)
+    fdim = decoder_cfgs[1]["feature_mapper_setting"]  # noqa: F841  (documented: level-1 features feed level 2)
+    P = nets.Params(sd)
+    Fdim = sd["keypoint_encoder.fc_layer.weight"].shape[1] - 3
+    feat = b.tensor("feature", 16, Fdim)
+    labels = b.tensor("labels", 1, B, B=1, dtype="i32")
+    b.begin_segment("decode")
+    b.step_begin()
+    dec = nets.lower_decode(b, P, decoder_cfgs, kp, feat, labels)
+    b.end_segment()
+    b.begin_segment("setup")
+    dec["emit_setup"]()
+    b.end_segment()
+    h = dict(keypoint=kp, feature=feat, labels=labels, out=dec["out"], starts=dec["starts"],
+             class_tables=dec["class_tables"], levels=dec["levels"])
+    return b, h
+
+
+def init_constants(machine, h):
+    """Upload the constants a freshly created program needs before its setup segment runs: the timestep list
+    0..T-1 and the class-embedding table(s).  `machine` is a Program or the CPU interpreter (same interface)."""
+    if "ts_table" in h:
+        machine.upload(h["ts_table"], np.arange(h["T"], dtype=np.float32))
+    if "class_emb" in h:
+        t, w = h["class_emb"]
+        machine.upload(t, w)
+    for t, w in h.get("class_tables", []):
+        machine.upload(t, w)

@@ -22,6 +22,7 @@ SYMBOLS = [
     "slide_three_interpolate_grad", "slide_knn_points", "slide_sample_farthest_points",
     "slide_program_create", "slide_program_destroy", "slide_program_arena", "slide_program_weights",
     "slide_program_run", "slide_program_capture", "slide_program_replay", "slide_program_launches",
+    "slide_program_set_gemm_backend", "slide_tc_error",
 ]
 
 
@@ -46,6 +47,14 @@ def load():
         lib.slide_program_weights.argtypes = [ctypes.c_void_p]
         lib.slide_program_destroy.argtypes = [ctypes.c_void_p]
         lib.slide_program_destroy.restype = None
+        lib.slide_program_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p,
+                                             ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        lib.slide_program_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        lib.slide_program_capture.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_void_p]
+        lib.slide_program_replay.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        lib.slide_program_launches.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        lib.slide_program_set_gemm_backend.argtypes = [ctypes.c_void_p, ctypes.c_int]
         _lib = lib
     return _lib
 

@@ -1,0 +1,429 @@
+"""Lowering of the reference's networks to slide programs (records of include/slide_program.h).
+
+Everything here is driven by the reference's own JSON hyper-parameters and state-dict key names
+(checkpoint ABI), so a reference checkpoint lowers unchanged:
+
+  lower_cloud_net        PointNet2CloudCondition.forward without a condition cloud
+                         (pointnet2/models/pointnet2_with_pcld_condition.py:286-489): the position / feature
+                         DDPM denoisers and the decoder levels' feature extractors
+  _lower_mlp             Mlp_plus_t_emb (pointnet2_ops_lib/pointnet2_ops/pointnet2_modules.py:72-176)
+  _lower_attention       AttentionModule (pointnet2_ops_lib/pointnet2_ops/attention.py:35-96)
+  _lower_sa / _lower_fp  PointnetSAModule / PointnetKnnFPModule forward (pointnet2_modules.py:222-292, 771-873)
+  _lower_feature_map     FeatureMapModule forward (pointnet2_modules.py:640-663)
+  lower_decode           PointAutoencoder.decode (pointnet2/models/autoencoder.py:42-45,
+                         point_upsample_decoder.py:106-190, keypoint_decoder.py:25-36)
+
+Algebra used (exact in real arithmetic, fp32 re-association only):
+  * GroupNorm statistics are produced by the GEMM that writes a tensor and applied by its consumers (XF).
+  * AttentionModule's conv over cat[q_i broadcast over K, k_ij] is split into a per-point GEMM on q (np rows)
+    plus a per-pair GEMM on k (np*K rows): W[q;k] = Wq q + Wk k.  GroupNorm over the concatenation still
+    uses the joint statistics (the q rows enter them with weight K).
+"""
+import numpy as np
+
+from .program import XF, NO_XF, Builder  # noqa: F401
+
+
+def _np(x):
+    if hasattr(x, "detach"):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x, dtype=np.float32)
+
+
+class Params(object):
+    """Prefix view over a state dict (values: torch tensors or numpy arrays)."""
+
+    def __init__(self, sd, prefix=""):
+        self.sd, self.prefix = sd, prefix
+
+    def __getitem__(self, key):
+        return _np(self.sd[self.prefix + key])
+
+    def has(self, key):
+        return (self.prefix + key) in self.sd
+
+    def sub(self, name):
+        return Params(self.sd, self.prefix + name + ".")
+
+
+def _gn_dims(C):
+    """MyGroupNorm(min(32, C), C): (normalised channels, channels per group)."""
+    G = min(32, C)
+    nnorm = C - C % G
+    return nnorm, nnorm // G
+
+
+def _conv(b, P, cols=None):
+    """Conv2d/Conv1d 1x1 (or Linear) weight -> (W tuple for Builder.gemm, bias offset)."""
+    w = P["weight"]
+    w = w.reshape(w.shape[0], -1)
+    if cols is not None:
+        w = w[:, cols[0]:cols[1]]
+    off, ldw = b.weight_matrix(w)
+    bias = b.weight(P["bias"]) if P.has("bias") else -1
+    return (off, ldw, w.shape[0], w.shape[1]), bias
+
+
+class _Ctx(object):
+    """Per-network lowering context: timestep-table / condition sources and activation name."""
+
+    def __init__(self, b, cfg, t_src=None, cond_src=None):
+        self.b, self.cfg = b, cfg
+        self.t_src = t_src        # Tensor [T, 4*t_dim] (swish'ed timestep embeddings for every t) or None
+        self.cond_src = cond_src  # Tensor [B, class_condition_dim] or None
+        self.setup = []           # deferred setup GEMMs (emitted into the setup segment)
+        act = cfg.get("activation", "relu")
+        if act != "relu":
+            raise NotImplementedError("activation %r (shipped configs use relu)" % act)
+        if cfg["bn_first"] or not cfg.get("bn", True) or not cfg["res_connect"]:
+            raise NotImplementedError("bn_first / bn=False / res_connect=False are not lowered")
+
+
+def _lower_mlp(ctx, P, G, R, name, out=None, use_t=False, use_cond=False):
+    """Mlp_plus_t_emb with bn_first=False, res_connect=True.  G: input [B*R, Cin].  Returns H [B*R, Cout]."""
+    b = ctx.b
+    if P.has("first_conv.weight") or P.has("fc_second_condition.weight"):
+        raise NotImplementedError("first_conv / second condition")
+    stages = [("first_mlp.0", "first_mlp.1"), ("second_mlp.0", "second_mlp.1")]
+    j = 0
+    while P.has("rest_mlp.%d.weight" % (3 * j)):
+        stages.append(("rest_mlp.%d" % (3 * j), "rest_mlp.%d" % (3 * j + 1)))
+        j += 1
+    prev, xf_prev = G, NO_XF
+    for si, (ck, gk) in enumerate(stages):
+        W, bias = _conv(b, P.sub(ck))
+        N = W[2]
+        nnorm, cg = _gn_dims(N)
+        assert P[gk + ".group_norm.weight"].shape[0] == nnorm
+        raw = b.tensor("%s.raw%d" % (name, si), R, N, B=G.B)
+        st = b.stats("%s.st%d" % (name, si), nnorm, cg, R, R * cg, B=G.B)
+        b.gemm(prev, W, raw, bias=bias, xfa=xf_prev, stats=st, note="%s.conv%d" % (name, si))
+        addvec, addmode = None, 0
+        if si == 0 and P.has("fc.weight"):
+            assert use_t and ctx.t_src is not None, "module has a timestep projection but no timestep source"
+            Wt, bt = _conv(b, P.sub("fc"))
+            addvec = b.tensor("%s.ttab" % name, ctx.t_src.rows, N, B=1)
+            ctx.setup.append(dict(A=ctx.t_src, W=Wt, out=addvec, bias=bt, note="%s.fc(t)" % name))
+            addmode = 1
+        if si == 1 and P.has("fc_condition.weight"):
+            assert use_cond and ctx.cond_src is not None, "module has a condition projection but no condition"
+            Wc, bc = _conv(b, P.sub("fc_condition"))
+            addvec = b.tensor("%s.cvec" % name, 1, N, B=G.B)
+            ctx.setup.append(dict(A=ctx.cond_src, W=Wc, out=addvec, bias=bc, note="%s.fc_condition" % name))
+            addmode = 0
+        xf_prev = XF(stats=st.tensor, cg=cg, nnorm=nnorm, choff=0, gamma=b.weight(P[gk + ".group_norm.weight"]),
+                     beta=b.weight(P[gk + ".group_norm.bias"]), R=R, count=R * cg, relu=True, addvec=addvec,
+                     addmode=addmode)
+        prev = raw
+    N = prev.C
+    if out is None:
+        out = b.tensor("%s.out" % name, R, N, B=G.B)
+    if P.has("res_connect.weight"):
+        Wr, br = _conv(b, P.sub("res_connect"))
+        b.gemm(G, Wr, out, bias=br, resid=prev, xfr=xf_prev, note="%s.res" % name)
+    else:
+        raise NotImplementedError("identity residual (mlp_spec[0] == mlp_spec[-1])")
+    return out
+
+
+def _lower_attention(ctx, P, q_feat, G, H, npnt, K, out, name):
+    """AttentionModule(attention_bn=True, transform_grouped_feat_out=True); counts == K ('nn' neighbours)."""
+    b = ctx.b
+    att = ctx.cfg["attention_setting"]
+    assert att["attention_bn"] and att["transform_grouped_feat_out"]
+    B = G.B
+    Wq, bq = _conv(b, P.sub("feat_conv"))
+    Wk, bk = _conv(b, P.sub("grouped_feat_conv"))
+    C1, C2 = Wq[2], Wk[2]
+    nn1, cg1 = _gn_dims(C1 + C2)
+    st1 = b.stats(name + ".st_cat", nn1, cg1, npnt * K, npnt * K * cg1, B=B)
+    q = b.tensor(name + ".q", npnt, C1, B=B)
+    k = b.tensor(name + ".k", npnt * K, C2, B=B)
+    b.gemm(q_feat, Wq, q, bias=bq, act="relu", stats=st1, st_R=npnt, st_choff=0, st_weight=K, note=name + ".q")
+    b.gemm(G, Wk, k, bias=bk, act="relu", stats=st1, st_R=npnt * K, st_choff=C1, note=name + ".k")
+    g1 = b.weight(P["weight_conv.1.group_norm.weight"])
+    be1 = b.weight(P["weight_conv.1.group_norm.bias"])
+    W1q, _ = _conv(b, P.sub("weight_conv.2"), cols=(0, C1))
+    W1k, b1 = _conv(b, P.sub("weight_conv.2"), cols=(C1, C1 + C2))
+    inter = W1q[2]
+    qp = b.tensor(name + ".qp", npnt, inter, B=B)
+    b.gemm(q, W1q, qp, xfa=XF(stats=st1.tensor, cg=cg1, nnorm=nn1, choff=0, gamma=g1, beta=be1, R=npnt,
+                              count=npnt * K * cg1), note=name + ".w1q")
+    nn2, cg2 = _gn_dims(inter)
+    st2 = b.stats(name + ".st_s1", nn2, cg2, npnt * K, npnt * K * cg2, B=B)
+    s1 = b.tensor(name + ".s1", npnt * K, inter, B=B)
+    b.gemm(k, W1k, s1, bias=b1, act="relu", ev=qp, ev_div=K, stats=st2, st_R=npnt * K,
+           xfa=XF(stats=st1.tensor, cg=cg1, nnorm=nn1, choff=C1, gamma=g1, beta=be1, R=npnt * K,
+                  count=npnt * K * cg1), note=name + ".w1k")
+    W2, b2 = _conv(b, P.sub("weight_conv.5"))
+    Co = W2[2]
+    scores = b.tensor(name + ".scores", npnt * K, Co, B=B)
+    b.gemm(s1, W2, scores, bias=b2,
+           xfa=XF(stats=st2.tensor, cg=cg2, nnorm=nn2, choff=0, gamma=b.weight(P["weight_conv.4.group_norm.weight"]),
+                  beta=b.weight(P["weight_conv.4.group_norm.bias"]), R=npnt * K, count=npnt * K * cg2),
+           note=name + ".w2")
+    Wv, bv = _conv(b, P.sub("feat_out_conv.0"))
+    v = b.tensor(name + ".v", npnt * K, Co, B=B)
+    if att["last_activation"]:
+        nn3, cg3 = _gn_dims(Co)
+        st3 = b.stats(name + ".st_v", nn3, cg3, npnt * K, npnt * K * cg3, B=B)
+        b.gemm(H, Wv, v, bias=bv, stats=st3, st_R=npnt * K, note=name + ".v")
+        xfv = XF(stats=st3.tensor, cg=cg3, nnorm=nn3, choff=0, gamma=b.weight(P["feat_out_conv.1.group_norm.weight"]),
+                 beta=b.weight(P["feat_out_conv.1.group_norm.bias"]), R=npnt * K, count=npnt * K * cg3, relu=True)
+    else:
+        b.gemm(H, Wv, v, bias=bv, note=name + ".v")
+        xfv = NO_XF
+    assert out.C == Co
+    b.softmax_wsum(scores, v, xfv, out, B * npnt, K, note=name + ".softmax")
+    return out
+
+
+def _lower_sa(ctx, P, xyz, feats, npoint, nsample, name):
+    """-> (new_xyz [B*np,3], features [B*np,Cout])."""
+    b, cfg = ctx.b, ctx.cfg
+    N, B = xyz.R, xyz.B
+    if N <= npoint:
+        new_xyz, q_feat, npnt = xyz, feats, N
+    else:
+        npnt = npoint
+        pick = b.tensor(name + ".fps", 1, npnt, B=B, dtype="i32")
+        b.fps(0, xyz, npnt, pick, note=name + ".fps")
+        new_xyz = b.tensor(name + ".new_xyz", npnt, 3, B=B)
+        b.gather_rows(xyz, pick, npnt, new_xyz, note=name + ".gather_xyz")
+        q_feat = b.tensor(name + ".qfeat", npnt, feats.C, B=B)
+        b.gather_rows(feats, pick, npnt, q_feat, note=name + ".gather_feat")
+    K = min(nsample, N)
+    idx = b.tensor(name + ".idx", npnt, K, B=B, dtype="i32")
+    b.knn(new_xyz, xyz, K, idx, note=name + ".knn")
+    inc_abs, inc_ctr = cfg["include_abs_coordinate"], cfg.get("include_center_coordinate", False)
+    assert cfg["model.use_xyz"]
+    Cg = feats.C + 3 + 3 * int(inc_abs) + 3 * int(inc_ctr)
+    G = b.tensor(name + ".grouped", npnt * K, Cg, B=B)
+    b.group(0, feats, feats.C, xyz, new_xyz, idx, K, G, include_abs=inc_abs, include_center=inc_ctr,
+            note=name + ".group")
+    H = _lower_mlp(ctx, P.sub("mlps.0"), G, npnt * K, name + ".mlp", use_t=True, use_cond=True)
+    out = b.tensor(name + ".out", npnt, H.C, B=B)
+    _lower_attention(ctx, P.sub("attention_modules.0"), q_feat, G, H, npnt, K, out, name + ".att")
+    return new_xyz, out
+
+
+def _lower_fp(ctx, P, unknown, known, unknow_feats, known_feats, K, name, out=None):
+    b = ctx.b
+    n, B = unknown.R, unknown.B
+    idx = b.tensor(name + ".idx", n, K, B=B, dtype="i32")
+    d2 = b.tensor(name + ".d2", n, K, B=B)
+    b.knn(unknown, known, K, idx, d2=d2, note=name + ".knn")
+    G = b.tensor(name + ".grouped", n * K, known_feats.C + 11, B=B)
+    b.group(1, known_feats, known_feats.C, known, unknown, idx, K, G, d2=d2, note=name + ".group")
+    H1 = _lower_mlp(ctx, P.sub("mlp1"), G, n * K, name + ".mlp1")
+    d = H1.C
+    cat = b.tensor(name + ".cat", n, d + unknow_feats.C + 3, B=B)
+    _lower_attention(ctx, P.sub("attention_module"), unknow_feats, G, H1, n, K, cat.cols(0, d), name + ".att")
+    b.copy_cols(unknow_feats, cat.cols(d, unknow_feats.C), note=name + ".cat_skip")
+    b.copy_cols(unknown.cols(0, 3), cat.cols(d + unknow_feats.C, 3), note=name + ".cat_xyz")
+    return _lower_mlp(ctx, P.sub("mlp2"), cat, n, name + ".mlp2", out=out, use_t=True, use_cond=True)
+
+
+def _lower_feature_map(ctx, P, xyz, feats, new_xyz, q_feat, nsample, name, out):
+    b, cfg = ctx.b, ctx.cfg
+    npnt, B = new_xyz.R, new_xyz.B
+    K = min(nsample, xyz.R)
+    idx = b.tensor(name + ".idx", npnt, K, B=B, dtype="i32")
+    b.knn(new_xyz, xyz, K, idx, note=name + ".knn")
+    inc_abs, inc_ctr = cfg["include_abs_coordinate"], cfg.get("include_center_coordinate", False)
+    Cg = feats.C + 3 + 3 * int(inc_abs) + 3 * int(inc_ctr)
+    G = b.tensor(name + ".grouped", npnt * K, Cg, B=B)
+    b.group(0, feats, feats.C, xyz, new_xyz, idx, K, G, include_abs=inc_abs, include_center=inc_ctr,
+            note=name + ".group")
+    H = _lower_mlp(ctx, P.sub("mlp"), G, npnt * K, name + ".mlp")
+    return _lower_attention(ctx, P.sub("attention_module"), q_feat, G, H, npnt, K, out, name + ".att")
+
+
+def t_embedding_source(b, P, cfg, T, name):
+    """Timestep-embedding table for t = 0..T-1: swish(fc_t2(swish(fc_t1(calc_t_emb(t))))) -> [T, 4*t_dim].
+    Returns (tensor, emit) where emit() appends the ops (setup segment).  calc_t_emb:
+    pointnet2/models/pointnet2_ssg_sem.py:14-31; fc_t1/fc_t2: pointnet2_with_pcld_condition.py:354-359."""
+    t_dim = cfg["t_dim"]
+    half = t_dim // 2
+    import torch
+    freq = torch.exp(torch.arange(half) * -(np.log(10000) / (half - 1))).numpy()  # same ops as the reference
+    freq_off = b.weight(freq)
+    ts = b.tensor(name + ".ts", 1, T, B=1, ld=T)  # dense f32 [T]
+    emb = b.tensor(name + ".temb0", T, t_dim, B=1)
+    W1, b1 = _conv(b, P.sub("fc_t1"))
+    W2, b2 = _conv(b, P.sub("fc_t2"))
+    h1 = b.tensor(name + ".temb1", T, W1[2], B=1)
+    h2 = b.tensor(name + ".temb2", T, W2[2], B=1)
+
+    def emit():
+        b.temb(ts, freq_off, half, emb, note=name + ".calc_t_emb")
+        b.gemm(emb, W1, h1, bias=b1, act="swish", note=name + ".fc_t1")
+        b.gemm(h1, W2, h2, bias=b2, act="swish", note=name + ".fc_t2")
+    return ts, h2, emit
+
+
+def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None):
+    """Lower PointNet2CloudCondition (no condition cloud).
+
+    X: arena tensor [B*n_points, 3 + in_fea_dim] (xyz first).  T: number of timesteps (DDPM denoisers) or None.
+    labels: i32 tensor [B, 1] (class condition) or None.
+    Returns dict(out=Tensor [B*n_points, out_channels], emit_setup=callable, inputs={...}).
+    The network ops are appended to b immediately; emit_setup() must be called inside the setup segment
+    (before the network runs) -- it emits the timestep tables and condition vectors.
+    """
+    assert not cfg.get("include_local_feature", True) and not cfg.get("include_global_feature", False)
+    arch = cfg["architecture"]
+    assert arch["neighbor_definition"] == "nn" and arch.get("use_knn_FP", False)
+    assert not arch.get("include_grouper", False)
+    if cfg.get("use_position_encoding", False):
+        raise NotImplementedError("position encoding")
+    B = X.B
+    inputs = {}
+    setup_pre = []
+    t_src = None
+    if T is not None and cfg["include_t"]:
+        ts, t_src, emit_t = t_embedding_source(b, P, cfg, T, name)
+        inputs["ts_table"] = ts
+        setup_pre.append(emit_t)
+    cond_src = None
+    if labels is not None and cfg["include_class_condition"]:
+        emb_w = P["class_emb.weight"]
+        table = b.tensor(name + ".class_emb", emb_w.shape[0], emb_w.shape[1], B=1)
+        inputs["class_emb"] = (table, emb_w)
+        cond_src = b.tensor(name + ".cond", 1, emb_w.shape[1], B=B)
+        lab_all = labels
+
+        def emit_c():
+            # class_emb(label): a row gather from the table, all samples index the same (B=1) table
+            b._emit("SLIDE_OP_GATHER_ROWS", {"GA_SRC": table.off, "GA_LDS": table.ld, "GA_N": table.R,
+                                             "GA_IDX": lab_all.off, "GA_M": B, "GA_DST": cond_src.off,
+                                             "GA_LDD": cond_src.ld, "GA_NCOLS": table.C, "GA_B": 1},
+                    note=name + ".class_emb")
+        setup_pre.append(emit_c)
+    ctx = _Ctx(b, cfg, t_src, cond_src)
+
+    Fin = X.C - 3
+    assert X.R == n_points
+    xyz = X.cols(0, 3)
+    if cfg["attach_position_to_input_feature"]:
+        feats = b.tensor(name + ".feat0", n_points, Fin + 3, B=B)
+        if Fin > 0:
+            b.copy_cols(X.cols(3, Fin), feats.cols(0, Fin), note=name + ".in_feat")
+        b.copy_cols(X.cols(0, 3), feats.cols(Fin, 3), note=name + ".in_xyz")
+    else:
+        assert Fin > 0
+        feats = X.cols(3, Fin)
+    l_xyz, l_feat = [xyz], [feats]
+    for i, (npoint, nsample) in enumerate(zip(arch["npoint"], arch["nsample"])):
+        nx, nf = _lower_sa(ctx, P.sub("SA_modules.%d" % i), l_xyz[i], l_feat[i], npoint, nsample,
+                           "%s.SA%d" % (name, i))
+        l_xyz.append(nx)
+        l_feat.append(nf)
+    n_fp = len(arch["decoder_feature_dim"]) - 1
+    transform = cfg.get("transform_output", True)
+    head_in = None
+    for i in range(-1, -(n_fp + 1), -1):
+        dst = None
+        if i == -n_fp:
+            d0 = arch["decoder_feature_dim"][0]
+            if transform:
+                head_in = b.tensor(name + ".head_in", n_points, d0 + 3, B=B)
+                dst = head_in.cols(0, d0)
+            elif out is not None:
+                dst = out
+        l_feat[i - 1] = _lower_fp(ctx, P.sub("FP_modules.%d" % (n_fp + i)), l_xyz[i - 1], l_xyz[i], l_feat[i - 1],
+                                  l_feat[i], arch.get("K", 3), "%s.FP%d" % (name, n_fp + i), out=dst)
+    result = l_feat[0]
+    if transform:
+        d0 = arch["decoder_feature_dim"][0]
+        b.copy_cols(xyz, head_in.cols(d0, 3), note=name + ".head_xyz")
+        W0, b0 = _conv(b, P.sub("fc_lyaer.0"))
+        raw = b.tensor(name + ".head_raw", n_points, W0[2], B=B)
+        assert W0[2] % 32 == 0
+        cg = W0[2] // 32
+        st = b.stats(name + ".head_st", W0[2], cg, n_points, n_points * cg, B=B)
+        b.gemm(head_in, W0, raw, bias=b0, stats=st, st_R=n_points, note=name + ".head0")
+        W3, b3 = _conv(b, P.sub("fc_lyaer.3"))
+        if out is None:
+            out = b.tensor(name + ".eps", n_points, W3[2], B=B)
+        b.gemm(raw, W3, out, bias=b3,
+               xfa=XF(stats=st.tensor, cg=cg, nnorm=W0[2], choff=0, gamma=b.weight(P["fc_lyaer.1.weight"]),
+                      beta=b.weight(P["fc_lyaer.1.bias"]), R=n_points, count=n_points * cg, relu=True),
+               note=name + ".head3")
+        result = out
+
+    def emit_setup():
+        for fn in setup_pre:
+            fn()
+        for g in ctx.setup:
+            b.gemm(g["A"], g["W"], g["out"], bias=g["bias"], note=g["note"])
+    return dict(out=result, emit_setup=emit_setup, inputs=inputs, levels=(l_xyz, l_feat))
+
+
+# ---------------------------------------------------------------------------------------------------
+# autoencoder decode
+# ---------------------------------------------------------------------------------------------------
+def _lower_upsample_points(b, P, cfg, final_feature, new_xyz, start, name):
+    """PointUpsampleDecoder.upsample_points (point_upsample_decoder.py:149-182).  final_feature [B*N, Cf],
+    new_xyz [B*N, Cx]; start: i32 [B,1] FPS start indices (pytorch3d random_start_point).  Returns
+    the upsampled cloud [B*n_out, out_dim]."""
+    up = cfg["upsampling_setting"]
+    if up["first_refine_coarse_points"]:
+        raise NotImplementedError("first_refine_coarse_points")
+    B, N = new_xyz.B, new_xyz.R
+    cat = b.tensor(name + ".up_in", N, final_feature.C + new_xyz.C, B=B)
+    b.copy_cols(final_feature, cat.cols(0, final_feature.C), note=name + ".up_cat_f")
+    b.copy_cols(new_xyz, cat.cols(final_feature.C, new_xyz.C), note=name + ".up_cat_x")
+    W, bias = _conv(b, P.sub("fc_layer"))
+    disp = b.tensor(name + ".disp", N, W[2], B=B)
+    b.gemm(cat, W, disp, bias=bias, note=name + ".fc_layer")
+    factor = up["point_upsample_factor"]
+    out_dim = cfg["out_dim"]
+    in_dim = cfg.get("in_position_and_normal_dim", out_dim)
+    pts = b.tensor(name + ".split", N * factor, out_dim, B=B)
+    b.upsample(new_xyz, min(in_dim, out_dim), disp, pts, factor, up["output_scale_factor"], note=name + ".upsample")
+    n_out = up["num_output_points"]
+    assert N * factor >= n_out
+    if N * factor > n_out:
+        sel = b.tensor(name + ".sel", 1, n_out, B=B, dtype="i32")
+        b.fps(1, pts, n_out, sel, start=start, note=name + ".fps_p3d")
+        res = b.tensor(name + ".points", n_out, out_dim, B=B)
+        b.gather_rows(pts, sel, n_out, res, note=name + ".masked_gather")
+        return res
+    return pts
+
+
+def lower_decode(b, P, decoder_cfgs, keypoint, feature, labels, name="ae"):
+    """PointAutoencoder.decode.  keypoint [B*16, 3], feature [B*16, 48] arena tensors, labels i32 [B,1].
+    Returns dict(out=[B*2048, 6], starts=[i32 [B,1] per level], emit_setup, inputs)."""
+    B = keypoint.B
+    starts = [b.tensor("%s.start%d" % (name, i), 1, B, B=1, dtype="i32") for i in range(len(decoder_cfgs))]
+    setups, class_tables = [], []
+    new_xyz = _lower_upsample_points(b, P.sub("keypoint_encoder"), decoder_cfgs[0], feature, keypoint, starts[0],
+                                     name + ".L1")
+    xyzs, feats = [keypoint, new_xyz], [feature]
+    for i, cfg in enumerate(decoder_cfgs[1:]):
+        Pd = P.sub("decoder.decoders.%d" % i)
+        lname = "%s.L%d" % (name, i + 2)
+        cur = xyzs[i + 1]
+        d0 = cfg["architecture"]["decoder_feature_dim"][0]
+        md = cfg["feature_mapper_setting"]["out_dim"]
+        final = b.tensor(lname + ".final", cur.R, d0 + md, B=B)
+        net = lower_cloud_net(b, Pd.sub("feature_extractor"), cfg, cur, cur.R, lname + ".fx", T=None, labels=labels,
+                              out=final.cols(0, d0))
+        setups.append(net["emit_setup"])
+        if "class_emb" in net["inputs"]:
+            class_tables.append(net["inputs"]["class_emb"])
+        ctx = _Ctx(b, cfg)
+        prev_xyz = xyzs[i].cols(0, 3)
+        cur_xyz = cur.cols(0, 3)
+        _lower_feature_map(ctx, Pd.sub("feature_mapper"), prev_xyz, feats[i], cur_xyz, net["out"],
+                           cfg["feature_mapper_setting"]["nsample"], lname + ".fm", final.cols(d0, md))
+        assert not ctx.setup
+        xyzs.append(_lower_upsample_points(b, Pd, cfg, final, cur, starts[i + 1], lname))
+        feats.append(final)
+
+    def emit_setup():
+        for fn in setups:
+            fn()
+    return dict(out=xyzs[-1], starts=starts, emit_setup=emit_setup, class_tables=class_tables, levels=xyzs)
