@@ -1,0 +1,246 @@
+"""GPU sampling pipeline: position DDPM -> feature (latent) DDPM -> autoencoder decode, one process per GPU.
+
+This is the host side of the hot path that the reference spreads over
+  sampling_and_inference/point_cloud_generation.py + util.sampling                   (16 keypoints)
+  sampling_and_inference/latent_ddpm_keypoint_conditional_generation.py +
+  diffusion_utils/diffusion.py::LatentDiffusion.denoise_and_reconstruct              (48-d features + decode)
+with the same RNG call order (so identical seeds give identical noise):
+  position DDPM   x_T and one z per step from CPU torch.normal                        (util.py:131-136,225,253)
+  latent DDPM     x_T from CPU torch.randn (diffusion.py:373), per-step noise from CUDA randn_like (:88)
+  decode          one CPU torch.randint per cloud and level for the FPS start index   (pytorch3d 0.7.0)
+Noise is always drawn for the FULL batch and then sliced per rank, so results do not depend on the world size.
+
+There is no CPU or PyTorch fallback: every network op runs in libslide_b200.so; torch is used for device
+memory, RNG, streams and (multi-GPU) the NCCL all-gather.
+"""
+import numpy as np
+import torch
+
+from . import engine, weights
+from .program import Program
+
+
+class DDPMSampler(object):
+    """One denoiser + its ancestral sampling loop, resident on one GPU."""
+
+    def __init__(self, pointnet_cfg, sd, B, table, mode, keep_cols, T, device, graph_steps=20, backend="auto"):
+        self.B, self.T, self.mode = B, T, mode
+        self.builder, self.h = engine.build_ddpm(pointnet_cfg, sd, B, T, table, mode, keep_cols=keep_cols)
+        self.prog = Program(self.builder, device)
+        self.prog.set_gemm_backend(backend)
+        self.C = self.h["C"]
+        self.graph_steps = graph_steps
+        while T % self.graph_steps:
+            self.graph_steps -= 1
+        self._captured = False
+        engine.init_constants(self.prog, self.h)
+
+    def set_labels(self, labels):
+        """labels: int tensor (B,).  Recomputes the per-module condition vectors (setup segment)."""
+        self.prog.upload(self.h["labels"], labels.to(torch.int32))
+        self.prog.run_segment("setup")
+
+    def noise_view(self):
+        """(T, B*16, C) device view; noise_view()[t] is what the update of step t adds."""
+        return self.prog.view(self.h["noise"]).view(self.T, self.B * self.h["n_points"], self.C)
+
+    def x_view(self):
+        return self.prog.view(self.h["x"])[:, :self.C]
+
+    def run(self, steps=None):
+        """Run the loop from t = T-1 down (x and noise must be in place).  steps=None -> all T."""
+        steps = self.T if steps is None else steps
+        first, count = self.builder.segments["step"]
+        self.prog.set_step(self.T)
+        if not self._captured:
+            # one eager step first: configures kernel attributes outside of stream capture
+            self.prog.run(first, count)
+            self.prog.set_step(self.T)
+            self.prog.capture(0, first, count, repeat=self.graph_steps)
+            self._captured = True
+        n_graph, rest = divmod(steps, self.graph_steps)
+        self.prog.replay(0, n_graph)
+        for _ in range(rest):
+            self.prog.run(first, count)
+
+    def launches_per_step(self):
+        return self.prog.launches(*self.builder.segments["step"])
+
+
+class Decoder(object):
+    def __init__(self, decoder_cfgs, sd, chunk, device, backend="auto"):
+        self.chunk = chunk
+        self.builder, self.h = engine.build_decode(decoder_cfgs, sd, chunk)
+        self.prog = Program(self.builder, device)
+        self.prog.set_gemm_backend(backend)
+        engine.init_constants(self.prog, self.h)
+        self.n_levels = len(self.h["starts"])
+        self.out_points = self.h["out"].R
+        self.out_dim = self.h["out"].C
+
+    def run(self, keypoint, feature, labels, starts, out):
+        """keypoint (B,16,3), feature (B,16,F), labels (B,), starts (levels,B) int, out (B,P,6) device tensors."""
+        B = keypoint.shape[0]
+        assert B % self.chunk == 0, "batch must be a multiple of the decode chunk"
+        for c0 in range(0, B, self.chunk):
+            sl = slice(c0, c0 + self.chunk)
+            self.prog.upload(self.h["labels"], labels[sl].to(torch.int32))
+            self.prog.upload(self.h["keypoint"], keypoint[sl])
+            self.prog.upload(self.h["feature"], feature[sl])
+            for lvl, t in enumerate(self.h["starts"]):
+                self.prog.upload(t, starts[lvl, sl].to(torch.int32))
+            self.prog.run_segment("setup")
+            self.prog.run_segment("decode")
+            out[sl].copy_(self.prog.view(self.h["out"])[:, :self.out_dim].view(self.chunk, self.out_points, self.out_dim))
+
+    def launches_per_chunk(self):
+        return self.prog.launches(*self.builder.segments["decode"]) + self.prog.launches(*self.builder.segments["setup"])
+
+
+def default_state_dicts(seed=0):
+    return {"position": weights.random_state_dict(weights.load_json("schema_position_ddpm.json"), seed + 1),
+            "latent": weights.random_state_dict(weights.load_json("schema_latent_ddpm.json"), seed + 2),
+            "autoencoder": weights.random_state_dict(weights.load_json("schema_autoencoder.json"), seed + 3)}
+
+
+class SlidePipeline(object):
+    """position DDPM -> latent DDPM -> decode for `local_batch` shapes on this GPU (rank `rank` of `world`)."""
+
+    def __init__(self, cfg, global_batch, rank=0, world=1, device=None, state_dicts=None, decode_chunk=32,
+                 ddpm_steps=None, backend="auto"):
+        assert global_batch % world == 0
+        self.cfg, self.B, self.rank, self.world = cfg, global_batch, rank, world
+        self.Bl = global_batch // world
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        sds = default_state_dicts() if state_dicts is None else state_dicts
+        pos, lat = cfg["position_ddpm"], cfg["latent_ddpm"]
+        d = pos["diffusion_config"]
+        self.T_pos = d["T"]
+        self.T_lat = lat["standard_diffusion_config"]["num_diffusion_timesteps"]
+        self.pos = DDPMSampler(pos["pointnet_config"], sds["position"], self.Bl,
+                               engine.position_table(d["T"], d["beta_0"], d["beta_T"]), 0, 0, self.T_pos, self.device,
+                               backend=backend)
+        self.lat = DDPMSampler(lat["pointnet_config"], sds["latent"], self.Bl,
+                               engine.latent_table(lat["standard_diffusion_config"]), 1, 3, self.T_lat, self.device,
+                               backend=backend)
+        chunk = min(decode_chunk, self.Bl)
+        while self.Bl % chunk:
+            chunk -= 1
+        self.dec = Decoder(cfg["autoencoder"]["decoders"], sds["autoencoder"], chunk, self.device, backend=backend)
+        self.ddpm_steps = ddpm_steps  # None = full schedules (anything else is a debugging aid, not a valid benchmark)
+        self.out = torch.empty(self.Bl, self.dec.out_points, self.dec.out_dim, device=self.device)
+        self._labels = None
+        n = self.Bl * 16
+        self._pos_noise_host = torch.empty(self.T_pos, n, 3).pin_memory()
+        self._lat_xT_host = torch.empty(self.Bl, 16, self.lat.C).pin_memory()
+        self._pos_xT_host = torch.empty(self.Bl, 16, 3).pin_memory()
+        self._labels_host = torch.empty(self.Bl, dtype=torch.int64).pin_memory()
+        self._starts_host = torch.empty(self.dec.n_levels, self.Bl, dtype=torch.int64).pin_memory()
+        self._out_host = torch.empty(self.Bl, self.dec.out_points, self.dec.out_dim).pin_memory()
+
+    # ---- host-side RNG in the reference's call order (full batch, then this rank's slice) -------------------
+    def draw_host_inputs(self, labels):
+        """labels: CPU int tensor (global_batch,).  Draws, on the CPU default generator and in the reference's
+        order, everything the reference draws on the host; stores this rank's slices in pinned buffers."""
+        B, T = self.B, self.T_pos
+        lo, hi = self.rank * self.Bl, (self.rank + 1) * self.Bl
+        size = (B, 16, 3)
+        if (B * 48) % 16 == 0:
+            big = torch.normal(0, 1, size=(T,) + size)  # == T sequential torch.normal(0,1,size) calls (chunks of 16)
+        else:
+            big = torch.stack([torch.normal(0, 1, size=size) for _ in range(T)])
+        # big[0] = x_T; big[1+i] = z added after step t = T-1-i (i = 0..T-2)
+        nz = self._pos_noise_host.view(T, self.Bl, 16, 3)
+        nz[0].zero_()
+        nz[1:] = torch.flip(big[1:, lo:hi], dims=[0])
+        self._pos_xT_host.copy_(big[0, lo:hi])
+        self._lat_xT_host.copy_(torch.randn(B, 16, self.lat.C)[lo:hi])
+        self._labels_host.copy_(labels[lo:hi])
+        # pytorch3d 0.7.0: one randint per cloud, batch order, level after level
+        n_in = 16
+        for lvl, dcfg in enumerate(self.cfg["autoencoder"]["decoders"]):
+            up = dcfg["upsampling_setting"]
+            P = n_in * up["point_upsample_factor"]
+            if P > up["num_output_points"]:  # FPS (and its draws) only happen when points must be dropped
+                draws = torch.tensor([int(torch.randint(high=P, size=(1,)).item()) for _ in range(B)])
+                self._starts_host[lvl].copy_(draws[lo:hi])
+            else:
+                self._starts_host[lvl].zero_()
+            n_in = up["num_output_points"]
+
+    # ---- device path -----------------------------------------------------------------------------------
+    def stage_inputs(self):
+        """Host -> device copies (pinned memory, async on the current stream) of everything draw_host_inputs staged."""
+        dev = self.device
+        labels = self._labels_host.to(dev, non_blocking=True)
+        if self._labels is None or not torch.equal(self._labels, labels):
+            self.pos.set_labels(labels)
+            self.lat.set_labels(labels)
+            self._labels = labels
+        self.pos.noise_view().copy_(self._pos_noise_host, non_blocking=True)
+        self._pos_xT_dev = self._pos_xT_host.to(dev, non_blocking=True)
+        self._lat_xT_dev = self._lat_xT_host.to(dev, non_blocking=True)
+        self._starts_dev = self._starts_host.to(dev, non_blocking=True)
+
+    def sample_resident(self):
+        """The three stages on inputs that stage_inputs() already put in HBM; returns the (Bl, 2048, 6) device tensor."""
+        dev = self.device
+        # 1. position DDPM
+        self.pos.x_view().copy_(self._pos_xT_dev.view(-1, 3))
+        self.pos.run(self.ddpm_steps)
+        kp = self.pos.x_view().view(self.Bl, 16, 3)
+        # 2. latent DDPM on the generated keypoints (keypoint-conditional: xyz columns are never updated)
+        x = self.lat.x_view().view(self.Bl, 16, self.lat.C)
+        x.copy_(self._lat_xT_dev)
+        x[:, :, 0:3] = kp
+        nz = self.lat.noise_view().view(self.T_lat, self.Bl, 16, self.lat.C)
+        if self.world == 1:
+            for i in range(self.T_lat - 1, -1, -1):  # the reference's randn_like sequence (diffusion.py:88)
+                torch.randn((self.Bl, 16, self.lat.C), device=dev, out=nz[i])
+        else:
+            full = torch.empty(self.B, 16, self.lat.C, device=dev)
+            lo = self.rank * self.Bl
+            for i in range(self.T_lat - 1, -1, -1):
+                torch.randn((self.B, 16, self.lat.C), device=dev, out=full)
+                nz[i].copy_(full[lo:lo + self.Bl])
+        self.lat.run(self.ddpm_steps)
+        feat = x[:, :, 3:].contiguous()
+        # 3. decode
+        self.dec.run(kp.contiguous(), feat, self._labels, self._starts_dev, self.out)
+        return self.out
+
+    def sample(self):
+        """Public entry: host buffers in (pinned), device tensor out."""
+        self.stage_inputs()
+        return self.sample_resident()
+
+    def sample_to_host(self):
+        out = self.sample()
+        self._out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._out_host
+
+    def h2d_bytes(self):
+        return (self._pos_noise_host.numel() + self._pos_xT_host.numel() + self._lat_xT_host.numel()) * 4 + \
+            self._labels_host.numel() * 8 + self._starts_host.numel() * 8
+
+    def d2h_bytes(self):
+        return self._out_host.numel() * 4
+
+    def gpu_launches(self):
+        """Kernels of libslide_b200.so launched by one sample() call."""
+        sp = self.T_pos if self.ddpm_steps is None else self.ddpm_steps
+        sl = self.T_lat if self.ddpm_steps is None else self.ddpm_steps
+        return (sp * self.pos.launches_per_step() + sl * self.lat.launches_per_step() +
+                (self.Bl // self.dec.chunk) * self.dec.launches_per_chunk())
+
+
+def all_gather_outputs(local_out, world):
+    """The path's single collective: one NCCL all-gather of the (B/W, 2048, 6) clouds (replaces the reference's
+    per-rank .npz files + rank-0 concatenation, pointnet2/mesh_evaluation.py:42,156-186)."""
+    import torch.distributed as dist
+    if world == 1:
+        return local_out
+    full = torch.empty((world,) + tuple(local_out.shape), device=local_out.device, dtype=local_out.dtype)
+    dist.all_gather_into_tensor(full.view(-1), local_out.reshape(-1))
+    return full.view((-1,) + tuple(local_out.shape[1:]))

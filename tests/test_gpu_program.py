@@ -1,0 +1,181 @@
+"""GPU parity of the CUDA executor against the CPU interpreter / oracle, record by record and end to end.
+All calls go through the C ABI (slide_program_* in libslide_b200.so)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ir_exec, ref_model
+from slide_b200 import engine, lib
+from slide_b200.program import Program, KIND_NAME
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"simt": 2e-4, "auto": 6e-3}
+
+
+def _teacher_forced(b, m, prog, first, count, rtol, log):
+    """Before every record copy the interpreter's arena to the GPU, run that one record on both, compare all tensors."""
+    worst = []
+    for i in range(first, first + count):
+        prog.raw_arena().copy_(torch.from_numpy(m.arena))
+        m.run(i, 1)
+        prog.run(i, 1)
+        torch.cuda.synchronize()
+        gpu = prog.raw_arena().cpu().numpy()
+        bad = common.compare_tensors(b, m, gpu, rtol)
+        kind = KIND_NAME[b.ops[i][0]]
+        log.append("op %3d %-22s %-28s %s" % (i, kind, b.ops[i][3], "ok" if not bad else bad[:4]))
+        if bad:
+            worst.append((i, kind, b.ops[i][3], bad[:4]))
+    return worst
+
+
+@pytest.mark.parametrize("which,backend,B", [("pos", "simt", 8), ("lat", "simt", 8), ("pos", "auto", 8), ("lat", "auto", 8)])
+def test_records_teacher_forced(which, backend, B, pipeline_cfg):
+    b, h, pc, sd = common.ddpm_program(pipeline_cfg, which, B, with_noise=True, T=4)
+    m = ir_exec.Machine(b)
+    labels = np.arange(B) % 13
+    common.init_machine(m, h, labels)
+    g = torch.Generator().manual_seed(7)
+    m.upload(h["x"], torch.randn(B * 16, h["C"], generator=g))
+    m.upload(h["noise"], torch.randn(h["noise"].rows, h["C"], generator=g))
+    m.set_step(3)
+    prog = Program(b)
+    prog.set_gemm_backend(backend)
+    log = []
+    bad = _teacher_forced(b, m, prog, *b.segments["setup"], rtol=TOL[backend], log=log)
+    bad += _teacher_forced(b, m, prog, *b.segments["step"], rtol=TOL[backend], log=log)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/records_%s_%s.log" % (which, backend), "w") as f:
+        f.write("\n".join(log) + "\n")
+    assert lib.load().slide_tc_error() == 0, "tcgen05 pipeline wait timed out"
+    assert not bad, bad[:6]
+
+
+@pytest.mark.parametrize("which", ["pos", "lat"])
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+def test_denoiser_forward_golden(which, backend, golden, pipeline_cfg):
+    """eps at t in {999, 500, 0} against the reference's golden vectors (B=2 replicated to B=16 so that the
+    tensor-core path is exercised with full tiles)."""
+    rep = 8
+    B = 2 * rep
+    b, h, pc, sd = common.ddpm_program(pipeline_cfg, which, B)
+    prog = Program(b)
+    prog.set_gemm_backend(backend)
+    engine.init_constants(prog, h)
+    prog.upload(h["labels"], torch.from_numpy(np.tile(golden["label"], rep).astype(np.int32)))
+    prog.run_segment("setup")
+    x = torch.from_numpy(np.tile(golden[which + "_x"], (rep, 1, 1)))
+    for t in (999, 500, 0):
+        prog.upload(h["x"], x)
+        prog.set_step(t + 1)
+        prog.run_segment("forward")
+        eps = prog.download(h["eps"]).cpu().numpy().reshape(B, 16, -1)
+        want = np.tile(golden["%s_eps_t%d" % (which, t)], (rep, 1, 1))
+        err = np.abs(eps - want).max()
+        assert err < (5e-5 if backend == "simt" else 2e-2) * max(1.0, np.abs(want).max()), (t, err)
+    assert lib.load().slide_tc_error() == 0
+
+
+@pytest.mark.parametrize("which", ["pos", "lat"])
+def test_sampler_loop_and_graph_replay(which, golden, pipeline_cfg):
+    """A few ancestral steps: eager records == CUDA-graph replay (bit-exact), and both == the oracle's loop."""
+    B, T, steps = 4, 1000, 4
+    b, h, pc, sd = common.ddpm_program(pipeline_cfg, which, B, with_noise=True)
+    label = torch.tensor([0, 4, 7, 12])
+    g = torch.Generator().manual_seed(5)
+    C = h["C"]
+    x_T = torch.randn(B, 16, C, generator=g)
+    kp = torch.rand(B, 16, 3, generator=g) - 0.5
+    noises = {t: torch.randn(B, 16, C, generator=g) for t in range(T - 1, T - 1 - steps, -1)}
+    net = lambda x, ts: ref_model.cloud_condition_net(x, ref_model.Params(sd), pc, ts=ts, label=label)
+    with torch.no_grad():
+        if which == "pos":
+            d = pipeline_cfg["position_ddpm"]["diffusion_config"]
+            want = ref_model.position_sampling(net, x_T, noises, ref_model.position_schedule(d["T"], d["beta_0"], d["beta_T"]),
+                                               n_steps=steps)
+            x0 = x_T
+        else:
+            sch = ref_model.latent_schedule(pipeline_cfg["latent_ddpm"]["standard_diffusion_config"])
+            want = ref_model.latent_denoise(net, x_T, kp, noises, sch, n_steps=steps)
+            x0 = torch.cat([kp, x_T[:, :, 3:]], dim=2)
+    prog = Program(b)
+    prog.set_gemm_backend("simt")
+    engine.init_constants(prog, h)
+    prog.upload(h["labels"], label.int())
+    nz = prog.view(h["noise"]).view(T, B * 16, C)
+    for t, v in noises.items():
+        nz[t].copy_(v.reshape(B * 16, C))
+    prog.run_segment("setup")
+    results = []
+    for mode in ("eager", "graph"):
+        prog.upload(h["x"], x0)
+        prog.set_step(T)
+        first, count = b.segments["step"]
+        if mode == "eager":
+            for _ in range(steps):
+                prog.run(first, count)
+        else:
+            prog.capture(0, first, count, repeat=2)
+            prog.replay(0, steps // 2)
+        torch.cuda.synchronize()
+        assert int(prog.view(b.step).item()) == T - steps
+        results.append(prog.download(h["x"]).cpu().reshape(B, 16, C))
+    assert torch.equal(results[0], results[1])
+    assert (results[0] - want).abs().max() < 2e-4 * max(1.0, want.abs().max())
+
+
+def _chamfer(a, b):
+    d = torch.cdist(a, b)
+    return max(d.min(1)[0].max().item(), d.min(0)[0].max().item())
+
+
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+def test_decode_golden(backend, golden, pipeline_cfg):
+    B = 2
+    sd = common.state_dict("ae")
+    b, h = engine.build_decode(pipeline_cfg["autoencoder"]["decoders"], sd, B)
+    prog = Program(b)
+    prog.set_gemm_backend(backend)
+    engine.init_constants(prog, h)
+    prog.upload(h["labels"], torch.from_numpy(golden["label"].astype(np.int32)))
+    prog.upload(h["keypoint"], torch.from_numpy(golden["dec_kp"]))
+    prog.upload(h["feature"], torch.from_numpy(golden["dec_feat"]))
+    for t, s in zip(h["starts"], golden["dec_starts"]):
+        prog.upload(t, torch.from_numpy(s.astype(np.int32)))
+    prog.run_segment("setup")
+    prog.run_segment("decode")
+    torch.cuda.synchronize()
+    l1 = prog.download(h["levels"][1]).cpu().reshape(B, 256, 6)
+    assert np.abs(l1.numpy() - golden["dec_l1"]).max() < (1e-6 if backend == "simt" else 1e-4)
+    out = prog.download(h["out"]).cpu().reshape(B, 2048, 6)
+    want = torch.from_numpy(golden["dec_out"])
+    assert torch.isfinite(out).all()
+    for i in range(B):
+        assert _chamfer(out[i, :, :3], want[i, :, :3]) < (2e-3 if backend == "simt" else 1e-2)
+    assert lib.load().slide_tc_error() == 0
+
+
+def test_decode_records_teacher_forced(golden, pipeline_cfg):
+    """Every record of the decode program (FPS, gathers, feature mapper, up-sampling) against the interpreter."""
+    B = 2
+    sd = common.state_dict("ae")
+    b, h = engine.build_decode(pipeline_cfg["autoencoder"]["decoders"], sd, B)
+    m = ir_exec.Machine(b)
+    engine.init_constants(m, h)
+    m.upload(h["labels"], golden["label"].astype(np.int32))
+    m.upload(h["keypoint"], golden["dec_kp"])
+    m.upload(h["feature"], golden["dec_feat"])
+    for t, s in zip(h["starts"], golden["dec_starts"]):
+        m.upload(t, s.astype(np.int32))
+    prog = Program(b)
+    prog.set_gemm_backend("simt")
+    log = []
+    bad = _teacher_forced(b, m, prog, *b.segments["setup"], rtol=2e-4, log=log)
+    bad += _teacher_forced(b, m, prog, *b.segments["decode"], rtol=2e-4, log=log)
+    with open("gpurun_out/records_decode_simt.log", "w") as f:
+        f.write("\n".join(log) + "\n")
+    assert not bad, bad[:6]
