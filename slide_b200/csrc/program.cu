@@ -512,18 +512,26 @@ int slide_program_run(slide_program *p, int first, int count, slide_stream_t str
 
 int slide_program_capture(slide_program *p, int slot, int first, int count, int repeat, slide_stream_t stream) {
   if (!p || slot < 0 || slot >= 8 || repeat < 1) return SLIDE_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
+  (void)stream;  // capture records work, it does not execute it: use a private stream (the legacy default
+                 // stream, which is what callers usually run on, cannot be captured)
+  cudaStream_t st = nullptr;
+  int rc = cuda_rc(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  if (rc != SLIDE_OK) return rc;
   if (p->graphs[slot]) {
     cudaGraphExecDestroy(p->graphs[slot]);
     p->graphs[slot] = nullptr;
   }
   const long long before = g_launch_count;
-  int rc = cuda_rc(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  if (rc != SLIDE_OK) return rc;
+  rc = cuda_rc(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  if (rc != SLIDE_OK) {
+    cudaStreamDestroy(st);
+    return rc;
+  }
   int run_rc = SLIDE_OK;
   for (int r = 0; r < repeat && run_rc == SLIDE_OK; ++r) run_rc = run_range(p, first, count, st);
   cudaGraph_t graph = nullptr;
   rc = cuda_rc(cudaStreamEndCapture(st, &graph));
+  cudaStreamDestroy(st);
   p->graph_launches[slot] = (int)(g_launch_count - before);
   g_launch_count = before;  // captured, not launched
   if (run_rc != SLIDE_OK || rc != SLIDE_OK) {

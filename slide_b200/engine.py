@@ -76,7 +76,7 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
     X = b.tensor("x", n_points, C)
     labels = b.tensor("labels", 1, B, B=1, dtype="i32")
     noise = b.tensor("noise", T * B * n_points if with_noise else 1, C, B=1, ld=C)
-    table_off = b.weight(np.asarray(table, dtype=np.float32).reshape(T, 8))
+    table_off = b.weight(np.asarray(table, dtype=np.float32).reshape(-1, 8)[:T])
     P = nets.Params(sd)
     b.begin_segment("step")
     b.step_begin()

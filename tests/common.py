@@ -33,11 +33,11 @@ def init_machine(m, h, labels):
     m.upload(h["labels"], np.asarray(labels, dtype=np.int32))
 
 
-def compare_tensors(builder, cpu, gpu_arena, rtol, note=""):
+def compare_tensors(builder, cpu, gpu_arena, rtol, note="", only=None):
     """Compare every arena tensor of the CPU interpreter with a downloaded GPU arena (uint8 numpy).
     Returns a list of (name, max_abs_err, scale) for tensors that deviate."""
     bad = []
-    for t in builder.tensors:
+    for t in (builder.tensors if only is None else only):
         dt = {"f32": np.float32, "i32": np.int32, "f64": np.float64}[t.dtype]
         n = t.rows * t.ld
         a = np.frombuffer(cpu.arena, dtype=dt, count=n, offset=t.off).reshape(t.rows, t.ld)[:, :t.C]

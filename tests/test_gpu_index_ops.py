@@ -25,7 +25,7 @@ def _clouds(B, N, seed, scale=1.0, dup=False, origin=False):
     if origin:  # points inside the |p|^2 <= 1e-3 ball, including index 0
         x[:, 0] = 0.001
         x[:, 5] = 0.01
-        x[:, 17] = -0.02
+        x[:, min(17, N - 1)] = -0.02
     return x.contiguous()
 
 

@@ -17,19 +17,29 @@ TOL = {"simt": 2e-4, "auto": 6e-3}
 
 
 def _teacher_forced(b, m, prog, first, count, rtol, log):
-    """Before every record copy the interpreter's arena to the GPU, run that one record on both, compare all tensors."""
+    """Run every record on both machines and compare the tensors it wrote.  After a mismatch the interpreter's arena
+    is copied to the GPU again so that one bad kernel does not hide the verdict on the following ones."""
     worst = []
+    prog.raw_arena().copy_(torch.from_numpy(m.arena))
     for i in range(first, first + count):
-        prog.raw_arena().copy_(torch.from_numpy(m.arena))
+        before = m.arena.copy()
         m.run(i, 1)
         prog.run(i, 1)
         torch.cuda.synchronize()
-        gpu = prog.raw_arena().cpu().numpy()
-        bad = common.compare_tensors(b, m, gpu, rtol)
+        touched = [t for t in b.tensors
+                   if not np.array_equal(before[t.off:t.off + t.nbytes], m.arena[t.off:t.off + t.nbytes])]
+        gpu = np.zeros_like(m.arena)
+        raw = prog.raw_arena()
+        for t in touched:
+            gpu[t.off:t.off + t.nbytes] = raw[t.off:t.off + t.nbytes].cpu().numpy()
+        bad = common.compare_tensors(b, m, gpu, rtol, only=touched)
         kind = KIND_NAME[b.ops[i][0]]
         log.append("op %3d %-22s %-28s %s" % (i, kind, b.ops[i][3], "ok" if not bad else bad[:4]))
         if bad:
             worst.append((i, kind, b.ops[i][3], bad[:4]))
+            prog.raw_arena().copy_(torch.from_numpy(m.arena))
+        step_off = b.step.off
+        raw[step_off:step_off + 4].copy_(torch.from_numpy(m.arena[step_off:step_off + 4]))
     return worst
 
 
