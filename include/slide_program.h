@@ -106,6 +106,9 @@ enum slide_gemm_field {
   GEMM_XFA, /* XF block for A */
   GEMM_XFR = GEMM_XFA + XF_NFIELD, /* XF block for resid */
   GEMM_STEP = GEMM_XFR + XF_NFIELD, /* step counter (for XF_ADDMODE 1) */
+  GEMM_WP_W,  /* tensor-core copy of W (or -1): TF32-rounded, tiled [ceil(K/32)][WP_NA][8 rows][128 B], each
+                 8x128 B atom in the SWIZZLE_128B pattern, zero padded -- one bulk copy per (N tile, K block) */
+  GEMM_WP_NA, /* 8-row atoms per K block in that copy (N rounded up to a multiple of 256, / 8) */
   GEMM_NFIELD
 };
 

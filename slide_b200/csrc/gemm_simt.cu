@@ -40,14 +40,16 @@ __global__ void __launch_bounds__(STHREADS) gemm_simt_kernel(GemmArgs a) {
 
   // loader mapping: thread -> (row = tid / 4, 4 consecutive k starting at (tid % 4) * 4)
   const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int lm = m0 + lr;
+  const int lsA = (lm < a.M) ? lm / a.xfa.R : 0;  // sample of the row this thread loads (fixed over the K loop)
   for (int k0 = 0; k0 < a.K; k0 += SBK) {
     {
-      const int m = m0 + lr;
+      const int m = lm;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int k = k0 + lk + u;
         float v = 0.f;
-        if (m < a.M && k < a.K) v = xf_apply(a.xfa, tabA, sA0, m, k, a.A[(size_t)m * a.lda + k], step);
+        if (m < a.M && k < a.K) v = xf_apply(a.xfa, tabA, sA0, lsA, k, a.A[(size_t)m * a.lda + k], step);
         As[lk + u][lr] = v;
       }
       const int n = n0 + lr;
@@ -76,20 +78,23 @@ __global__ void __launch_bounds__(STHREADS) gemm_simt_kernel(GemmArgs a) {
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
     if (m >= a.M) continue;
+    const int sR = a.res ? m / a.xfr.R : 0;
+    const int sS = a.st_stats ? m / a.st_R - sS0 : 0;
+    const float *evrow = a.ev ? a.ev + (size_t)(m / a.evdiv) * a.evld : nullptr;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= a.N) continue;
       float v = acc[i][j];
       if (a.bias) v += __ldg(a.bias + n);
-      if (a.ev) v += a.ev[(size_t)(m / a.evdiv) * a.evld + n];
-      if (a.res) v += xf_apply(a.xfr, tabR, sR0, m, n, a.res[(size_t)m * a.ldr + n], step);
+      if (evrow) v += evrow[n];
+      if (a.res) v += xf_apply(a.xfr, tabR, sR0, sR, n, a.res[(size_t)m * a.ldr + n], step);
       v = act_apply(a.act, v);
       a.C[(size_t)m * a.ldc + n] = v;
       if (a.st_stats) {
         const int ch = a.st_choff + n;
         if (ch < a.st_nnorm) {
-          float *slot = stacc + (((m / a.st_R) - sS0) * XF_MAXG + ch / a.st_cg) * 2;
+          float *slot = stacc + (sS * XF_MAXG + ch / a.st_cg) * 2;
           atomicAdd(slot, v);
           atomicAdd(slot + 1, v * v);
         }

@@ -1,27 +1,33 @@
 // tcgen05 GEMM for sm_100a: C = act( xfA(A) W^T + bias + ev + xfR(resid) ) with TF32 operands, fp32 accumulation
 // in tensor memory, and the fused GroupNorm prologue / statistics epilogue of SLIDE_OP_GEMM.
 //
-// Why not TMA for the operands: the A operand is not stored in the form the tensor core consumes -- the
-// producing layer's GroupNorm + ReLU + timestep/condition vector are applied WHILE loading (that is what
-// removes the separate normalisation pass over HBM), so operand tiles go global -> registers (transform,
-// round-to-nearest TF32) -> shared memory in the canonical K-major SWIZZLE_128B layout, and are handed to the
-// tensor core through the async proxy.  One elected thread issues tcgen05.mma (M=128, N=BN, K=8 per
-// instruction); accumulators live in TMEM and are drained by four warps with tcgen05.ld, transposed through
-// shared memory so that every global store / residual load is a coalesced 128-byte row segment.
+// Operand paths
+//   W (weights)  : a TF32-rounded copy tiled on the host exactly as the B operand sits in shared memory
+//                  (slide_program.h, GEMM_WP_W), so one cp.async.bulk per (N tile, K block) lands a whole
+//                  SWIZZLE_128B tile and signals the stage's mbarrier with its byte count -- no thread touches it.
+//   A (activations): NOT stored in the form the tensor core consumes: the producing layer's GroupNorm + ReLU +
+//                  timestep/condition vector are applied WHILE loading (this is what removes the separate
+//                  normalisation pass over HBM).  Four producer warps move A global -> registers (transform,
+//                  round-to-nearest TF32) -> shared memory in the K-major SWIZZLE_128B layout, with the next
+//                  K block's global loads already in flight while the current one is transformed and stored.
+//   D            : one elected thread issues tcgen05.mma (M=128, N=BN, K=8 per instruction); the accumulator lives
+//                  in TMEM and is drained by the four producer warps with tcgen05.ld, transposed through shared
+//                  memory so that every global store / residual load is a coalesced 128-byte row segment.
 //
-// CTA = 160 threads: warps 0-3 load operand stages, then run the epilogue (warp w owns TMEM lanes 32w..32w+31);
-// warp 4 allocates TMEM and issues the MMAs.  Two CTAs fit per SM (<= 113 KB shared memory, <= 256 TMEM
-// columns each), so one CTA's epilogue overlaps the other's main loop.
+// CTA = 160 threads: warps 0-3 produce A, then run the epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4
+// allocates TMEM and issues the MMAs.  Shared memory is sized so that two CTAs share an SM: one CTA's epilogue
+// overlaps the other's main loop.
 #include "common.cuh"
 #include "program.cuh"
 
 namespace slide {
 
-constexpr int TBM = 128;      // rows per CTA tile (UMMA M)
-constexpr int TBK = 32;       // fp32 elements per K block = one 128-byte swizzle row
+constexpr int TBM = 128;  // rows per CTA tile (UMMA M)
+constexpr int TBK = 32;   // fp32 elements per K block = one 128-byte swizzle row
 constexpr int TC_THREADS = 160;
 constexpr int TC_PRODUCERS = 128;
-constexpr int TC_TABLE_BUDGET = 48 * 1024;  // bytes of shared memory for the A transform table
+constexpr int TC_TABLE_BUDGET = 40 * 1024;  // bytes of shared memory for the A transform table
+constexpr int TC_MAX_DYN_SMEM = 227 * 1024;
 
 __device__ int g_tc_error = 0;  // set when a barrier wait times out (never in a correct run)
 
@@ -32,6 +38,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -47,9 +56,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must not hang the GPU.  After ~2 s (or once any thread has given up) the wait
-// returns false and the kernel drains without touching tensor memory results.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return true;
+// returns false and the kernel drains without using tensor-memory results.
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (uint32_t it = 1;; ++it) {
@@ -63,6 +71,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
       }
     }
   }
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  return mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ uint32_t to_tf32(float v) {
@@ -89,21 +101,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
 }
 
-struct TcSmemLayout {
-  int stage_bytes, stages_bytes, table_off, table_bytes, bar_off, total;
-};
-
-__host__ __device__ inline TcSmemLayout tc_layout(int BN, int STAGES, int table_entries) {
-  TcSmemLayout L;
-  L.stage_bytes = (TBM + BN) * TBK * 4;
-  const int epi_bytes = 4 * 32 * 33 * 4 + XF_MAXS * BN * 16;  // transpose buffers + resid transform table
-  L.stages_bytes = STAGES * L.stage_bytes > epi_bytes ? STAGES * L.stage_bytes : epi_bytes;
-  L.table_off = L.stages_bytes;
-  L.table_bytes = table_entries * 16;
-  L.bar_off = L.table_off + ((L.table_bytes + 15) / 16) * 16;
-  L.total = L.bar_off + 256 + XF_MAXS * XF_MAXG * 2 * 4 + 1024 /* alignment slack */;
-  return L;
+// Shared-memory carve-up (bytes from the 1024-aligned base): operand stages | A transform table | control.
+// After the main loop the stage area is reused for the epilogue's transpose buffers and resid transform table.
+__host__ __device__ constexpr int tc_stage_bytes(int BN) { return (TBM + BN) * TBK * 4; }
+__host__ __device__ constexpr int tc_epi_bytes(int BN) { return 4 * 32 * 33 * 4 + XF_MAXS * BN * 16; }
+__host__ __device__ constexpr int tc_stages_bytes(int BN, int STAGES) {
+  return STAGES * tc_stage_bytes(BN) > tc_epi_bytes(BN) ? STAGES * tc_stage_bytes(BN) : tc_epi_bytes(BN);
 }
+constexpr int TC_CTRL_BYTES = 256 + XF_MAXS * XF_MAXG * 2 * 4;
 
 // Fill a transform table: entry (sl, k) = (scale, shift, add, 0) so that y = relu?(x*scale + shift) + add.
 __device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, int s0, int ns, int ncols, int col0,
@@ -134,15 +139,17 @@ __device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, int s0,
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, int table_stride, int table_rows) {
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
+                                                             int table_stride, int table_rows) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const TcSmemLayout L = tc_layout(BN, STAGES, 0);
+  constexpr int STAGE_BYTES = tc_stage_bytes(BN);
+  constexpr int W_BYTES = BN * TBK * 4;
   const bool has_xfa = a.xfa.stats != nullptr || a.xfa.addvec != nullptr || a.xfa.relu != 0;
-  float4 *tabA = reinterpret_cast<float4 *>(smem + L.table_off);
+  float4 *tabA = reinterpret_cast<float4 *>(smem + tc_stages_bytes(BN, STAGES));
   const int tabA_bytes = has_xfa ? table_rows * table_stride * 16 : 0;
-  uint8_t *ctrl = smem + L.table_off + ((tabA_bytes + 15) / 16) * 16;
+  uint8_t *ctrl = smem + tc_stages_bytes(BN, STAGES) + tabA_bytes;
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(ctrl);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *accum_bar = empty_bar + STAGES;
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, int tab
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(full_bar + s), TC_PRODUCERS);
+      mbar_init(smem_u32(full_bar + s), TC_PRODUCERS + 1);  // 128 A producers + the W bulk copy's expect_tx arrive
       mbar_init(smem_u32(empty_bar + s), 1);
     }
     mbar_init(smem_u32(accum_bar), 1);
@@ -181,37 +188,55 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, int tab
 
   bool ok = true;
   if (warp < 4) {
-    // ------------------------------------------------------------------------------------- producers
+    // ------------------------------------------------------------------------------------- A producers
     const int chunk = tid & 7;   // 16-byte chunk within the 128-byte K row
-    const int rbase = tid >> 3;  // 0..15
+    const int rbase = tid >> 3;  // 0..15; this thread owns rows rbase + 16 i, i = 0..7
+    const float *arow[8];
+    int trow[8];  // offset of the row's sample in the transform table
+    bool rvalid[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + rbase + 16 * i;
+      rvalid[i] = m < a.M;
+      arow[i] = a.A + (size_t)(rvalid[i] ? m : 0) * a.lda + chunk * 4;
+      trow[i] = has_xfa && rvalid[i] ? (m / a.xfa.R - sA0) * table_stride + chunk * 4 : 0;
+    }
+    const bool relu = a.xfa.relu != 0;
+    float4 va[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rvalid[i] && chunk * 4 < a.K) va[i] = *reinterpret_cast<const float4 *>(arow[i]);
+    }
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
       if (ok) ok = mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
-      uint8_t *sa = smem + (size_t)s * L.stage_bytes;
-      uint8_t *sb = sa + TBM * TBK * 4;
-      const int k = kb * TBK + chunk * 4;
-      // A tile: 128 rows, 8 rows in flight per thread
-      float4 va[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + rbase + 16 * i;
-        va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < a.M && k < a.K) va[i] = *reinterpret_cast<const float4 *>(a.A + (size_t)m * a.lda + k);
+      uint8_t *sa = smem + (size_t)s * STAGE_BYTES;
+      if (tid == 0) {
+        // weights: one bulk copy of the pre-tiled, pre-swizzled (N tile, K block); completes on full_bar[s]
+        const uint32_t bar = smem_u32(full_bar + s);
+        mbar_arrive_expect_tx(bar, (uint32_t)W_BYTES);
+        const float *src = Wp + ((size_t)kb * wp_na + (size_t)(n0 >> 3)) * 256;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(sa + TBM * TBK * 4)),
+            "l"(src), "r"((uint32_t)W_BYTES), "r"(bar)
+            : "memory");
       }
+      const int k = kb * TBK + chunk * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rbase + 16 * i;
-        const int m = m0 + r;
         float v[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
-        if (has_xfa && m < a.M) {
-          const float4 *t = tabA + (m / a.xfa.R - sA0) * table_stride + k;
+        if (has_xfa && rvalid[i]) {
+          const float4 *t = tabA + trow[i] + kb * TBK;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (k + u < a.K) {
               const float4 c = t[u];
               float y = fmaf(v[u], c.x, c.y);
-              if (a.xfa.relu) y = fmaxf(y, 0.f);
+              if (relu) y = fmaxf(y, 0.f);
               v[u] = y + c.z;
             }
           }
@@ -222,28 +247,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, int tab
         const uint4 o = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
         *reinterpret_cast<uint4 *>(sa + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
       }
-      // W tile: BN rows
-#pragma unroll
-      for (int i0 = 0; i0 < BN / 16; i0 += 8) {
-        float4 vw[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = n0 + rbase + 16 * (i0 + i);
-          vw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i0 + i < BN / 16 && n < a.N && k < a.K)
-            vw[i] = __ldg(reinterpret_cast<const float4 *>(a.W + (size_t)n * a.ldw + k));
-        }
+      // next K block's global loads go out now and overlap this stage's MMA
+      if (kb + 1 < num_kb) {
+        const int kn = k + TBK;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (i0 + i < BN / 16) {
-            const int r = rbase + 16 * (i0 + i);
-            float v[4] = {vw[i].x, vw[i].y, vw[i].z, vw[i].w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (k + u >= a.K) v[u] = 0.f;
-            const uint4 o = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
-            *reinterpret_cast<uint4 *>(sb + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
-          }
+          va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rvalid[i] && kn < a.K) va[i] = *reinterpret_cast<const float4 *>(arow[i] + (size_t)(kb + 1) * TBK);
         }
       }
       // make the generic-proxy writes visible to the tensor core (async proxy), then signal
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, int tab
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         if (ok) ok = mbar_wait(smem_u32(full_bar + s), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + (size_t)s * L.stage_bytes);
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const uint64_t da = make_smem_desc(sa);
         const uint64_t db = make_smem_desc(sa + TBM * TBK * 4);
         if (ok) {
@@ -294,21 +304,27 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, int tab
     if (ok) ok = mbar_wait(smem_u32(accum_bar), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  // every stage buffer is dead now (all MMAs completed before accum_bar fired): reuse it
+  // every stage buffer is dead now (all MMAs completed before accum_bar fired): reuse the area
   float *tbuf = reinterpret_cast<float *>(smem) + warp * (32 * 33);
   float4 *tabR = reinterpret_cast<float4 *>(smem + 4 * 32 * 33 * 4);
   const bool has_xfr = a.res && (a.xfr.stats != nullptr || a.xfr.addvec != nullptr || a.xfr.relu != 0);
   const int sR0 = m0 / a.xfr.R;
-  // all 160 threads reach this barrier: producers are past their last smem write, warp 4 is past its issue loop
   __syncthreads();
   if (has_xfr) {
     const int ncols = min(BN, a.N - n0);
     fill_xf_table(a.xfr, tabR, sR0, mlast / a.xfr.R - sR0 + 1, ncols, n0, BN, step, tid, TC_THREADS);
+    __syncthreads();  // has_xfr is uniform over the CTA
   }
-  __syncthreads();
 
   if (warp < 4) {
+    const int mw = m0 + warp * 32;                // first row of this warp
+    const int rr_end = min(32, a.M - mw);         // rows of this warp that exist (warp-uniform, may be <= 0)
     const int sS0 = m0 / a.st_R;
+    // row -> (ev row, resid sample, statistics sample) by counters: no division inside the loops
+    const int ev_row0 = a.ev ? mw / a.evdiv : 0, ev_rem0 = a.ev ? mw % a.evdiv : 0;
+    const int xr_s0 = has_xfr ? mw / a.xfr.R - sR0 : 0, xr_rem0 = has_xfr ? mw % a.xfr.R : 0;
+    const int st_s0 = a.st_stats ? mw / a.st_R - sS0 : 0, st_rem0 = a.st_stats ? mw % a.st_R : 0;
+    const bool xr_relu = a.xfr.relu != 0;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= a.N) break;
       uint32_t r[32];
@@ -330,7 +346,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, int tab
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      // transpose: thread (= row) writes its 32 columns; then lane = column
+      // transpose: thread (= row) writes its 32 columns; afterwards lane = column
 #pragma unroll
       for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
       __syncwarp();
@@ -339,47 +355,59 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, int tab
       const float bias = (ncol && a.bias) ? __ldg(a.bias + n) : 0.f;
       const int stch = a.st_choff + n;
       const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
+      float *stslot = stacc + (st_s0 * XF_MAXG + (dost ? stch / a.st_cg : 0)) * 2;
       float ssum = 0.f, ssq = 0.f;
-      int scur = -1;
-      for (int rr = 0; rr < 32; ++rr) {
-        const int m = m0 + warp * 32 + rr;
-        if (m >= a.M) break;
+      const float *evp = a.ev ? a.ev + (size_t)ev_row0 * a.evld + n : nullptr;
+      int ev_rem = ev_rem0;
+      const float4 *xrp = tabR + xr_s0 * BN + c0 + lane;
+      int xr_rem = xr_rem0;
+      int st_rem = st_rem0;
+      const float *resp = a.res ? a.res + (size_t)mw * a.ldr + n : nullptr;
+      float *cp = a.C + (size_t)mw * a.ldc + n;
+      for (int rr = 0; rr < rr_end; ++rr) {
         if (ncol) {
           float v = tbuf[rr * 33 + lane] + bias;
-          if (a.ev) v += a.ev[(size_t)(m / a.evdiv) * a.evld + n];
-          if (a.res) {
-            float x = a.res[(size_t)m * a.ldr + n];
+          if (evp) v += *evp;
+          if (resp) {
+            float x = *resp;
             if (has_xfr) {
-              const float4 c = tabR[(m / a.xfr.R - sR0) * BN + c0 + lane];
+              const float4 c = *xrp;
               x = fmaf(x, c.x, c.y);
-              if (a.xfr.relu) x = fmaxf(x, 0.f);
+              if (xr_relu) x = fmaxf(x, 0.f);
               x += c.z;
             }
             v += x;
           }
           v = act_apply(a.act, v);
-          a.C[(size_t)m * a.ldc + n] = v;
+          *cp = v;
+          ssum += v;
+          ssq = fmaf(v, v, ssq);
+        }
+        // advance the row counters (warp-uniform)
+        cp += a.ldc;
+        if (resp) resp += a.ldr;
+        if (evp && ++ev_rem == a.evdiv) {
+          ev_rem = 0;
+          evp += a.evld;
+        }
+        if (has_xfr && ++xr_rem == a.xfr.R) {
+          xr_rem = 0;
+          xrp += BN;
+        }
+        if (a.st_stats && ++st_rem == a.st_R) {
+          st_rem = 0;
           if (dost) {
-            const int sm = m / a.st_R;
-            if (sm != scur) {
-              if (scur >= 0) {
-                float *slot = stacc + ((scur - sS0) * XF_MAXG + stch / a.st_cg) * 2;
-                atomicAdd(slot, ssum);
-                atomicAdd(slot + 1, ssq);
-              }
-              scur = sm;
-              ssum = 0.f;
-              ssq = 0.f;
-            }
-            ssum += v;
-            ssq = fmaf(v, v, ssq);
+            atomicAdd(stslot, ssum);
+            atomicAdd(stslot + 1, ssq);
           }
+          stslot += XF_MAXG * 2;
+          ssum = 0.f;
+          ssq = 0.f;
         }
       }
-      if (dost && scur >= 0) {
-        float *slot = stacc + ((scur - sS0) * XF_MAXG + stch / a.st_cg) * 2;
-        atomicAdd(slot, ssum);
-        atomicAdd(slot + 1, ssq);
+      if (dost && st_rem != 0) {  // rows left over since the last sample boundary
+        atomicAdd(stslot, ssum);
+        atomicAdd(stslot + 1, ssq);
       }
       __syncwarp();
     }
@@ -406,12 +434,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, int tab
 // A row tile must map onto whole samples (or lie inside one): then it touches at most XF_MAXS of them.
 static bool spans_ok_tc(int R) { return R % TBM == 0 || (TBM % R == 0 && TBM / R <= XF_MAXS); }
 static int tc_rows_per_tile(int R) { return R % TBM == 0 ? 1 : TBM / R; }
-static int tc_table_stride(const GemmArgs &a) { return ((a.K + 3) / 4) * 4; }
+static int tc_table_stride(const GemmArgs &a) { return ((a.K + TBK - 1) / TBK) * TBK; }
 static bool has_xf(const XFd &x) { return x.stats || x.addvec || x.relu; }
 
-bool gemm_tc_eligible(const GemmArgs &a) {
-  if (a.M < TBM || a.K < 48 || a.N < 32) return false;
-  if (((uintptr_t)a.A & 15) || (a.lda & 3) || ((uintptr_t)a.W & 15) || (a.ldw & 3)) return false;
+bool gemm_tc_eligible(const GemmArgs &a, const float *Wp) {
+  if (!Wp) return false;
+  if (a.M < TBM || a.K < 32 || a.N < 32) return false;
+  if (((uintptr_t)a.A & 15) || (a.lda & 3) || ((uintptr_t)Wp & 15)) return false;
   if (has_xf(a.xfa)) {
     if (!spans_ok_tc(a.xfa.R)) return false;
     if (tc_rows_per_tile(a.xfa.R) * tc_table_stride(a) * 16 > TC_TABLE_BUDGET) return false;
@@ -425,15 +454,11 @@ bool gemm_tc_eligible(const GemmArgs &a) {
   return true;
 }
 
-constexpr int TC_MAX_DYN_SMEM = 227 * 1024;
-
 template <int BN, int STAGES>
-static int launch_tc(const GemmArgs &a, cudaStream_t st) {
+static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
   const int stride = tc_table_stride(a);
   const int rows = has_xf(a.xfa) ? tc_rows_per_tile(a.xfa.R) : 0;
-  const TcSmemLayout L = tc_layout(BN, STAGES, 0);
-  const int table_bytes = rows * stride * 16;
-  const int total = L.table_off + ((table_bytes + 15) / 16) * 16 + 256 + XF_MAXS * XF_MAXG * 2 * 4 + 1024;
+  const int total = tc_stages_bytes(BN, STAGES) + rows * stride * 16 + TC_CTRL_BYTES + 1024 /* alignment slack */;
   if (total > TC_MAX_DYN_SMEM) return SLIDE_ERR_UNSUPPORTED;
   static bool configured = false;
   if (!configured) {
@@ -443,15 +468,29 @@ static int launch_tc(const GemmArgs &a, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(ceil_div(a.M, TBM), ceil_div(a.N, BN));
-  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, total, st>>>(a, stride, rows);
+  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, total, st>>>(a, Wp, wp_na, stride, rows);
   return after_launch();
 }
 
-int launch_gemm_tc(const GemmArgs &a, cudaStream_t st) {
-  if (a.N > 128) return launch_tc<256, 2>(a, st);
-  if (a.N > 64) return launch_tc<128, 3>(a, st);
-  if (a.N > 32) return launch_tc<64, 4>(a, st);
-  return launch_tc<32, 4>(a, st);
+int launch_gemm_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
+  // Widest N tile that still gives every SM about two CTAs; small problems take narrow tiles for parallelism.
+  const int mt = ceil_div(a.M, TBM);
+  const int want = 2 * 148;
+  int bn = 32;
+  if (a.N > 128 && mt * ceil_div(a.N, 256) >= want)
+    bn = 256;
+  else if (a.N > 64 && mt * ceil_div(a.N, 128) >= want)
+    bn = 128;
+  else if (a.N > 32 && mt * ceil_div(a.N, 64) >= want)
+    bn = 64;
+  else if (a.N > 32 && mt * ceil_div(a.N, 32) < want / 4)
+    bn = 64;  // tiny problem either way: fewer, fatter tiles
+  switch (bn) {
+    case 256: return launch_tc<256, 2>(a, Wp, wp_na, st);
+    case 128: return launch_tc<128, 3>(a, Wp, wp_na, st);
+    case 64: return launch_tc<64, 4>(a, Wp, wp_na, st);
+    default: return launch_tc<32, 4>(a, Wp, wp_na, st);
+  }
 }
 
 int tc_error_flag() {

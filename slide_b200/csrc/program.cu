@@ -396,7 +396,8 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       a.xfa = make_xf(p, q + GEMM_XFA);
       a.xfr = make_xf(p, q + GEMM_XFR);
       a.step = AP<int>(p, q[GEMM_STEP]);
-      if (p->gemm_backend == 0 && gemm_tc_eligible(a)) return launch_gemm_tc(a, st);
+      const float *wp = WP<float>(p, q[GEMM_WP_W]);
+      if (p->gemm_backend == 0 && gemm_tc_eligible(a, wp)) return launch_gemm_tc(a, wp, (int)q[GEMM_WP_NA], st);
       return launch_gemm_simt(a, st);
     }
     case SLIDE_OP_SOFTMAX_WSUM: {

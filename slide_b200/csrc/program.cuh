@@ -57,11 +57,9 @@ __device__ __forceinline__ void xf_fill_table(const XFd &x, float2 *tab, int s0,
   }
 }
 
-// Apply the transform to one element: `row` is the global row, `col` the local column of the loaded tensor.
-__device__ __forceinline__ float xf_apply(const XFd &x, const float2 *tab, int s0, long long row, int col, float v,
-                                          int step) {
-  int s = 0;
-  if (x.stats || (x.addvec && x.addmode == 0)) s = (int)(row / x.R);
+// Apply the transform to one element of sample `s` (= row / x.R, computed once per row by the caller); `col` is
+// the local column of the loaded tensor.
+__device__ __forceinline__ float xf_apply(const XFd &x, const float2 *tab, int s0, int s, int col, float v, int step) {
   if (x.stats) {
     const int ch = x.choff + col;
     if (ch < x.nnorm) {
@@ -84,8 +82,8 @@ __device__ __forceinline__ float act_apply(int act, float v) {
 }
 
 int launch_gemm_simt(const GemmArgs &a, cudaStream_t st);
-bool gemm_tc_eligible(const GemmArgs &a);
-int launch_gemm_tc(const GemmArgs &a, cudaStream_t st);
+bool gemm_tc_eligible(const GemmArgs &a, const float *Wp);
+int launch_gemm_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st);
 int tc_error_flag();
 int program_fps(int mode, const float *xyz, int ldx, int B, int N, int m, const int *start, int *out, cudaStream_t st);
 

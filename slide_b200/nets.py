@@ -24,6 +24,10 @@ import numpy as np
 from .program import XF, NO_XF, Builder  # noqa: F401
 
 
+# contractions at least this large get a tensor-core weight copy (the kernel applies further shape tests)
+TC_MIN_K, TC_MIN_N = 32, 32
+
+
 def _np(x):
     if hasattr(x, "detach"):
         x = x.detach().cpu().numpy()
@@ -61,6 +65,9 @@ def _conv(b, P, cols=None):
         w = w[:, cols[0]:cols[1]]
     off, ldw = b.weight_matrix(w)
     bias = b.weight(P["bias"]) if P.has("bias") else -1
+    if w.shape[1] >= TC_MIN_K and w.shape[0] >= TC_MIN_N:
+        wp, na = b.weight_matrix_tc(w)  # tensor-core copy (TF32, pre-swizzled tiles)
+        return (off, ldw, w.shape[0], w.shape[1], wp, na), bias
     return (off, ldw, w.shape[0], w.shape[1]), bias
 
 

@@ -164,6 +164,24 @@ class Builder(object):
         buf[:, :K] = w
         return self.weight(buf), ldw
 
+    def weight_matrix_tc(self, w):
+        """Tensor-core copy of an (N, K) weight: TF32-rounded (round to nearest even on the 13 dropped mantissa
+        bits) and tiled exactly as the tcgen05 B operand is laid out in shared memory, so that the kernel
+        fetches one (N tile, K block) with a single bulk copy.  Returns (offset, atoms per K block)."""
+        w = np.asarray(w, dtype=np.float32)
+        N, K = w.shape
+        KB, NP = (K + 31) // 32, _align(N, 256)
+        bits = np.zeros((NP, KB * 32), dtype=np.uint32)
+        bits[:N, :K] = w.view(np.uint32)
+        bits = ((bits + np.uint32(0xFFF) + ((bits >> np.uint32(13)) & np.uint32(1))) & np.uint32(0xFFFFE000))
+        t = bits.reshape(NP // 8, 8, KB, 8, 4)          # [atom, r, kb, chunk, within]
+        out = np.zeros((KB, NP // 8, 8, 8, 4), dtype=np.uint32)
+        for r in range(8):
+            for c in range(8):
+                # logical 16-byte chunk c of row r lives at physical chunk c ^ r
+                out[:, :, r, c ^ r, :] = t[:, r, :, c, :].transpose(1, 0, 2)
+        return self.weight(out.view(np.float32).reshape(-1)), NP // 8
+
     def weights_blob(self):
         blob = np.zeros(max(self.weights_bytes, 64), dtype=np.uint8)
         for off, a in self.wchunks:
@@ -209,8 +227,9 @@ class Builder(object):
 
     def gemm(self, A, W, out, bias=-1, act=None, xfa=NO_XF, ev=None, ev_div=1, resid=None, xfr=NO_XF, stats=None,
              st_R=None, st_choff=0, st_weight=1, note=""):
-        """out = act(xfa(A) W^T + bias + ev[row // ev_div] + xfr(resid)); W = (offset, ldw, N, K)."""
-        woff, ldw, N, K = W
+        """out = act(xfa(A) W^T + bias + ev[row // ev_div] + xfr(resid)); W = (offset, ldw, N, K[, wp_off, wp_na])."""
+        woff, ldw, N, K = W[:4]
+        wp_off, wp_na = (W[4], W[5]) if len(W) > 4 else (-1, 0)
         assert A.C == K and out.C == N and A.rows == out.rows, (note, A.C, K, out.C, N, A.rows, out.rows)
         f = {"GEMM_A": A.off, "GEMM_LDA": A.ld, "GEMM_M": A.rows, "GEMM_K": K, "GEMM_W_W": woff, "GEMM_LDW": ldw,
              "GEMM_N": N, "GEMM_C": out.off, "GEMM_LDC": out.ld, "GEMM_BIAS_W": bias, "GEMM_ACT": ACT[act],
@@ -220,7 +239,7 @@ class Builder(object):
              "GEMM_ST_STATS": stats.tensor.off if stats is not None else -1,
              "GEMM_ST_CG": stats.cg if stats is not None else 1, "GEMM_ST_NNORM": stats.nnorm if stats is not None else 0,
              "GEMM_ST_CHOFF": st_choff, "GEMM_ST_R": (st_R if st_R is not None else stats.R) if stats is not None else 1, "GEMM_ST_WEIGHT": st_weight,
-             "GEMM_STEP": self.step.off}
+             "GEMM_STEP": self.step.off, "GEMM_WP_W": wp_off, "GEMM_WP_NA": wp_na}
         if ev is not None:
             assert ev.C == N and ev.rows * ev_div == A.rows
         if resid is not None:

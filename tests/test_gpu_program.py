@@ -22,6 +22,9 @@ def _teacher_forced(b, m, prog, first, count, rtol, log):
     worst = []
     prog.raw_arena().copy_(torch.from_numpy(m.arena))
     for i in range(first, first + count):
+        if KIND_NAME[b.ops[i][0]] in ("SLIDE_OP_FPS", "SLIDE_OP_KNN"):
+            # index ops are discontinuous in their inputs: give both machines bit-identical inputs
+            prog.raw_arena().copy_(torch.from_numpy(m.arena))
         before = m.arena.copy()
         m.run(i, 1)
         prog.run(i, 1)
@@ -134,7 +137,8 @@ def test_sampler_loop_and_graph_replay(which, golden, pipeline_cfg):
         torch.cuda.synchronize()
         assert int(prog.view(b.step).item()) == T - steps
         results.append(prog.download(h["x"]).cpu().reshape(B, 16, C))
-    assert torch.equal(results[0], results[1])
+    # eager and graph-replayed runs execute the same kernels; only the order of the fp64 statistics atomics varies
+    assert (results[0] - results[1]).abs().max() < 1e-5 * max(1.0, want.abs().max())
     assert (results[0] - want).abs().max() < 2e-4 * max(1.0, want.abs().max())
 
 
