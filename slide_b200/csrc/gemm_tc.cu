@@ -142,8 +142,9 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
                                                              int table_stride, int table_rows) {
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operand tiles need 1024-byte alignment
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // SWIZZLE_128B operand tiles need 1024-byte alignment (pointer arithmetic on the __shared__ array keeps the
+  // address space known to the compiler: LDS/STS instead of generic accesses)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int STAGE_BYTES = tc_stage_bytes(BN);
   constexpr int W_BYTES = BN * TBK * 4;
   const bool has_xfa = a.xfa.stats != nullptr || a.xfa.addvec != nullptr || a.xfa.relu != 0;
@@ -317,14 +318,22 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
   }
 
   if (warp < 4) {
-    const int mw = m0 + warp * 32;                // first row of this warp
-    const int rr_end = min(32, a.M - mw);         // rows of this warp that exist (warp-uniform, may be <= 0)
+    const int mw = m0 + warp * 32;         // first row of this warp
+    const int rr_end = min(32, a.M - mw);  // rows of this warp that exist (warp-uniform, may be <= 0)
     const int sS0 = m0 / a.st_R;
-    // row -> (ev row, resid sample, statistics sample) by counters: no division inside the loops
-    const int ev_row0 = a.ev ? mw / a.evdiv : 0, ev_rem0 = a.ev ? mw % a.evdiv : 0;
-    const int xr_s0 = has_xfr ? mw / a.xfr.R - sR0 : 0, xr_rem0 = has_xfr ? mw % a.xfr.R : 0;
-    const int st_s0 = a.st_stats ? mw / a.st_R - sS0 : 0, st_rem0 = a.st_stats ? mw % a.st_R : 0;
     const bool xr_relu = a.xfr.relu != 0;
+    // Fast path: blocks of 8 rows never straddle an ev row / resid sample / statistics sample.
+    const bool fast = rr_end == 32 && (!a.ev || a.evdiv % 8 == 0) && (!has_xfr || a.xfr.R % 8 == 0) &&
+                      (!a.st_stats || a.st_R % 8 == 0);
+    // per 8-row block: ev row, resid-table row, statistics row (hoisted: no division inside the loops)
+    int ev_off[4], xr_off[4], st_off[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int mb = mw + 8 * q;
+      ev_off[q] = a.ev ? (mb / a.evdiv) * a.evld : 0;
+      xr_off[q] = has_xfr ? (mb / a.xfr.R - sR0) * BN : 0;
+      st_off[q] = a.st_stats ? (mb / a.st_R - sS0) * XF_MAXG * 2 : 0;
+    }
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= a.N) break;
       uint32_t r[32];
@@ -355,59 +364,87 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
       const float bias = (ncol && a.bias) ? __ldg(a.bias + n) : 0.f;
       const int stch = a.st_choff + n;
       const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
-      float *stslot = stacc + (st_s0 * XF_MAXG + (dost ? stch / a.st_cg : 0)) * 2;
-      float ssum = 0.f, ssq = 0.f;
-      const float *evp = a.ev ? a.ev + (size_t)ev_row0 * a.evld + n : nullptr;
-      int ev_rem = ev_rem0;
-      const float4 *xrp = tabR + xr_s0 * BN + c0 + lane;
-      int xr_rem = xr_rem0;
-      int st_rem = st_rem0;
-      const float *resp = a.res ? a.res + (size_t)mw * a.ldr + n : nullptr;
-      float *cp = a.C + (size_t)mw * a.ldc + n;
-      for (int rr = 0; rr < rr_end; ++rr) {
+      const int stg = dost ? stch / a.st_cg : 0;
+      if (fast) {
         if (ncol) {
-          float v = tbuf[rr * 33 + lane] + bias;
-          if (evp) v += *evp;
-          if (resp) {
-            float x = *resp;
-            if (has_xfr) {
-              const float4 c = *xrp;
-              x = fmaf(x, c.x, c.y);
-              if (xr_relu) x = fmaxf(x, 0.f);
-              x += c.z;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int rb = 8 * q;
+            const int mb = mw + rb;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = tbuf[(rb + i) * 33 + lane] + bias;
+            if (a.ev) {
+              const float e = a.ev[(size_t)ev_off[q] + n];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += e;
             }
-            v += x;
+            if (a.res) {
+              float x[8];
+              const float *rp = a.res + (size_t)mb * a.ldr + n;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = rp[(size_t)i * a.ldr];
+              if (has_xfr) {
+                const float4 c = tabR[xr_off[q] + c0 + lane];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float y = fmaf(x[i], c.x, c.y);
+                  if (xr_relu) y = fmaxf(y, 0.f);
+                  x[i] = y + c.z;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += x[i];
+            }
+            if (a.act == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (a.act == 2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = act_apply(2, v[i]);
+            }
+            float *cp = a.C + (size_t)mb * a.ldc + n;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cp[(size_t)i * a.ldc] = v[i];
+            if (dost) {
+              float ssum = 0.f, ssq = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                ssum += v[i];
+                ssq = fmaf(v[i], v[i], ssq);
+              }
+              float *slot = stacc + st_off[q] + stg * 2;
+              atomicAdd(slot, ssum);
+              atomicAdd(slot + 1, ssq);
+            }
           }
-          v = act_apply(a.act, v);
-          *cp = v;
-          ssum += v;
-          ssq = fmaf(v, v, ssq);
         }
-        // advance the row counters (warp-uniform)
-        cp += a.ldc;
-        if (resp) resp += a.ldr;
-        if (evp && ++ev_rem == a.evdiv) {
-          ev_rem = 0;
-          evp += a.evld;
-        }
-        if (has_xfr && ++xr_rem == a.xfr.R) {
-          xr_rem = 0;
-          xrp += BN;
-        }
-        if (a.st_stats && ++st_rem == a.st_R) {
-          st_rem = 0;
-          if (dost) {
-            atomicAdd(stslot, ssum);
-            atomicAdd(stslot + 1, ssq);
+      } else {
+        // general path (ragged tiles / odd sample sizes): one row at a time
+        for (int rr = 0; rr < rr_end; ++rr) {
+          const int m = mw + rr;
+          if (ncol) {
+            float v = tbuf[rr * 33 + lane] + bias;
+            if (a.ev) v += a.ev[(size_t)(m / a.evdiv) * a.evld + n];
+            if (a.res) {
+              float x = a.res[(size_t)m * a.ldr + n];
+              if (has_xfr) {
+                const float4 c = tabR[(m / a.xfr.R - sR0) * BN + c0 + lane];
+                x = fmaf(x, c.x, c.y);
+                if (xr_relu) x = fmaxf(x, 0.f);
+                x += c.z;
+              }
+              v += x;
+            }
+            v = act_apply(a.act, v);
+            a.C[(size_t)m * a.ldc + n] = v;
+            if (dost) {
+              float *slot = stacc + ((m / a.st_R - sS0) * XF_MAXG + stg) * 2;
+              atomicAdd(slot, v);
+              atomicAdd(slot + 1, v * v);
+            }
           }
-          stslot += XF_MAXG * 2;
-          ssum = 0.f;
-          ssq = 0.f;
         }
-      }
-      if (dost && st_rem != 0) {  // rows left over since the last sample boundary
-        atomicAdd(stslot, ssum);
-        atomicAdd(stslot + 1, ssq);
       }
       __syncwarp();
     }
