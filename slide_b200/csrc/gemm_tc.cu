@@ -108,12 +108,25 @@ __host__ __device__ constexpr int tc_epi_bytes(int BN) { return 4 * 32 * 33 * 4 
 __host__ __device__ constexpr int tc_stages_bytes(int BN, int STAGES) {
   return STAGES * tc_stage_bytes(BN) > tc_epi_bytes(BN) ? STAGES * tc_stage_bytes(BN) : tc_epi_bytes(BN);
 }
-constexpr int TC_CTRL_BYTES = 256 + XF_MAXS * XF_MAXG * 2 * 4;
+constexpr int TC_CTRL_BYTES = 256 + XF_MAXS * XF_MAXG * 2 * 4 + XF_MAXS * XF_MAXG * 8;  // barriers | stats | (mean, rstd)
 
 // Fill a transform table: entry (sl, k) = (scale, shift, add, 0) so that y = relu?(x*scale + shift) + add.
-__device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, int s0, int ns, int ncols, int col0,
-                                              int stride, int step, int tid, int nthreads) {
+// Two phases so that the fp64 part runs once per (sample, group), not once per column: `mr` (>= ns * XF_MAXG
+// float2, shared) receives (mean, rstd); the caller's CTA must call this with all `nthreads` threads.
+__device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, float2 *mr, int s0, int ns, int ncols,
+                                              int col0, int stride, int step, int tid, int nthreads) {
   const int G = x.stats ? x.nnorm / x.cg : 1;
+  if (x.stats) {
+    for (int e = tid; e < ns * G; e += nthreads) {
+      const int sl = e / G, g = e - sl * G;
+      const double *st = x.stats + ((size_t)(s0 + sl) * G + g) * 2;
+      const double m = st[0] * (double)x.inv_count;
+      double var = st[1] * (double)x.inv_count - m * m;
+      var = var < 0.0 ? 0.0 : var;
+      mr[sl * XF_MAXG + g] = make_float2((float)m, (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS)));
+    }
+    __syncthreads();
+  }
   for (int e = tid; e < ns * ncols; e += nthreads) {
     const int sl = e / ncols, kk = e - sl * ncols;
     const int k = col0 + kk;
@@ -121,13 +134,9 @@ __device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, int s0,
     if (x.stats) {
       const int ch = x.choff + k;
       if (ch < x.nnorm) {
-        const double *st = x.stats + ((size_t)(s0 + sl) * G + ch / x.cg) * 2;
-        const double m = st[0] * (double)x.inv_count;
-        double var = st[1] * (double)x.inv_count - m * m;
-        var = var < 0.0 ? 0.0 : var;
-        const float rstd = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS));
-        scale = rstd * __ldg(x.gamma + ch);
-        shift = __ldg(x.beta + ch) - (float)m * scale;
+        const float2 v = mr[sl * XF_MAXG + ch / x.cg];
+        scale = v.y * __ldg(x.gamma + ch);
+        shift = __ldg(x.beta + ch) - v.x * scale;
       }
     }
     if (x.addvec) {
@@ -156,6 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
   uint64_t *accum_bar = empty_bar + STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
   float *stacc = reinterpret_cast<float *>(ctrl + 256);
+  float2 *mrbuf = reinterpret_cast<float2 *>(ctrl + 256 + XF_MAXS * XF_MAXG * 2 * 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
   }
   const int sA0 = m0 / a.xfa.R;
   if (has_xfa)
-    fill_xf_table(a.xfa, tabA, sA0, mlast / a.xfa.R - sA0 + 1, a.K, 0, table_stride, step, tid, TC_THREADS);
+    fill_xf_table(a.xfa, tabA, mrbuf, sA0, mlast / a.xfa.R - sA0 + 1, a.K, 0, table_stride, step, tid, TC_THREADS);
   if (a.st_stats)
     for (int e = tid; e < XF_MAXS * XF_MAXG * 2; e += TC_THREADS) stacc[e] = 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -313,7 +323,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
   __syncthreads();
   if (has_xfr) {
     const int ncols = min(BN, a.N - n0);
-    fill_xf_table(a.xfr, tabR, sR0, mlast / a.xfr.R - sR0 + 1, ncols, n0, BN, step, tid, TC_THREADS);
+    fill_xf_table(a.xfr, tabR, mrbuf, sR0, mlast / a.xfr.R - sR0 + 1, ncols, n0, BN, step, tid, TC_THREADS);
     __syncthreads();  // has_xfr is uniform over the CTA
   }
 
@@ -325,6 +335,11 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
     // Fast path: blocks of 8 rows never straddle an ev row / resid sample / statistics sample.
     const bool fast = rr_end == 32 && (!a.ev || a.evdiv % 8 == 0) && (!has_xfr || a.xfr.R % 8 == 0) &&
                       (!a.st_stats || a.st_R % 8 == 0);
+    // GroupNorm groups are st_cg consecutive channels.  When st_cg is a power of two and the group grid is aligned
+    // with this warp's 32-column chunks, the lanes of a group are reduced with shuffles before the shared atomics.
+    const int st_seg = a.st_cg < 32 ? a.st_cg : 32;
+    const bool st_pow2 = a.st_stats && (a.st_cg & (a.st_cg - 1)) == 0 && ((a.st_choff + n0) % st_seg) == 0 &&
+                         (a.st_nnorm % st_seg) == 0;
     // per 8-row block: ev row, resid-table row, statistics row (hoisted: no division inside the loops)
     int ev_off[4], xr_off[4], st_off[4];
 #pragma unroll
@@ -366,7 +381,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
       const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
       const int stg = dost ? stch / a.st_cg : 0;
       if (fast) {
-        if (ncol) {
+        float ssum = 0.f, ssq = 0.f;
+        {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int rb = 8 * q;
@@ -375,7 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = tbuf[(rb + i) * 33 + lane] + bias;
             if (a.ev) {
-              const float e = a.ev[(size_t)ev_off[q] + n];
+              const float e = ncol ? a.ev[(size_t)ev_off[q] + n] : 0.f;
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += e;
             }
@@ -383,7 +399,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
               float x[8];
               const float *rp = a.res + (size_t)mb * a.ldr + n;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = rp[(size_t)i * a.ldr];
+              for (int i = 0; i < 8; ++i) x[i] = ncol ? rp[(size_t)i * a.ldr] : 0.f;
               if (has_xfr) {
                 const float4 c = tabR[xr_off[q] + c0 + lane];
 #pragma unroll
@@ -403,19 +419,39 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = act_apply(2, v[i]);
             }
-            float *cp = a.C + (size_t)mb * a.ldc + n;
+            if (ncol) {
+              float *cp = a.C + (size_t)mb * a.ldc + n;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cp[(size_t)i * a.ldc] = v[i];
-            if (dost) {
-              float ssum = 0.f, ssq = 0.f;
+              for (int i = 0; i < 8; ++i) cp[(size_t)i * a.ldc] = v[i];
+            }
+            if (a.st_stats) {  // warp-uniform
+              if (dost) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                ssum += v[i];
-                ssq = fmaf(v[i], v[i], ssq);
+                for (int i = 0; i < 8; ++i) {
+                  ssum += v[i];
+                  ssq = fmaf(v[i], v[i], ssq);
+                }
               }
-              float *slot = stacc + st_off[q] + stg * 2;
-              atomicAdd(slot, ssum);
-              atomicAdd(slot + 1, ssq);
+              // flush when the next block belongs to another sample (or this is the last block)
+              if (q == 3 || st_off[q + 1] != st_off[q]) {
+                float rs = ssum, rq = ssq;
+                bool leader = dost;
+                if (st_pow2) {
+                  // lanes of one GroupNorm group are st_cg consecutive columns (aligned): segmented butterfly sum
+                  for (int d = 1; d < st_seg; d <<= 1) {
+                    rs += __shfl_xor_sync(0xffffffffu, rs, d);
+                    rq += __shfl_xor_sync(0xffffffffu, rq, d);
+                  }
+                  leader = dost && (lane & (st_seg - 1)) == 0;
+                }
+                if (leader) {
+                  float *slot = stacc + st_off[q] + stg * 2;
+                  atomicAdd(slot, rs);
+                  atomicAdd(slot + 1, rq);
+                }
+                ssum = 0.f;
+                ssq = 0.f;
+              }
             }
           }
         }
