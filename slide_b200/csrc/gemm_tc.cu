@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
   float2 *mrbuf = reinterpret_cast<float2 *>(ctrl + 256 + XF_MAXS * XF_MAXG * 2 * 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;  // N tiles of one row tile are adjacent: A stays in L2
   const int mlast = min(m0 + TBM, a.M) - 1;
   const int step = a.step ? *a.step : 0;
   const int num_kb = (a.K + TBK - 1) / TBK;
@@ -236,11 +236,23 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
             : "memory");
       }
       const int k = kb * TBK + chunk * 4;
+      float4 tc[4];
+      if (has_xfa && table_rows == 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) tc[u] = tabA[k + u];  // the table is padded to a multiple of TBK entries
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rbase + 16 * i;
         float v[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
-        if (has_xfa && rvalid[i]) {
+        if (has_xfa && table_rows == 1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float y = fmaf(v[u], tc[u].x, tc[u].y);
+            if (relu) y = fmaxf(y, 0.f);
+            v[u] = y + tc[u].z;
+          }
+        } else if (has_xfa && rvalid[i]) {
           const float4 *t = tabA + trow[i] + kb * TBK;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -540,7 +552,8 @@ static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t
     if (e != cudaSuccess) return cuda_rc(e);
     configured = true;
   }
-  dim3 grid(ceil_div(a.M, TBM), ceil_div(a.N, BN));
+  dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, TBM));
+  if (grid.y > 65535) return SLIDE_ERR_UNSUPPORTED;
   gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, total, st>>>(a, Wp, wp_na, stride, rows);
   return after_launch();
 }
