@@ -17,6 +17,8 @@
 // CTA = 160 threads: warps 0-3 produce A, then run the epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4
 // allocates TMEM and issues the MMAs.  Shared memory is sized so that two CTAs share an SM: one CTA's epilogue
 // overlaps the other's main loop.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "program.cuh"
 
@@ -24,8 +26,9 @@ namespace slide {
 
 constexpr int TBM = 128;  // rows per CTA tile (UMMA M)
 constexpr int TBK = 32;   // fp32 elements per K block = one 128-byte swizzle row
-constexpr int TC_THREADS = 160;
-constexpr int TC_PRODUCERS = 128;
+constexpr int TC_PWARPS = 8;                    // producer / epilogue warps
+constexpr int TC_PRODUCERS = TC_PWARPS * 32;    // 256 threads: 8 chunks x 32 row slots, 4 rows each
+constexpr int TC_THREADS = TC_PRODUCERS + 32;   // + warp 8: TMEM allocation and MMA issue
 constexpr int TC_TABLE_BUDGET = 40 * 1024;  // bytes of shared memory for the A transform table
 constexpr int TC_MAX_DYN_SMEM = 227 * 1024;
 
@@ -104,7 +107,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 // Shared-memory carve-up (bytes from the 1024-aligned base): operand stages | A transform table | control.
 // After the main loop the stage area is reused for the epilogue's transpose buffers and resid transform table.
 __host__ __device__ constexpr int tc_stage_bytes(int BN) { return (TBM + BN) * TBK * 4; }
-__host__ __device__ constexpr int tc_epi_bytes(int BN) { return 4 * 32 * 33 * 4 + XF_MAXS * BN * 16; }
+__host__ __device__ constexpr int tc_epi_bytes(int BN) { return TC_PWARPS * 32 * 33 * 4 + XF_MAXS * BN * 16; }
 __host__ __device__ constexpr int tc_stages_bytes(int BN, int STAGES) {
   return STAGES * tc_stage_bytes(BN) > tc_epi_bytes(BN) ? STAGES * tc_stage_bytes(BN) : tc_epi_bytes(BN);
 }
@@ -148,8 +151,10 @@ __device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, float2 
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
-                                                             int table_stride, int table_rows) {
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
+                                                             int table_stride, int table_rows, int dbg) {
+  // dbg (SLIDE_TC_DEBUG, profiling only -- results are wrong when set): 1 = no W copies, 2 = no A stores,
+  // 4 = no epilogue, 8 = no MMA
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment (pointer arithmetic on the __shared__ array keeps the
   // address space known to the compiler: LDS/STS instead of generic accesses)
@@ -175,13 +180,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(full_bar + s), TC_PRODUCERS + 1);  // 128 A producers + the W bulk copy's expect_tx arrive
+      mbar_init(smem_u32(full_bar + s), TC_PRODUCERS + 1);  // A producers + the W bulk copy's expect_tx arrive
       mbar_init(smem_u32(empty_bar + s), 1);
     }
     mbar_init(smem_u32(accum_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == TC_PWARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)(BN < 32 ? 32 : BN))
                  : "memory");
@@ -198,42 +203,49 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
   const uint32_t tmem_base = *tmem_slot;
 
   bool ok = true;
-  if (warp < 4) {
+  if (warp < TC_PWARPS) {
     // ------------------------------------------------------------------------------------- A producers
     const int chunk = tid & 7;   // 16-byte chunk within the 128-byte K row
-    const int rbase = tid >> 3;  // 0..15; this thread owns rows rbase + 16 i, i = 0..7
-    const float *arow[8];
-    int trow[8];  // offset of the row's sample in the transform table
-    bool rvalid[8];
+    const int rbase = tid >> 3;  // 0..31; this thread owns rows rbase + 32 i, i = 0..3
+    const float *arow[4];
+    int trow[4];  // offset of the row's sample in the transform table
+    bool rvalid[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + rbase + 16 * i;
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + rbase + 32 * i;
       rvalid[i] = m < a.M;
       arow[i] = a.A + (size_t)(rvalid[i] ? m : 0) * a.lda + chunk * 4;
       trow[i] = has_xfa && rvalid[i] ? (m / a.xfa.R - sA0) * table_stride + chunk * 4 : 0;
     }
     const bool relu = a.xfa.relu != 0;
-    float4 va[8];
+    // global loads run two K blocks ahead of the shared-memory stores (two register buffers)
+    auto load = [&](float4(&buf)[4], int kb) {
+      const int k = kb * TBK + chunk * 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rvalid[i] && chunk * 4 < a.K) va[i] = *reinterpret_cast<const float4 *>(arow[i]);
-    }
-    for (int kb = 0; kb < num_kb; ++kb) {
+      for (int i = 0; i < 4; ++i) {
+        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kb < num_kb && rvalid[i] && k < a.K) buf[i] = *reinterpret_cast<const float4 *>(arow[i] + (size_t)kb * TBK);
+      }
+    };
+    auto process = [&](float4(&buf)[4], int kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
       if (ok) ok = mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
       uint8_t *sa = smem + (size_t)s * STAGE_BYTES;
       if (tid == 0) {
-        // weights: one bulk copy of the pre-tiled, pre-swizzled (N tile, K block); completes on full_bar[s]
         const uint32_t bar = smem_u32(full_bar + s);
-        mbar_arrive_expect_tx(bar, (uint32_t)W_BYTES);
-        const float *src = Wp + ((size_t)kb * wp_na + (size_t)(n0 >> 3)) * 256;
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                smem_u32(sa + TBM * TBK * 4)),
-            "l"(src), "r"((uint32_t)W_BYTES), "r"(bar)
-            : "memory");
+        if (dbg & 1) {
+          mbar_arrive(bar);
+        } else {
+          // weights: one bulk copy of the pre-tiled, pre-swizzled (N tile, K block); completes on full_bar[s]
+          mbar_arrive_expect_tx(bar, (uint32_t)W_BYTES);
+          const float *src = Wp + ((size_t)kb * wp_na + (size_t)(n0 >> 3)) * 256;
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                  smem_u32(sa + TBM * TBK * 4)),
+              "l"(src), "r"((uint32_t)W_BYTES), "r"(bar)
+              : "memory");
+        }
       }
       const int k = kb * TBK + chunk * 4;
       float4 tc[4];
@@ -242,9 +254,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
         for (int u = 0; u < 4; ++u) tc[u] = tabA[k + u];  // the table is padded to a multiple of TBK entries
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rbase + 16 * i;
-        float v[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
+      for (int i = 0; i < 4; ++i) {
+        const int r = rbase + 32 * i;
+        float v[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
         if (has_xfa && table_rows == 1) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -268,20 +280,26 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
         for (int u = 0; u < 4; ++u)
           if (k + u >= a.K) v[u] = 0.f;
         const uint4 o = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
-        *reinterpret_cast<uint4 *>(sa + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
+        if (!(dbg & 2)) *reinterpret_cast<uint4 *>(sa + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
       }
-      // next K block's global loads go out now and overlap this stage's MMA
-      if (kb + 1 < num_kb) {
-        const int kn = k + TBK;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rvalid[i] && kn < a.K) va[i] = *reinterpret_cast<const float4 *>(arow[i] + (size_t)(kb + 1) * TBK);
-        }
-      }
+    };
+    auto publish = [&](int kb) {
       // make the generic-proxy writes visible to the tensor core (async proxy), then signal
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(smem_u32(full_bar + s));
+      mbar_arrive(smem_u32(full_bar + (kb % STAGES)));
+    };
+    float4 bufA[4], bufB[4];
+    load(bufA, 0);
+    load(bufB, 1);
+    for (int kb = 0; kb < num_kb; kb += 2) {
+      process(bufA, kb);
+      load(bufA, kb + 2);
+      publish(kb);
+      if (kb + 1 < num_kb) {
+        process(bufB, kb + 1);
+        load(bufB, kb + 3);
+        publish(kb + 1);
+      }
     }
   } else {
     // ------------------------------------------------------------------------------------- MMA issuer
@@ -295,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const uint64_t da = make_smem_desc(sa);
         const uint64_t db = make_smem_desc(sa + TBM * TBK * 4);
-        if (ok) {
+        if (ok && !(dbg & 8)) {
 #pragma unroll
           for (int kk = 0; kk < TBK / 8; ++kk) {
             const uint32_t accum = (kb > 0 || kk > 0) ? 1u : 0u;
@@ -323,13 +341,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
   }
 
   // ------------------------------------------------------------------------------------------- epilogue
-  if (warp < 4) {
+  if (warp < TC_PWARPS) {
     if (ok) ok = mbar_wait(smem_u32(accum_bar), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   // every stage buffer is dead now (all MMAs completed before accum_bar fired): reuse the area
-  float *tbuf = reinterpret_cast<float *>(smem) + warp * (32 * 33);
-  float4 *tabR = reinterpret_cast<float4 *>(smem + 4 * 32 * 33 * 4);
+  float *tbuf = reinterpret_cast<float *>(smem) + (warp < TC_PWARPS ? warp : 0) * (32 * 33);
+  float4 *tabR = reinterpret_cast<float4 *>(smem + TC_PWARPS * 32 * 33 * 4);
   const bool has_xfr = a.res && (a.xfr.stats != nullptr || a.xfr.addvec != nullptr || a.xfr.relu != 0);
   const int sR0 = m0 / a.xfr.R;
   __syncthreads();
@@ -339,8 +357,11 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
     __syncthreads();  // has_xfr is uniform over the CTA
   }
 
-  if (warp < 4) {
-    const int mw = m0 + warp * 32;         // first row of this warp
+  if (warp < TC_PWARPS) {
+    // warp w drains TMEM lanes 32 (w & 3) .. +31 (the hardware's lane window of warp w % 4); the two warps that share
+    // a lane window split the 32-column chunks: even chunks to warps 0-3, odd chunks to warps 4-7
+    const int lq = warp & 3, cpar = warp >> 2;
+    const int mw = m0 + lq * 32;           // first row of this warp
     const int rr_end = min(32, a.M - mw);  // rows of this warp that exist (warp-uniform, may be <= 0)
     const int sS0 = m0 / a.st_R;
     const bool xr_relu = a.xfr.relu != 0;
@@ -361,10 +382,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
       xr_off[q] = has_xfr ? (mb / a.xfr.R - sR0) * BN : 0;
       st_off[q] = a.st_stats ? (mb / a.st_R - sS0) * XF_MAXG * 2 : 0;
     }
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= a.N) break;
+    for (int c0 = 32 * cpar; c0 < BN; c0 += 64) {
+      if (n0 + c0 >= a.N || (dbg & 4)) break;
       uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
       if (ok) {
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -509,7 +530,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(GemmArgs a, const f
       if (v != 0.f) atomicAdd(a.st_stats + ((size_t)(sS0 + sl) * G) * 2 + rem, (double)v * (double)a.st_weight);
     }
   }
-  if (warp == 4) {
+  if (warp == TC_PWARPS) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)(BN < 32 ? 32 : BN))
                  : "memory");
@@ -554,23 +575,31 @@ static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t
   }
   dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, TBM));
   if (grid.y > 65535) return SLIDE_ERR_UNSUPPORTED;
-  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, total, st>>>(a, Wp, wp_na, stride, rows);
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char *e = getenv("SLIDE_TC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, total, st>>>(a, Wp, wp_na, stride, rows, dbg);
   return after_launch();
 }
 
 int launch_gemm_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
-  // Widest N tile that still gives every SM about two CTAs; small problems take narrow tiles for parallelism.
+  // Tile width.  Large problems (more tiles than one wave of 2 CTAs x 148 SMs) take the widest tile that does not
+  // pad N by more than 2x: fewest re-reads of A.  Small problems are latency-bound per CTA (prologue + a short K
+  // loop), so they take the narrowest tile that still fits in ONE wave: same critical path, less epilogue each.
   const int mt = ceil_div(a.M, TBM);
-  const int want = 2 * 148;
-  int bn = 32;
-  if (a.N > 128 && mt * ceil_div(a.N, 256) >= want)
-    bn = 256;
-  else if (a.N > 64 && mt * ceil_div(a.N, 128) >= want)
-    bn = 128;
-  else if (a.N > 32 && mt * ceil_div(a.N, 64) >= want)
-    bn = 64;
-  else if (a.N > 32 && mt * ceil_div(a.N, 32) < want / 4)
-    bn = 64;  // tiny problem either way: fewer, fatter tiles
+  const int wave = 2 * 148;
+  const int widest = a.N > 128 ? 256 : a.N > 64 ? 128 : a.N > 32 ? 64 : 32;
+  int bn = widest;
+  if (mt * ceil_div(a.N, widest) < wave) {
+    for (int c = 32; c <= widest; c <<= 1) {
+      if (mt * ceil_div(a.N, c) <= wave) {
+        bn = c;
+        break;
+      }
+    }
+  }
   switch (bn) {
     case 256: return launch_tc<256, 2>(a, Wp, wp_na, st);
     case 128: return launch_tc<128, 3>(a, Wp, wp_na, st);

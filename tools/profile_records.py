@@ -40,6 +40,19 @@ def main():
     prog.set_step(501)
     prog.run(first, count)
     torch.cuda.synchronize()
+    only = os.environ.get("PROFILE_ONLY")
+    if only:
+        # ncu mode: `ncu --profile-from-start off ...` captures just these records (one launch each, cold L2)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        for i in [int(v) for v in only.split(",")]:
+            flush.zero_()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            prog.run(first + i, 1)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            print("profiled record", i, b.ops[first + i][3])
+        return
     rows = []
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for i in range(first, first + count):
