@@ -142,31 +142,12 @@ class SlidePipeline(object):
     def draw_host_inputs(self, labels):
         """labels: CPU int tensor (global_batch,).  Draws, on the CPU default generator and in the reference's
         order, everything the reference draws on the host; stores this rank's slices in pinned buffers."""
-        B, T = self.B, self.T_pos
-        lo, hi = self.rank * self.Bl, (self.rank + 1) * self.Bl
-        size = (B, 16, 3)
-        if (B * 48) % 16 == 0:
-            big = torch.normal(0, 1, size=(T,) + size)  # == T sequential torch.normal(0,1,size) calls (chunks of 16)
-        else:
-            big = torch.stack([torch.normal(0, 1, size=size) for _ in range(T)])
-        # big[0] = x_T; big[1+i] = z added after step t = T-1-i (i = 0..T-2)
-        nz = self._pos_noise_host.view(T, self.Bl, 16, 3)
-        nz[0].zero_()
-        nz[1:] = torch.flip(big[1:, lo:hi], dims=[0])
-        self._pos_xT_host.copy_(big[0, lo:hi])
-        self._lat_xT_host.copy_(torch.randn(B, 16, self.lat.C)[lo:hi])
-        self._labels_host.copy_(labels[lo:hi])
-        # pytorch3d 0.7.0: one randint per cloud, batch order, level after level
-        n_in = 16
-        for lvl, dcfg in enumerate(self.cfg["autoencoder"]["decoders"]):
-            up = dcfg["upsampling_setting"]
-            P = n_in * up["point_upsample_factor"]
-            if P > up["num_output_points"]:  # FPS (and its draws) only happen when points must be dropped
-                draws = torch.tensor([int(torch.randint(high=P, size=(1,)).item()) for _ in range(B)])
-                self._starts_host[lvl].copy_(draws[lo:hi])
-            else:
-                self._starts_host[lvl].zero_()
-            n_in = up["num_output_points"]
+        d = draw_host_inputs(self.cfg, self.B, self.rank, self.world, labels)
+        self._pos_noise_host.view(self.T_pos, self.Bl, 16, 3).copy_(d["pos_noise"])
+        self._pos_xT_host.copy_(d["pos_xT"])
+        self._lat_xT_host.copy_(d["lat_xT"])
+        self._labels_host.copy_(d["labels"])
+        self._starts_host.copy_(d["starts"])
 
     # ---- device path -----------------------------------------------------------------------------------
     def stage_inputs(self):
@@ -235,6 +216,39 @@ class SlidePipeline(object):
                 (self.Bl // self.dec.chunk) * self.dec.launches_per_chunk())
 
 
+def draw_host_inputs(cfg, B, rank, world, labels):
+    """Everything the reference draws on the CPU generator, for the FULL batch and in the reference's call order,
+    sliced to rank `rank` of `world` (so results do not depend on the world size):
+      pos_xT (Bl,16,3), pos_noise (T,Bl,16,3) with pos_noise[t] = the z added after step t (util.py:225,253),
+      lat_xT (Bl,16,3+F) (diffusion.py:373), starts (levels,Bl) pytorch3d FPS start indices, labels (Bl,)."""
+    Bl = B // world
+    lo, hi = rank * Bl, (rank + 1) * Bl
+    T = cfg["position_ddpm"]["diffusion_config"]["T"]
+    C_lat = 3 + cfg["latent_ddpm"]["pointnet_config"]["in_fea_dim"]
+    size = (B, 16, 3)
+    if (B * 48) % 16 == 0:
+        big = torch.normal(0, 1, size=(T,) + size)  # == T sequential torch.normal(0,1,size) calls (chunks of 16)
+    else:
+        big = torch.stack([torch.normal(0, 1, size=size) for _ in range(T)])
+    # big[0] = x_T; big[1+i] = z added after step t = T-1-i (i = 0..T-2)
+    pos_noise = torch.zeros(T, Bl, 16, 3)
+    pos_noise[1:] = torch.flip(big[1:, lo:hi], dims=[0])
+    lat_xT = torch.randn(B, 16, C_lat)[lo:hi].clone()
+    decs = cfg["autoencoder"]["decoders"]
+    starts = torch.zeros(len(decs), Bl, dtype=torch.int64)
+    n_in = 16
+    for lvl, dcfg in enumerate(decs):
+        up = dcfg["upsampling_setting"]
+        P = n_in * up["point_upsample_factor"]
+        if P > up["num_output_points"]:  # FPS (and its draws) only happen when points must be dropped
+            # pytorch3d 0.7.0: one randint per cloud, batch order, level after level
+            draws = torch.tensor([int(torch.randint(high=P, size=(1,)).item()) for _ in range(B)])
+            starts[lvl] = draws[lo:hi]
+        n_in = up["num_output_points"]
+    return {"pos_xT": big[0, lo:hi].clone(), "pos_noise": pos_noise, "lat_xT": lat_xT, "starts": starts,
+            "labels": labels[lo:hi].clone()}
+
+
 def all_gather_outputs(local_out, world):
     """The path's single collective: one NCCL all-gather of the (B/W, 2048, 6) clouds (replaces the reference's
     per-rank .npz files + rank-0 concatenation, pointnet2/mesh_evaluation.py:42,156-186)."""
@@ -242,5 +256,8 @@ def all_gather_outputs(local_out, world):
     if world == 1:
         return local_out
     full = torch.empty((world,) + tuple(local_out.shape), device=local_out.device, dtype=local_out.dtype)
-    dist.all_gather_into_tensor(full.view(-1), local_out.reshape(-1))
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(full.view(-1), local_out.reshape(-1).contiguous())
+    else:  # gloo (CPU tests)
+        dist.all_gather(list(full.unbind(0)), local_out.contiguous())
     return full.view((-1,) + tuple(local_out.shape[1:]))

@@ -1,0 +1,59 @@
+"""Host-side sharding logic on CPU: world-size invariance of the RNG slicing and the output all-gather (gloo, 2 ranks)."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from slide_b200 import pipeline, weights
+
+
+def _small_cfg():
+    cfg = weights.load_json("pipeline_chair.json")
+    cfg["position_ddpm"]["diffusion_config"]["T"] = 5  # keep the CPU draw small; slicing logic is T-independent
+    return cfg
+
+
+def test_noise_slices_do_not_depend_on_world_size():
+    cfg = _small_cfg()
+    B = 8
+    labels = torch.full((B,), cfg["label"], dtype=torch.long)
+    torch.manual_seed(123)
+    full = pipeline.draw_host_inputs(cfg, B, 0, 1, labels)
+    parts = []
+    for r in range(2):
+        torch.manual_seed(123)
+        parts.append(pipeline.draw_host_inputs(cfg, B, r, 2, labels))
+    for key in ("pos_xT", "lat_xT", "labels"):
+        assert torch.equal(full[key], torch.cat([p[key] for p in parts], dim=0)), key
+    for key in ("pos_noise", "starts"):
+        assert torch.equal(full[key], torch.cat([p[key] for p in parts], dim=1)), key
+    # reference order: x_T first, then one z per step from T-1 down to 1, nothing at t = 0
+    torch.manual_seed(123)
+    x_T = torch.normal(0, 1, size=(B, 16, 3))
+    z = [torch.normal(0, 1, size=(B, 16, 3)) for _ in range(4)]
+    assert torch.equal(full["pos_xT"], x_T)
+    assert torch.equal(full["pos_noise"][4], z[0]) and torch.equal(full["pos_noise"][1], z[3])
+    assert full["pos_noise"][0].abs().max() == 0
+    assert int(full["starts"].max()) < 4096 and full["starts"].shape == (3, B)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    local = torch.full((3, 4, 6), float(rank)) + torch.arange(3).view(3, 1, 1)
+    full = pipeline.all_gather_outputs(local, world)
+    ok = full.shape == (3 * world, 4, 6) and all(
+        torch.equal(full[3 * r:3 * r + 3], torch.full((3, 4, 6), float(r)) + torch.arange(3).view(3, 1, 1))
+        for r in range(world))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_all_gather_two_ranks_gloo():
+    world = 2
+    port = 29500 + (os.getpid() % 500)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert out[0] and out[1]
