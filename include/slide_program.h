@@ -49,7 +49,8 @@ enum slide_op_kind {
   SLIDE_OP_KNN = 2,          /* K nearest neighbours (pytorch3d knn_points semantics), i32 indices + squared dists */
   SLIDE_OP_GROUP = 3,        /* build grouped rows [f_j | geometry] (QueryAndGroup 'nn' / group_knn) */
   SLIDE_OP_GEMM = 4,         /* C = act(xf(A) W^T + bias + addvec + xf(resid)), statistics of C */
-  SLIDE_OP_SOFTMAX_WSUM = 5, /* out[i,c] = sum_k xf(V)[i,k,c] * softmax_k(S[i,k,c])  (AttentionModule tail) */
+  SLIDE_OP_SOFTMAX_WSUM = 5, /* out[i,c] = sum_k xf(V)[i,k,c] * softmax_k(S[i,k,c])  (AttentionModule tail; the
+                                lowering normally fuses this into the score GEMM, see GEMM_SMK) */
   SLIDE_OP_COPY_COLS = 6,    /* dst[:, 0:n] = src[:, 0:n] */
   SLIDE_OP_DDPM_UPDATE = 7,  /* one ancestral sampling update (position or latent flavour) */
   SLIDE_OP_FPS = 8,          /* furthest point sampling (pointnet2_ops._ext or pytorch3d semantics) */
@@ -109,6 +110,10 @@ enum slide_gemm_field {
   GEMM_WP_W,  /* tensor-core copy of W (or -1): TF32-rounded, tiled [ceil(K/32)][WP_NA][8 rows][128 B], each
                  8x128 B atom in the SWIZZLE_128B pattern, zero padded -- one bulk copy per (N tile, K block) */
   GEMM_WP_NA, /* 8-row atoms per K block in that copy (N rounded up to a multiple of 256, / 8) */
+  GEMM_SMK,   /* > 0: fused AttentionModule tail.  The GEMM result S = xfA(A) W^T + bias is a score tensor; soft-max
+                 is taken over every group of SMK consecutive rows (the neighbours of one point) and applied to the
+                 VALUE tensor given by RES / XFR:  C[g, n] = sum_k xfR(RES)[g*SMK + k, n] * softmax_k(S[g*SMK + k, n]).
+                 C then has M / SMK rows; EV, ACT and ST_* must be unset. */
   GEMM_NFIELD
 };
 

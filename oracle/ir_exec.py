@@ -162,6 +162,13 @@ class Machine(object):
             div = g("GEMM_EVDIV")
             ev = self.A(g("GEMM_EV"), M // div, g("GEMM_EVLD"), N)
             c = c + ev[np.arange(M) // div]
+        smk = g("GEMM_SMK")
+        if smk > 0:
+            val = self.xf(np.array(self.A(g("GEMM_RES"), M, g("GEMM_LDR"), N)), p, V["GEMM_XFR"], step_off)
+            w = torch.softmax(torch.from_numpy(c.astype(np.float32).reshape(M // smk, smk, N)), dim=1).numpy()
+            out = (val.reshape(M // smk, smk, N) * w).sum(axis=1, dtype=np.float32)
+            self.A(g("GEMM_C"), M // smk, g("GEMM_LDC"), N)[...] = out
+            return
         if g("GEMM_RES") >= 0:
             c = c + self.xf(np.array(self.A(g("GEMM_RES"), M, g("GEMM_LDR"), N)), p, V["GEMM_XFR"], step_off)
         act = g("GEMM_ACT")

@@ -1,8 +1,11 @@
 // fp32 FFMA GEMM with the fused prologue / epilogue of SLIDE_OP_GEMM (see slide_program.h).
 //
 // This is the any-shape kernel: tiny K (the 12-channel position-DDPM inputs), N that is not a multiple of 8
-// (3-channel heads), unaligned column views.  Dense, aligned contractions go to gemm_tc.cu (tcgen05).
-//   C = act( xfA(A) W^T + bias + ev[row / evdiv] + xfR(resid) ),  GroupNorm statistics of C accumulated in fp64.
+// (3-channel heads), unaligned column views, ragged M.  Dense, aligned contractions go to gemm_tc.cu (tcgen05).
+//   C = act( xfA(A) W^T + bias + ev[row / evdiv] + xfR(resid) ),  GroupNorm statistics of C accumulated in fp64,
+//   or (GEMM_SMK) C[g] = sum_k xfR(resid)[g*K+k] * softmax_k(xfA(A) W^T + bias)[g*K+k].
+// The 64x64 accumulator tile is staged in shared memory so that the epilogue runs with thread = column:
+// coalesced stores / residual loads, per-column statistics in registers, soft-max down the rows.
 #include "common.cuh"
 #include "program.cuh"
 
@@ -13,6 +16,7 @@ constexpr int SBM = 64, SBN = 64, SBK = 16, STHREADS = 256;
 __global__ void __launch_bounds__(STHREADS) gemm_simt_kernel(GemmArgs a) {
   __shared__ float As[SBK][SBM + 4];
   __shared__ float Ws[SBK][SBN + 4];
+  __shared__ float tile[SBM][SBN + 1];
   __shared__ float2 tabA[XF_MAXS * XF_MAXG];
   __shared__ float2 tabR[XF_MAXS * XF_MAXG];
   __shared__ float stacc[XF_MAXS * XF_MAXG * 2];
@@ -44,12 +48,11 @@ __global__ void __launch_bounds__(STHREADS) gemm_simt_kernel(GemmArgs a) {
   const int lsA = (lm < a.M) ? lm / a.xfa.R : 0;  // sample of the row this thread loads (fixed over the K loop)
   for (int k0 = 0; k0 < a.K; k0 += SBK) {
     {
-      const int m = lm;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int k = k0 + lk + u;
         float v = 0.f;
-        if (m < a.M && k < a.K) v = xf_apply(a.xfa, tabA, sA0, lsA, k, a.A[(size_t)m * a.lda + k], step);
+        if (lm < a.M && k < a.K) v = xf_apply(a.xfa, tabA, sA0, lsA, k, a.A[(size_t)lm * a.lda + k], step);
         As[lk + u][lr] = v;
       }
       const int n = n0 + lr;
@@ -74,31 +77,75 @@ __global__ void __launch_bounds__(STHREADS) gemm_simt_kernel(GemmArgs a) {
     __syncthreads();
   }
 
+  // stage the accumulators: tile[row][col]
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= a.M) continue;
-    const int sR = a.res ? m / a.xfr.R : 0;
-    const int sS = a.st_stats ? m / a.st_R - sS0 : 0;
-    const float *evrow = a.ev ? a.ev + (size_t)(m / a.evdiv) * a.evld : nullptr;
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n >= a.N) continue;
-      float v = acc[i][j];
-      if (a.bias) v += __ldg(a.bias + n);
-      if (evrow) v += evrow[n];
-      if (a.res) v += xf_apply(a.xfr, tabR, sR0, sR, n, a.res[(size_t)m * a.ldr + n], step);
-      v = act_apply(a.act, v);
-      a.C[(size_t)m * a.ldc + n] = v;
-      if (a.st_stats) {
-        const int ch = a.st_choff + n;
-        if (ch < a.st_nnorm) {
-          float *slot = stacc + (sS * XF_MAXG + ch / a.st_cg) * 2;
-          atomicAdd(slot, v);
-          atomicAdd(slot + 1, v * v);
+    for (int j = 0; j < 4; ++j) tile[ty * 4 + i][tx * 4 + j] = acc[i][j];
+  __syncthreads();
+
+  // epilogue: thread = (column c, row quarter rq)
+  const int c = tid & 63, rq = tid >> 6;
+  const int n = n0 + c;
+  const bool ncol = n < a.N;
+  const float bias = (ncol && a.bias) ? __ldg(a.bias + n) : 0.f;
+  const int rows_here = mlast - m0 + 1;
+  if (a.smk > 0) {
+    // fused AttentionModule tail: soft-max over groups of smk rows, reduce the transformed values with it
+    const int K = a.smk;
+    if (ncol) {
+      for (int g0 = rq * K; g0 + K <= rows_here; g0 += 4 * K) {
+        float mx = -INFINITY;
+        for (int k = 0; k < K; ++k) mx = fmaxf(mx, tile[g0 + k][c]);
+        float den = 0.f, o = 0.f;
+        for (int k = 0; k < K; ++k) {
+          const int m = m0 + g0 + k;
+          const float w = expf(tile[g0 + k][c] - mx);  // the bias is common to the group: it cancels in the soft-max
+          const float x = xf_apply(a.xfr, tabR, sR0, m / a.xfr.R, n, a.res[(size_t)m * a.ldr + n], step);
+          den += w;
+          o = fmaf(x, w, o);
+        }
+        a.C[(size_t)((m0 + g0) / K) * a.ldc + n] = o / den;
+      }
+    }
+    return;
+  }
+  {
+    const int r0 = rq * 16;
+    const int ch = a.st_choff + n;
+    const bool dost = a.st_stats && ncol && ch < a.st_nnorm;
+    float ssum = 0.f, ssq = 0.f;
+    int scur = -1;
+    for (int rr = 0; rr < 16; ++rr) {
+      const int m = m0 + r0 + rr;
+      if (m >= a.M) break;
+      if (ncol) {
+        float v = tile[r0 + rr][c] + bias;
+        if (a.ev) v += a.ev[(size_t)(m / a.evdiv) * a.evld + n];
+        if (a.res) v += xf_apply(a.xfr, tabR, sR0, m / a.xfr.R, n, a.res[(size_t)m * a.ldr + n], step);
+        v = act_apply(a.act, v);
+        a.C[(size_t)m * a.ldc + n] = v;
+        if (dost) {
+          const int sm = m / a.st_R - sS0;
+          if (sm != scur) {
+            if (scur >= 0) {
+              float *slot = stacc + (scur * XF_MAXG + ch / a.st_cg) * 2;
+              atomicAdd(slot, ssum);
+              atomicAdd(slot + 1, ssq);
+            }
+            scur = sm;
+            ssum = 0.f;
+            ssq = 0.f;
+          }
+          ssum += v;
+          ssq = fmaf(v, v, ssq);
         }
       }
+    }
+    if (dost && scur >= 0) {
+      float *slot = stacc + (scur * XF_MAXG + ch / a.st_cg) * 2;
+      atomicAdd(slot, ssum);
+      atomicAdd(slot + 1, ssq);
     }
   }
   if (a.st_stats) {
@@ -121,6 +168,7 @@ int launch_gemm_simt(const GemmArgs &a, cudaStream_t st) {
   if (a.res && a.xfr.stats && (!spans_ok(a.xfr.R, SBM) || a.xfr.nnorm / a.xfr.cg > XF_MAXG))
     return SLIDE_ERR_UNSUPPORTED;
   if (a.st_stats && (!spans_ok(a.st_R, SBM) || a.st_nnorm / a.st_cg > XF_MAXG)) return SLIDE_ERR_UNSUPPORTED;
+  if (a.smk > 0 && (SBM % a.smk != 0)) return SLIDE_ERR_UNSUPPORTED;  // neighbour groups must not straddle row tiles
   dim3 grid(ceil_div(a.M, SBM), ceil_div(a.N, SBN));
   if (grid.y > 65535) return SLIDE_ERR_UNSUPPORTED;
   gemm_simt_kernel<<<grid, STHREADS, 0, st>>>(a);

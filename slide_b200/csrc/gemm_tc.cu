@@ -413,7 +413,34 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(GemmArgs a, cons
       const int stch = a.st_choff + n;
       const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
       const int stg = dost ? stch / a.st_cg : 0;
-      if (fast) {
+      if (fast && a.smk > 0) {
+        // fused AttentionModule tail: soft-max down each group of smk rows (the neighbours of one point), applied
+        // to the transformed value rows; one output row per group.  (bias is constant down a column: it cancels.)
+        const int K = a.smk;
+        if (ncol) {
+          for (int g0 = 0; g0 < 32; g0 += K) {
+            float mx = -INFINITY;
+            for (int k = 0; k < K; ++k) mx = fmaxf(mx, tbuf[(g0 + k) * 33 + lane]);
+            const float *vp = a.res + (size_t)(mw + g0) * a.ldr + n;
+            float4 c = make_float4(1.f, 0.f, 0.f, 0.f);
+            if (has_xfr) c = tabR[xr_off[g0 >> 3] + c0 + lane];
+            float den = 0.f, o = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+              const float w = __expf(tbuf[(g0 + k) * 33 + lane] - mx);
+              float x = vp[(size_t)k * a.ldr];
+              if (has_xfr) {
+                x = fmaf(x, c.x, c.y);
+                if (xr_relu) x = fmaxf(x, 0.f);
+                x += c.z;
+              }
+              den += w;
+              o = fmaf(x, w, o);
+            }
+            a.C[(size_t)((mw + g0) / K) * a.ldc + n] = o / den;
+          }
+        }
+      } else if (fast) {
         float ssum = 0.f, ssq = 0.f;
         {
 #pragma unroll
@@ -557,6 +584,8 @@ bool gemm_tc_eligible(const GemmArgs &a, const float *Wp) {
     if (a.xfr.stats && a.xfr.nnorm / a.xfr.cg > XF_MAXG) return false;
   }
   if (a.st_stats && (!spans_ok_tc(a.st_R) || a.st_nnorm / a.st_cg > XF_MAXG)) return false;
+  // fused soft-max: neighbour groups must tile a warp's 32 rows, full row tiles only
+  if (a.smk > 0 && (32 % a.smk != 0 || a.M % TBM != 0 || a.xfr.R % 8 != 0)) return false;
   return true;
 }
 

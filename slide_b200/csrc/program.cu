@@ -396,6 +396,8 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       a.xfa = make_xf(p, q + GEMM_XFA);
       a.xfr = make_xf(p, q + GEMM_XFR);
       a.step = AP<int>(p, q[GEMM_STEP]);
+      a.smk = (int)q[GEMM_SMK];
+      if (a.smk > 0 && (!a.res || a.ev || a.st_stats || a.act || a.M % a.smk)) return SLIDE_ERR_INVALID;
       const float *wp = WP<float>(p, q[GEMM_WP_W]);
       if (p->gemm_backend == 0 && gemm_tc_eligible(a, wp)) return launch_gemm_tc(a, wp, (int)q[GEMM_WP_NA], st);
       return launch_gemm_simt(a, st);

@@ -37,6 +37,7 @@ struct GemmArgs {
   float st_weight;
   XFd xfa, xfr;
   const int *step;
+  int smk;  // > 0: fused soft-max over groups of smk rows, applied to xfr(res); C has M / smk rows (GEMM_SMK)
 };
 
 // Per-CTA table of (mean, rstd) for the samples a row tile touches: [XF_MAXS][XF_MAXG].

@@ -164,11 +164,6 @@ def _lower_attention(ctx, P, q_feat, G, H, npnt, K, out, name):
                   count=npnt * K * cg1), note=name + ".w1k")
     W2, b2 = _conv(b, P.sub("weight_conv.5"))
     Co = W2[2]
-    scores = b.tensor(name + ".scores", npnt * K, Co, B=B)
-    b.gemm(s1, W2, scores, bias=b2,
-           xfa=XF(stats=st2.tensor, cg=cg2, nnorm=nn2, choff=0, gamma=b.weight(P["weight_conv.4.group_norm.weight"]),
-                  beta=b.weight(P["weight_conv.4.group_norm.bias"]), R=npnt * K, count=npnt * K * cg2),
-           note=name + ".w2")
     Wv, bv = _conv(b, P.sub("feat_out_conv.0"))
     v = b.tensor(name + ".v", npnt * K, Co, B=B)
     if att["last_activation"]:
@@ -181,7 +176,12 @@ def _lower_attention(ctx, P, q_feat, G, H, npnt, K, out, name):
         b.gemm(H, Wv, v, bias=bv, note=name + ".v")
         xfv = NO_XF
     assert out.C == Co
-    b.softmax_wsum(scores, v, xfv, out, B * npnt, K, note=name + ".softmax")
+    # scores = weight_conv.5(...) are never written: the GEMM's epilogue takes the soft-max over the K neighbours of
+    # each point and reduces the (normalised, ReLU'ed) values with it (GEMM_SMK)
+    b.gemm(s1, W2, out, bias=b2, resid=v, xfr=xfv, smk=K,
+           xfa=XF(stats=st2.tensor, cg=cg2, nnorm=nn2, choff=0, gamma=b.weight(P["weight_conv.4.group_norm.weight"]),
+                  beta=b.weight(P["weight_conv.4.group_norm.bias"]), R=npnt * K, count=npnt * K * cg2),
+           note=name + ".w2+softmax")
     return out
 
 

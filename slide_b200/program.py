@@ -226,11 +226,15 @@ class Builder(object):
             "GRP_ABS": int(include_abs), "GRP_CENTER": int(include_center), "GRP_B": out.B}, note=note)
 
     def gemm(self, A, W, out, bias=-1, act=None, xfa=NO_XF, ev=None, ev_div=1, resid=None, xfr=NO_XF, stats=None,
-             st_R=None, st_choff=0, st_weight=1, note=""):
+             st_R=None, st_choff=0, st_weight=1, smk=0, note=""):
         """out = act(xfa(A) W^T + bias + ev[row // ev_div] + xfr(resid)); W = (offset, ldw, N, K[, wp_off, wp_na])."""
         woff, ldw, N, K = W[:4]
         wp_off, wp_na = (W[4], W[5]) if len(W) > 4 else (-1, 0)
-        assert A.C == K and out.C == N and A.rows == out.rows, (note, A.C, K, out.C, N, A.rows, out.rows)
+        assert A.C == K and out.C == N, (note, A.C, K, out.C, N)
+        if smk:
+            assert A.rows == out.rows * smk and resid is not None and ev is None and stats is None and act is None
+        else:
+            assert A.rows == out.rows, (note, A.rows, out.rows)
         f = {"GEMM_A": A.off, "GEMM_LDA": A.ld, "GEMM_M": A.rows, "GEMM_K": K, "GEMM_W_W": woff, "GEMM_LDW": ldw,
              "GEMM_N": N, "GEMM_C": out.off, "GEMM_LDC": out.ld, "GEMM_BIAS_W": bias, "GEMM_ACT": ACT[act],
              "GEMM_EV": ev.off if ev is not None else -1, "GEMM_EVLD": ev.ld if ev is not None else 0,
@@ -239,7 +243,7 @@ class Builder(object):
              "GEMM_ST_STATS": stats.tensor.off if stats is not None else -1,
              "GEMM_ST_CG": stats.cg if stats is not None else 1, "GEMM_ST_NNORM": stats.nnorm if stats is not None else 0,
              "GEMM_ST_CHOFF": st_choff, "GEMM_ST_R": (st_R if st_R is not None else stats.R) if stats is not None else 1, "GEMM_ST_WEIGHT": st_weight,
-             "GEMM_STEP": self.step.off, "GEMM_WP_W": wp_off, "GEMM_WP_NA": wp_na}
+             "GEMM_STEP": self.step.off, "GEMM_WP_W": wp_off, "GEMM_WP_NA": wp_na, "GEMM_SMK": smk}
         if ev is not None:
             assert ev.C == N and ev.rows * ev_div == A.rows
         if resid is not None:
