@@ -150,8 +150,8 @@ __device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, float2 
   }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
+template <int BN, int STAGES, bool SMK>
+__global__ void __maxnreg__(112) gemm_tc_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
                                                              int table_stride, int table_rows, int dbg) {
   // dbg (SLIDE_TC_DEBUG, profiling only -- results are wrong when set): 1 = no W copies, 2 = no A stores,
   // 4 = no epilogue, 8 = no MMA
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(GemmArgs a, cons
       const int stch = a.st_choff + n;
       const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
       const int stg = dost ? stch / a.st_cg : 0;
-      if (fast && a.smk > 0) {
+      if (SMK) {
         // fused AttentionModule tail: soft-max down each group of smk rows (the neighbours of one point), applied
         // to the transformed value rows; one output row per group.  (bias is constant down a column: it cancels.)
         const int K = a.smk;
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(GemmArgs a, cons
             a.C[(size_t)((mw + g0) / K) * a.ldc + n] = o / den;
           }
         }
-      } else if (fast) {
+      } else if (!SMK && fast) {
         float ssum = 0.f, ssq = 0.f;
         {
 #pragma unroll
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(GemmArgs a, cons
             }
           }
         }
-      } else {
+      } else if (!SMK) {
         // general path (ragged tiles / odd sample sizes): one row at a time
         for (int rr = 0; rr < rr_end; ++rr) {
           const int m = mw + rr;
@@ -589,15 +589,15 @@ bool gemm_tc_eligible(const GemmArgs &a, const float *Wp) {
   return true;
 }
 
-template <int BN, int STAGES>
-static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
+template <int BN, int STAGES, bool SMK>
+static int launch_tc_impl(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
   const int stride = tc_table_stride(a);
   const int rows = has_xf(a.xfa) ? tc_rows_per_tile(a.xfa.R) : 0;
   const int total = tc_stages_bytes(BN, STAGES) + rows * stride * 16 + TC_CTRL_BYTES + 1024 /* alignment slack */;
   if (total > TC_MAX_DYN_SMEM) return SLIDE_ERR_UNSUPPORTED;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, SMK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TC_MAX_DYN_SMEM);
     if (e != cudaSuccess) return cuda_rc(e);
     configured = true;
@@ -609,8 +609,13 @@ static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t
     const char *e = getenv("SLIDE_TC_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
-  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, total, st>>>(a, Wp, wp_na, stride, rows, dbg);
+  gemm_tc_kernel<BN, STAGES, SMK><<<grid, TC_THREADS, total, st>>>(a, Wp, wp_na, stride, rows, dbg);
   return after_launch();
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
+  return a.smk > 0 ? launch_tc_impl<BN, STAGES, true>(a, Wp, wp_na, st) : launch_tc_impl<BN, STAGES, false>(a, Wp, wp_na, st);
 }
 
 int launch_gemm_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
