@@ -44,6 +44,23 @@ def needs_build():
         return f.read().strip() != _digest()
 
 
+def build_variant(name, defines):
+    """A/B helper for kernel tuning: compile csrc/ with extra -D flags into libslide_b200_<name>.so (select it at
+    run time with SLIDE_B200_LIB=<path>).  Not used by the product path."""
+    nvcc = os.environ.get("NVCC", "nvcc")
+    out = os.path.join(HERE, "libslide_b200_%s.so" % name)
+    objs = []
+    bdir = os.path.join(HERE, "build", name)
+    os.makedirs(bdir, exist_ok=True)
+    for src in _sources():
+        obj = os.path.join(bdir, os.path.basename(src) + ".o")
+        subprocess.check_call([nvcc] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + list(defines) +
+                              ["-c", src, "-o", obj], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        objs.append(obj)
+    subprocess.check_call([nvcc, "-shared", "-o", out] + objs + ["-cudart", "static"])
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ for sm_100a and link libslide_b200.so.  Returns the library path."""
     if not force and not needs_build():

@@ -150,8 +150,11 @@ __device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, float2 
   }
 }
 
+#ifndef TC_MAXNREG
+#define TC_MAXNREG 96  // measured on B200: 96 keeps two 288-thread CTAs per SM (112 and 128 run ~25% slower)
+#endif
 template <int BN, int STAGES, bool SMK>
-__global__ void __maxnreg__(112) gemm_tc_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
+__global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
                                                              int table_stride, int table_rows, int dbg) {
   // dbg (SLIDE_TC_DEBUG, profiling only -- results are wrong when set): 1 = no W copies, 2 = no A stores,
   // 4 = no epilogue, 8 = no MMA

@@ -19,6 +19,8 @@ Algebra used (exact in real arithmetic, fp32 re-association only):
     plus a per-pair GEMM on k (np*K rows): W[q;k] = Wq q + Wk k.  GroupNorm over the concatenation still
     uses the joint statistics (the q rows enter them with weight K).
 """
+import os
+
 import numpy as np
 
 from .program import XF, NO_XF, Builder  # noqa: F401
@@ -176,6 +178,14 @@ def _lower_attention(ctx, P, q_feat, G, H, npnt, K, out, name):
         b.gemm(H, Wv, v, bias=bv, note=name + ".v")
         xfv = NO_XF
     assert out.C == Co
+    if os.environ.get("SLIDE_FUSE_SOFTMAX", "1") == "0":  # A/B switch for tuning: unfused score GEMM + soft-max record
+        scores = b.tensor(name + ".scores", npnt * K, Co, B=B)
+        b.gemm(s1, W2, scores, bias=b2,
+               xfa=XF(stats=st2.tensor, cg=cg2, nnorm=nn2, choff=0, gamma=b.weight(P["weight_conv.4.group_norm.weight"]),
+                      beta=b.weight(P["weight_conv.4.group_norm.bias"]), R=npnt * K, count=npnt * K * cg2),
+               note=name + ".w2")
+        b.softmax_wsum(scores, v, xfv, out, B * npnt, K, note=name + ".softmax")
+        return out
     # scores = weight_conv.5(...) are never written: the GEMM's epilogue takes the soft-max over the K neighbours of
     # each point and reduces the (normalised, ReLU'ed) values with it (GEMM_SMK)
     b.gemm(s1, W2, out, bias=b2, resid=v, xfr=xfv, smk=K,
