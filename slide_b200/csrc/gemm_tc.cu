@@ -10,6 +10,10 @@
 //                  normalisation pass over HBM).  Four producer warps move A global -> registers (transform,
 //                  round-to-nearest TF32) -> shared memory in the K-major SWIZZLE_128B layout, with the next
 //                  K block's global loads already in flight while the current one is transformed and stored.
+//                  When A needs no transform (the grouped inputs and residual-summed tensors: q/k/v projections,
+//                  first convs, residual branches) the tile is fetched by TMA instead: one
+//                  cp.async.bulk.tensor.2d per stage (TFLOAT32 tensor map: the copy engine rounds fp32 to TF32 and
+//                  writes the SWIZZLE_128B layout), and the producer warps sleep until the epilogue.
 //   D            : one elected thread issues tcgen05.mma (M=128, N=BN, K=8 per instruction); the accumulator lives
 //                  in TMEM and is drained by the four producer warps with tcgen05.ld, transposed through shared
 //                  memory so that every global store / residual load is a coalesced 128-byte row segment.
@@ -17,7 +21,9 @@
 // CTA = 160 threads: warps 0-3 produce A, then run the epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4
 // allocates TMEM and issues the MMAs.  Shared memory is sized so that two CTAs share an SM: one CTA's epilogue
 // overlaps the other's main loop.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "program.cuh"
@@ -153,9 +159,10 @@ __device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, float2 
 #ifndef TC_MAXNREG
 #define TC_MAXNREG 96  // measured on B200: 96 keeps two 288-thread CTAs per SM (112 and 128 run ~25% slower)
 #endif
-template <int BN, int STAGES, bool SMK>
+template <int BN, int STAGES, bool SMK, bool TMA_A>
 __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
-                                                             int table_stride, int table_rows, int dbg) {
+                                                       int table_stride, int table_rows, int dbg,
+                                                       const __grid_constant__ CUtensorMap tmA) {
   // dbg (SLIDE_TC_DEBUG, profiling only -- results are wrong when set): 1 = no W copies, 2 = no A stores,
   // 4 = no epilogue, 8 = no MMA
   extern __shared__ uint8_t smem_raw[];
@@ -183,7 +190,8 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(full_bar + s), TC_PRODUCERS + 1);  // A producers + the W bulk copy's expect_tx arrive
+      // A producers + the W bulk copy's expect_tx arrive; with TMA for A only the expect_tx arrive
+      mbar_init(smem_u32(full_bar + s), TMA_A ? 1 : TC_PRODUCERS + 1);
       mbar_init(smem_u32(empty_bar + s), 1);
     }
     mbar_init(smem_u32(accum_bar), 1);
@@ -206,7 +214,33 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
   const uint32_t tmem_base = *tmem_slot;
 
   bool ok = true;
-  if (warp < TC_PWARPS) {
+  if (TMA_A && warp < TC_PWARPS) {
+    // ------------------------------------------------------------------------------------- TMA producer (one thread)
+    if (tid == 0) {
+      constexpr uint32_t A_BYTES = TBM * TBK * 4;
+      const uint64_t tmap = reinterpret_cast<uint64_t>(&tmA);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        if (ok) ok = mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t bar = smem_u32(full_bar + s);
+        mbar_arrive_expect_tx(bar, A_BYTES + (uint32_t)W_BYTES);
+        // A tile: rows m0.., columns kb*32..; out-of-range rows / columns are zero-filled by the copy engine
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(sa),
+            "l"(tmap), "r"(kb * TBK), "r"(m0), "r"(bar)
+            : "memory");
+        const float *src = Wp + ((size_t)kb * wp_na + (size_t)(n0 >> 3)) * 256;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                sa + TBM * TBK * 4),
+            "l"(src), "r"((uint32_t)W_BYTES), "r"(bar)
+            : "memory");
+      }
+    }
+    __syncwarp();
+  } else if (warp < TC_PWARPS) {
     // ------------------------------------------------------------------------------------- A producers
     const int chunk = tid & 7;   // 16-byte chunk within the 128-byte K row
     const int rbase = tid >> 3;  // 0..31; this thread owns rows rbase + 32 i, i = 0..3
@@ -573,9 +607,14 @@ static int tc_rows_per_tile(int R) { return R % TBM == 0 ? 1 : TBM / R; }
 static int tc_table_stride(const GemmArgs &a) { return ((a.K + TBK - 1) / TBK) * TBK; }
 static bool has_xf(const XFd &x) { return x.stats || x.addvec || x.relu; }
 
+#ifndef TC_MIN_MACS
+#define TC_MIN_MACS 0  // A/B on B200: the tcgen05 kernel beats the FFMA kernel even for the 4096-row point-level GEMMs
+#endif
+
 bool gemm_tc_eligible(const GemmArgs &a, const float *Wp) {
   if (!Wp) return false;
   if (a.M < TBM || a.K < 32 || a.N < 32) return false;
+  if ((long long)a.M * a.N * a.K < TC_MIN_MACS) return false;
   if (((uintptr_t)a.A & 15) || (a.lda & 3) || ((uintptr_t)Wp & 15)) return false;
   if (has_xf(a.xfa)) {
     if (!spans_ok_tc(a.xfa.R)) return false;
@@ -592,15 +631,46 @@ bool gemm_tc_eligible(const GemmArgs &a, const float *Wp) {
   return true;
 }
 
-template <int BN, int STAGES, bool SMK>
-static int launch_tc_impl(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// A as a 2-D TFLOAT32 tensor [M rows, K columns] with row pitch lda: box = 128 rows x 32 columns, SWIZZLE_128B.
+static bool make_a_map(const GemmArgs &a, CUtensorMap *m) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
+  const cuuint64_t strides[1] = {(cuuint64_t)a.lda * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)TBM};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float *>(a.A), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES, bool SMK, bool TMA_A>
+static int launch_tc_impl(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st, const CUtensorMap &tm) {
   const int stride = tc_table_stride(a);
   const int rows = has_xf(a.xfa) ? tc_rows_per_tile(a.xfa.R) : 0;
   const int total = tc_stages_bytes(BN, STAGES) + rows * stride * 16 + TC_CTRL_BYTES + 1024 /* alignment slack */;
   if (total > TC_MAX_DYN_SMEM) return SLIDE_ERR_UNSUPPORTED;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, SMK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, SMK, TMA_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TC_MAX_DYN_SMEM);
     if (e != cudaSuccess) return cuda_rc(e);
     configured = true;
@@ -612,13 +682,23 @@ static int launch_tc_impl(const GemmArgs &a, const float *Wp, int wp_na, cudaStr
     const char *e = getenv("SLIDE_TC_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
-  gemm_tc_kernel<BN, STAGES, SMK><<<grid, TC_THREADS, total, st>>>(a, Wp, wp_na, stride, rows, dbg);
+  gemm_tc_kernel<BN, STAGES, SMK, TMA_A><<<grid, TC_THREADS, total, st>>>(a, Wp, wp_na, stride, rows, dbg, tm);
   return after_launch();
 }
 
 template <int BN, int STAGES>
 static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
-  return a.smk > 0 ? launch_tc_impl<BN, STAGES, true>(a, Wp, wp_na, st) : launch_tc_impl<BN, STAGES, false>(a, Wp, wp_na, st);
+  static int use_tma = -1;
+  if (use_tma < 0) {
+    const char *e = getenv("SLIDE_TC_TMA");
+    use_tma = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (a.smk > 0) return launch_tc_impl<BN, STAGES, true, false>(a, Wp, wp_na, st, tm);
+  // A needs no transform and its rows are 16-byte aligned with a 16-byte pitch: let TMA fetch it
+  if (use_tma && !has_xf(a.xfa) && make_a_map(a, &tm)) return launch_tc_impl<BN, STAGES, false, true>(a, Wp, wp_na, st, tm);
+  return launch_tc_impl<BN, STAGES, false, false>(a, Wp, wp_na, st, tm);
 }
 
 int launch_gemm_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {

@@ -1,12 +1,9 @@
 mkdir -p gpurun_out
-for v in default r96 r128; do
-  for f in 1 0; do
-    if [ $v = default ]; then unset SLIDE_B200_LIB; else export SLIDE_B200_LIB=$PWD/slide_b200/libslide_b200_$v.so; fi
-    SLIDE_FUSE_SOFTMAX=$f python tools/profile_records.py lat 256 auto > gpurun_out/ab_lat_${v}_f$f.txt 2>&1
-    echo "$v fuse=$f: $(head -1 gpurun_out/ab_lat_${v}_f$f.txt)"
-    grep -E "SA1.att.v |SA1.att.w2|SA1.att.softmax|SA1.mlp.res |SA1.mlp.conv1 " gpurun_out/ab_lat_${v}_f$f.txt | cut -c1-100
-  done
+timeout 900 python -m pytest tests/test_gpu_program.py -m gpu -q --timeout 900 -p no:cacheprovider -k "golden or (teacher_forced and auto)" > gpurun_out/t_prog.log 2>&1; echo "prog rc=$?"; tail -n 3 gpurun_out/t_prog.log | cut -c1-300
+for v in 1 0; do
+    SLIDE_TC_TMA=$v python tools/profile_records.py lat 256 auto > gpurun_out/ab_lat_tma$v.txt 2>&1
+    SLIDE_TC_TMA=$v python tools/profile_records.py pos 256 auto > gpurun_out/ab_pos_tma$v.txt 2>&1
+    echo "tma=$v: $(head -1 gpurun_out/ab_lat_tma$v.txt)"
+    echo "tma=$v: $(head -1 gpurun_out/ab_pos_tma$v.txt)"
+    grep -E "SA1.att.v |SA1.att.k |SA1.mlp.res |SA1.mlp.conv0 |SA1.att.q " gpurun_out/ab_lat_tma$v.txt | cut -c1-100
 done
-unset SLIDE_B200_LIB
-python tools/profile_records.py pos 256 auto | head -1
-SLIDE_B200_LIB=$PWD/slide_b200/libslide_b200_r96.so python tools/profile_records.py pos 256 auto | head -1
