@@ -57,6 +57,8 @@ enum slide_op_kind {
   SLIDE_OP_GATHER_ROWS = 9,  /* dst[(s,j), :] = src[(s, idx[s,j]), :] */
   SLIDE_OP_UPSAMPLE = 10,    /* point_upsample: children = coarse + displacement * scale / sqrt(factor) */
   SLIDE_OP_TEMB = 11,        /* sinusoidal timestep embedding (calc_t_emb) */
+  SLIDE_OP_COLMAX = 12,      /* out[s,c] = max_r xf(X)[s*R + r, c]  (Pnet2Stage's global max-pool) */
+  SLIDE_OP_KL = 13,          /* DiagonalGaussianDistribution: mode, or mean + exp(0.5*clamp(logvar)) * noise */
   SLIDE_OP_KIND_COUNT
 };
 
@@ -150,6 +152,14 @@ enum slide_upsample_field {
 
 /* out[i, 0:half] = sin(ts[i] * freq[j]), out[i, half:2*half] = cos(...); ts f32 [ROWS], FREQ_W f32 [half] */
 enum slide_temb_field { TE_TS = 0, TE_FREQ_W, TE_HALF, TE_OUT, TE_LDO, TE_ROWS };
+
+/* out f32 [B, C] (row stride LDO); X f32 [B*R, C]; XF block = transform applied to X before the max
+ * (pointnet2/models/pnet.py:32-39: F.max_pool2d over the points after the shared MLP's GroupNorm + ReLU) */
+enum slide_colmax_field { CM_X = 0, CM_LDX, CM_R, CM_C, CM_OUT, CM_LDO, CM_B, CM_STEP, CM_XF, CM_NFIELD = CM_XF + XF_NFIELD };
+
+/* P f32 [ROWS, 2C] = [mean | logvar]; out[r,c] = mean[r,c] (NOISE < 0: posterior mode) or
+ * mean[r,c] + exp(0.5 * clamp(logvar[r,c], -30, 20)) * noise[r,c]   (pointnet2/data_utils/distributions.py:4-17,41-42) */
+enum slide_kl_field { KL_P = 0, KL_LDP, KL_C, KL_NOISE, KL_LDN, KL_OUT, KL_LDO, KL_ROWS };
 
 #ifdef __cplusplus
 }

@@ -262,6 +262,22 @@ class Machine(object):
         out = coarse[:, None, :] + (disp * np.float32(f[0])) * np.float32(f[1])
         self.A(g("UP_OUT"), rows * fac, g("UP_LDO"), Fd)[...] = out.reshape(rows * fac, Fd).astype(np.float32)
 
+    def op_colmax(self, p, f):
+        g = lambda k: int(p[V[k]])
+        B, R, C = g("CM_B"), g("CM_R"), g("CM_C")
+        x = self.xf(np.array(self.A(g("CM_X"), B * R, g("CM_LDX"), C)), p, V["CM_XF"], g("CM_STEP"))
+        self.A(g("CM_OUT"), B, g("CM_LDO"), C)[...] = x.reshape(B, R, C).max(axis=1)
+
+    def op_kl(self, p, f):
+        g = lambda k: int(p[V[k]])
+        rows, C = g("KL_ROWS"), g("KL_C")
+        P = torch.from_numpy(np.array(self.A(g("KL_P"), rows, g("KL_LDP"), 2 * C)))
+        mean, logvar = P[:, :C], P[:, C:]
+        if g("KL_NOISE") >= 0:
+            noise = torch.from_numpy(np.array(self.A(g("KL_NOISE"), rows, g("KL_LDN"), C)))
+            mean = mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
+        self.A(g("KL_OUT"), rows, g("KL_LDO"), C)[...] = mean.numpy()
+
     def op_temb(self, p, f):
         g = lambda k: int(p[V[k]])
         rows, half = g("TE_ROWS"), g("TE_HALF")

@@ -21,6 +21,10 @@ Citations (relative to /root/reference; OPS = pointnet2_ops_lib/pointnet2_ops):
   upsample_points / propagate_feature / decode
                        pointnet2/models/point_upsample_decoder.py:106-190, keypoint_decoder.py:25-36,
                        autoencoder.py:42-45
+  pnet2stage           pointnet2/models/pnet.py:7-40
+  encoder_net          pointnet2/models/pointnet2_feature_extractor.py:143-218 (PointNet2Encoder.forward)
+  kl_latent            pointnet2/data_utils/distributions.py:4-43 + point_upsample_decoder.py:95-104
+  encode               pointnet2/models/autoencoder.py:37-40, point_upsample_decoder.py:106-147 (KL branch)
   position_schedule / position_sampling   pointnet2/util.py:167-259
   latent_schedule / denoising_step / denoise_and_reconstruct
                        pointnet2/diffusion_utils/diffusion.py:12-39,58-95,158-208,346-404
@@ -158,7 +162,7 @@ def group_knn(x, y, feats_at_y, K):
     return out.transpose(2, 3).transpose(1, 2)
 
 
-def sa_module(xyz, features, P, npoint, nsample, cfg, t_emb, cond):
+def sa_module(xyz, features, P, npoint, nsample, cfg, t_emb, cond, cond2=None):
     act = cfg.get("activation", "relu")
     if xyz.shape[1] <= npoint:
         new_xyz, q_feat = xyz, features
@@ -168,7 +172,7 @@ def sa_module(xyz, features, P, npoint, nsample, cfg, t_emb, cond):
         q_feat = features.gather(2, pick[:, None, :].expand(-1, features.shape[1], -1))
     grouped = query_and_group_nn(xyz, new_xyz, features, nsample, cfg["include_abs_coordinate"],
                                  cfg.get("include_center_coordinate", False))
-    h = mlp_plus_t_emb(grouped, P.sub("mlps.0"), cfg["res_connect"], act, t_emb=t_emb, cond=cond)
+    h = mlp_plus_t_emb(grouped, P.sub("mlps.0"), cfg["res_connect"], act, t_emb=t_emb, cond=cond, cond2=cond2)
     out = attention(q_feat, grouped, h, P.sub("attention_modules.0"), cfg["attention_setting"]["last_activation"])
     return new_xyz, out
 
@@ -291,6 +295,63 @@ def decode(keypoint, feature, P, decoder_cfgs, label, start_idx_list=None):
         xyzs.append(upsample_points(f, xyzs[i + 1], Pd, cfg, sl[i + 1]))
         feats.append(f)
     return xyzs[-1], xyzs
+
+
+# ------------------------------------------------------------------------------------ autoencoder encode
+def pnet2stage(x, P, act="relu"):
+    """Pnet2Stage.forward with remove_last_activation=False: x (B,C,N) -> global feature (B, mlp2[-1])."""
+    f = mlp_plus_t_emb(x.unsqueeze(-1), P.sub("mlp1"), False, act)
+    g = F.max_pool2d(f, kernel_size=[f.size(2), 1]).expand(-1, -1, f.size(2), -1)
+    f = mlp_plus_t_emb(torch.cat([f, g], dim=1), P.sub("mlp2"), False, act)
+    return F.max_pool2d(f, kernel_size=[f.size(2), 1]).squeeze(-1).squeeze(-1)
+
+
+def encoder_net(pointcloud, P, cfg, label=None):
+    """PointNet2Encoder.forward (no timestep): -> (out (B, np_last, C_last), l_xyz, l_features)."""
+    assert not cfg["bn_first"] and cfg.get("bn", True) and not cfg["include_t"]
+    arch = cfg["architecture"]
+    assert arch["neighbor_definition"] == "nn"
+    in_fea = cfg["in_fea_dim"]
+    if cfg["attach_position_to_input_feature"]:
+        pointcloud = torch.cat([pointcloud, pointcloud[:, :, 0:3]], dim=2)
+    xyz = pointcloud[..., 0:3].contiguous()
+    features = pointcloud[..., 3:].transpose(1, 2).contiguous() if pointcloud.size(-1) > 3 else None
+    class_emb = F.embedding(label, P["class_emb.weight"]) if (label is not None and cfg["include_class_condition"]) else None
+    if cfg.get("include_global_feature", False):
+        assert not cfg.get("global_feature_remove_last_activation", True)
+        g_in = torch.cat([xyz, pointcloud[:, :, 3:3 + in_fea]], dim=2) if in_fea > 0 else xyz
+        cond, cond2 = pnet2stage(g_in.transpose(1, 2), P.sub("global_pnet")), class_emb
+    else:
+        cond, cond2 = class_emb, None
+    l_xyz, l_feat = [xyz], [features]
+    for i, (npoint, nsample) in enumerate(zip(arch["npoint"], arch["nsample"])):
+        nx, nf = sa_module(l_xyz[i], l_feat[i], P.sub("SA_modules.%d" % i), npoint, nsample, cfg, None, cond, cond2)
+        l_xyz.append(nx)
+        l_feat.append(nf)
+    return l_feat[-1].transpose(1, 2), l_xyz, l_feat
+
+
+def kl_latent(params, noise=None):
+    """DiagonalGaussianDistribution over the channel dim of (B,N,2C): mode (noise None) or mean + std * noise."""
+    mean, logvar = torch.chunk(params, 2, dim=2)
+    if noise is None:
+        return mean
+    return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
+
+
+def encode(pointcloud, keypoint, P, enc_cfg, kp_cfg, label, noises=None):
+    """PointAutoencoder.encode with apply_kl_regularization=True.  noises = (n1 (B,16,C1), n2 (B,16,C2)) replaces the
+    two CPU torch.randn draws of DiagonalGaussianDistribution.sample; None = posterior mode (sample_posterior=False)."""
+    out, l_xyz, _ = encoder_net(pointcloud, P.sub("encoder"), enc_cfg, label)
+    Pk = P.sub("keypoint_encoder")
+    cfgx = dict(kp_cfg)
+    f1, _, _ = encoder_net(keypoint, Pk.sub("feature_extractor"), cfgx, label)
+    f1 = kl_latent(f1, None if noises is None else noises[0])
+    mapped = feature_map_module(l_xyz[-1], out.transpose(1, 2).contiguous(), keypoint[:, :, 0:3].contiguous(),
+                                f1.transpose(1, 2), Pk.sub("feature_mapper"), kp_cfg["feature_mapper_setting"]["nsample"],
+                                kp_cfg).transpose(1, 2)
+    mapped = kl_latent(mapped, None if noises is None else noises[1])
+    return torch.cat([f1, mapped], dim=2)
 
 
 # ------------------------------------------------------------------------------------ samplers

@@ -276,6 +276,60 @@ __global__ void temb_kernel(const float *__restrict__ ts, const float *__restric
   out[(size_t)r * ldo + half + j] = cosf(arg);
 }
 
+// out[s,c] = max_r xf(X)[s*R + r, c]: thread per (sample, column), coalesced in c (Pnet2Stage's global max-pool)
+__global__ void colmax_kernel(const float *__restrict__ X, int ldx, int R, int C, XFd xf,
+                              const int *__restrict__ step_ptr, float *__restrict__ out, int ldo, int B) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)B * C) return;
+  const int s = (int)(e / C), c = (int)(e - (long long)s * C);
+  const int step = step_ptr ? *step_ptr : 0;
+  float mean = 0.f, rstd = 1.f, gam = 1.f, bet = 0.f;
+  bool norm = false;
+  if (xf.stats) {
+    const int ch = xf.choff + c;
+    if (ch < xf.nnorm) {
+      norm = true;
+      const int G = xf.nnorm / xf.cg;
+      const double *st = xf.stats + ((size_t)s * G + ch / xf.cg) * 2;  // xf.R == R: one statistics row per sample
+      const double m = st[0] * (double)xf.inv_count;
+      double var = st[1] * (double)xf.inv_count - m * m;
+      var = var < 0.0 ? 0.0 : var;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS));
+      gam = __ldg(xf.gamma + ch);
+      bet = __ldg(xf.beta + ch);
+    }
+  }
+  float add = 0.f;
+  if (xf.addvec) {
+    const long long arow = xf.addmode == 0 ? s : (xf.addmode == 1 ? step : 0);
+    add = xf.addvec[arow * xf.addld + c];
+  }
+  float mx = -INFINITY;
+  for (int r = 0; r < R; ++r) {
+    float v = X[((size_t)s * R + r) * ldx + c];
+    if (norm) v = (v - mean) * rstd * gam + bet;
+    if (xf.relu) v = fmaxf(v, 0.f);
+    mx = fmaxf(mx, v + add);
+  }
+  out[(size_t)s * ldo + c] = mx;
+}
+
+// DiagonalGaussianDistribution: mode, or mean + exp(0.5 * clamp(logvar, -30, 20)) * noise (op by op like torch)
+__global__ void kl_kernel(const float *__restrict__ P, int ldp, int C, const float *__restrict__ noise, int ldn,
+                          float *__restrict__ out, int ldo, long long rows) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * C) return;
+  const long long r = e / C;
+  const int c = (int)(e - r * C);
+  float v = P[r * ldp + c];
+  if (noise) {
+    const float lv = fminf(fmaxf(P[r * ldp + C + c], -30.0f), 20.0f);
+    v = __fadd_rn(v, __fmul_rn(expf(__fmul_rn(0.5f, lv)), noise[r * ldn + c]));
+  }
+  out[r * ldo + c] = v;
+}
+
 }  // namespace slide
 
 using namespace slide;
@@ -449,6 +503,23 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       const int rows = (int)q[TE_ROWS], half = (int)q[TE_HALF];
       temb_kernel<<<grid_for((long long)rows * half, 256), 256, 0, st>>>(
           AP<float>(p, q[TE_TS]), WP<float>(p, q[TE_FREQ_W]), half, AP<float>(p, q[TE_OUT]), (int)q[TE_LDO], rows);
+      return after_launch();
+    }
+    case SLIDE_OP_COLMAX: {
+      const int B = (int)q[CM_B], C = (int)q[CM_C];
+      XFd xf = make_xf(p, q + CM_XF);
+      if (xf.stats && xf.R != (int)q[CM_R]) return SLIDE_ERR_UNSUPPORTED;
+      colmax_kernel<<<grid_for((long long)B * C, 128), 128, 0, st>>>(AP<float>(p, q[CM_X]), (int)q[CM_LDX], (int)q[CM_R], C,
+                                                                   xf, AP<int>(p, q[CM_STEP]), AP<float>(p, q[CM_OUT]),
+                                                                   (int)q[CM_LDO], B);
+      return after_launch();
+    }
+    case SLIDE_OP_KL: {
+      const long long rows = q[KL_ROWS];
+      const int C = (int)q[KL_C];
+      kl_kernel<<<grid_for(rows * C, 256), 256, 0, st>>>(AP<float>(p, q[KL_P]), (int)q[KL_LDP], C,
+                                                         AP<float>(p, q[KL_NOISE]), (int)q[KL_LDN],
+                                                         AP<float>(p, q[KL_OUT]), (int)q[KL_LDO], rows);
       return after_launch();
     }
     default:

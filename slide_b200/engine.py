@@ -114,6 +114,26 @@ def build_decode(decoder_cfgs, sd, B):
     return b, h
 
 
+def build_encode(enc_cfg, kp_cfg, sd, B, n_points, sample_posterior=False):
+    """PointAutoencoder.encode for B clouds of n_points (xyz + normal) and their 16 keypoints."""
+    b = Builder(B)
+    cloud = b.tensor("cloud", n_points, 3 + enc_cfg["in_fea_dim"])
+    kp = b.tensor("keypoint", 16, 3)
+    labels = b.tensor("labels", 1, B, B=1, dtype="i32")
+    C1 = kp_cfg["architecture"]["feature_dim"][-1]
+    C2 = kp_cfg["feature_mapper_setting"]["out_dim"]
+    noises = None
+    if sample_posterior:
+        noises = (b.tensor("noise1", 16, C1), b.tensor("noise2", 16, C2))
+    P = nets.Params(sd)
+    b.begin_segment("encode")
+    b.step_begin()
+    enc = nets.lower_encode(b, P, enc_cfg, kp_cfg, cloud, kp, labels, noises)
+    b.end_segment()
+    h = dict(cloud=cloud, keypoint=kp, labels=labels, out=enc["out"], class_tables=enc["class_tables"], noises=noises)
+    return b, h
+
+
 def init_constants(machine, h):
     """Upload the constants a freshly created program needs before its setup segment runs: the timestep list
     0..T-1 and the class-embedding table(s).  `machine` is a Program or the CPU interpreter (same interface)."""

@@ -76,10 +76,12 @@ def _conv(b, P, cols=None):
 class _Ctx(object):
     """Per-network lowering context: timestep-table / condition sources and activation name."""
 
-    def __init__(self, b, cfg, t_src=None, cond_src=None):
+    def __init__(self, b, cfg, t_src=None, cond_src=None, cond2_src=None, inline=False):
         self.b, self.cfg = b, cfg
         self.t_src = t_src        # Tensor [T, 4*t_dim] (swish'ed timestep embeddings for every t) or None
-        self.cond_src = cond_src  # Tensor [B, class_condition_dim] or None
+        self.cond_src = cond_src  # Tensor [B, condition_dim] or None (class embedding, or the global feature)
+        self.cond2_src = cond2_src  # Tensor [B, second_condition_dim] or None
+        self.inline = inline      # True: condition projections depend on run-time data -> emit them in place
         self.setup = []           # deferred setup GEMMs (emitted into the setup segment)
         act = cfg.get("activation", "relu")
         if act != "relu":
@@ -87,26 +89,42 @@ class _Ctx(object):
         if cfg["bn_first"] or not cfg.get("bn", True) or not cfg["res_connect"]:
             raise NotImplementedError("bn_first / bn=False / res_connect=False are not lowered")
 
+    def project(self, **g):
+        """A per-sample / per-timestep projection feeding an additive vector."""
+        if self.inline:
+            self.b.gemm(g["A"], g["W"], g["out"], bias=g["bias"], note=g["note"])
+        else:
+            self.setup.append(g)
 
-def _lower_mlp(ctx, P, G, R, name, out=None, use_t=False, use_cond=False):
-    """Mlp_plus_t_emb with bn_first=False, res_connect=True.  G: input [B*R, Cin].  Returns H [B*R, Cout]."""
+
+def _lower_mlp(ctx, P, G, R, name, out=None, use_t=False, use_cond=False, res=True, xf_in=NO_XF, first_cols=None,
+               first_ev=None):
+    """Mlp_plus_t_emb with bn_first=False.  G: input [B*R, Cin] (xf_in = transform still to be applied to it).
+    res=True (res_connect): returns the materialised output H [B*R, Cout].
+    res=False (Pnet2Stage's MLPs): returns (raw, xf) -- the last conv's raw output and the transform its consumers apply.
+    first_cols / first_ev: the first conv acts on cat[G, v broadcast over rows]; G's share of the weight is
+    columns first_cols and the other share enters as the per-sample vector first_ev = (tensor, rows per sample)."""
     b = ctx.b
-    if P.has("first_conv.weight") or P.has("fc_second_condition.weight"):
-        raise NotImplementedError("first_conv / second condition")
+    if P.has("first_conv.weight"):
+        raise NotImplementedError("first_conv")
     stages = [("first_mlp.0", "first_mlp.1"), ("second_mlp.0", "second_mlp.1")]
     j = 0
     while P.has("rest_mlp.%d.weight" % (3 * j)):
         stages.append(("rest_mlp.%d" % (3 * j), "rest_mlp.%d" % (3 * j + 1)))
         j += 1
-    prev, xf_prev = G, NO_XF
+    prev, xf_prev = G, xf_in
     for si, (ck, gk) in enumerate(stages):
-        W, bias = _conv(b, P.sub(ck))
+        W, bias = _conv(b, P.sub(ck), cols=first_cols if si == 0 else None)
         N = W[2]
         nnorm, cg = _gn_dims(N)
         assert P[gk + ".group_norm.weight"].shape[0] == nnorm
         raw = b.tensor("%s.raw%d" % (name, si), R, N, B=G.B)
         st = b.stats("%s.st%d" % (name, si), nnorm, cg, R, R * cg, B=G.B)
-        b.gemm(prev, W, raw, bias=bias, xfa=xf_prev, stats=st, note="%s.conv%d" % (name, si))
+        if si == 0 and first_ev is not None:
+            b.gemm(prev, W, raw, bias=bias, xfa=xf_prev, ev=first_ev[0], ev_div=first_ev[1], stats=st,
+                   note="%s.conv%d" % (name, si))
+        else:
+            b.gemm(prev, W, raw, bias=bias, xfa=xf_prev, stats=st, note="%s.conv%d" % (name, si))
         addvec, addmode = None, 0
         if si == 0 and P.has("fc.weight"):
             assert use_t and ctx.t_src is not None, "module has a timestep projection but no timestep source"
@@ -118,12 +136,20 @@ def _lower_mlp(ctx, P, G, R, name, out=None, use_t=False, use_cond=False):
             assert use_cond and ctx.cond_src is not None, "module has a condition projection but no condition"
             Wc, bc = _conv(b, P.sub("fc_condition"))
             addvec = b.tensor("%s.cvec" % name, 1, N, B=G.B)
-            ctx.setup.append(dict(A=ctx.cond_src, W=Wc, out=addvec, bias=bc, note="%s.fc_condition" % name))
+            ctx.project(A=ctx.cond_src, W=Wc, out=addvec, bias=bc, note="%s.fc_condition" % name)
+            addmode = 0
+        if si == len(stages) - 1 and P.has("fc_second_condition.weight"):
+            assert si >= 2 and ctx.cond2_src is not None, "second condition needs a rest_mlp stage and a source"
+            Wc, bc = _conv(b, P.sub("fc_second_condition"))
+            addvec = b.tensor("%s.c2vec" % name, 1, N, B=G.B)
+            ctx.project(A=ctx.cond2_src, W=Wc, out=addvec, bias=bc, note="%s.fc_second_condition" % name)
             addmode = 0
         xf_prev = XF(stats=st.tensor, cg=cg, nnorm=nnorm, choff=0, gamma=b.weight(P[gk + ".group_norm.weight"]),
                      beta=b.weight(P[gk + ".group_norm.bias"]), R=R, count=R * cg, relu=True, addvec=addvec,
                      addmode=addmode)
         prev = raw
+    if not res:
+        return prev, xf_prev
     N = prev.C
     if out is None:
         out = b.tensor("%s.out" % name, R, N, B=G.B)
@@ -375,6 +401,91 @@ def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None)
         for g in ctx.setup:
             b.gemm(g["A"], g["W"], g["out"], bias=g["bias"], note=g["note"])
     return dict(out=result, emit_setup=emit_setup, inputs=inputs, levels=(l_xyz, l_feat))
+
+
+# ---------------------------------------------------------------------------------------------------
+# autoencoder encode
+# ---------------------------------------------------------------------------------------------------
+def _lower_pnet2stage(ctx, P, X, n_points, name):
+    """Pnet2Stage.forward (pointnet2/models/pnet.py:26-40), remove_last_activation=False.  X [B*n, C] -> [B, C_out].
+    cat[feature, max-pooled feature broadcast over points] is never formed: the second MLP's first conv is split
+    into its per-point share (on the rows) and its global share (one row per sample, added in the epilogue)."""
+    b = ctx.b
+    B = X.B
+    raw, xf = _lower_mlp(ctx, P.sub("mlp1"), X, n_points, name + ".mlp1", res=False)
+    C1 = raw.C
+    g1 = b.tensor(name + ".g1", 1, C1, B=B)
+    b.colmax(raw, xf, n_points, g1, note=name + ".maxpool1")
+    Wg, _ = _conv(b, P.sub("mlp2.first_mlp.0"), cols=(C1, 2 * C1))
+    gp = b.tensor(name + ".gproj", 1, Wg[2], B=B)
+    b.gemm(g1, Wg, gp, note=name + ".mlp2.conv0(global)")
+    raw2, xf2 = _lower_mlp(ctx, P.sub("mlp2"), raw, n_points, name + ".mlp2", res=False, xf_in=xf, first_cols=(0, C1),
+                           first_ev=(gp, n_points))
+    out = b.tensor(name + ".global", 1, raw2.C, B=B)
+    b.colmax(raw2, xf2, n_points, out, note=name + ".maxpool2")
+    return out
+
+
+def lower_encoder_net(b, P, cfg, X, n_points, name, labels):
+    """PointNet2Encoder.forward (pointnet2/models/pointnet2_feature_extractor.py:143-218), no timestep.
+    X [B*n_points, 3 + in_fea_dim].  Returns dict(out=[B*np_last, C_last], xyz=[B*np_last, 3])."""
+    arch = cfg["architecture"]
+    assert arch["neighbor_definition"] == "nn" and not cfg["include_t"]
+    B = X.B
+    class_src = None
+    if labels is not None and cfg["include_class_condition"]:
+        emb_w = P["class_emb.weight"]
+        table = b.tensor(name + ".class_emb", emb_w.shape[0], emb_w.shape[1], B=1)
+        class_src = b.tensor(name + ".cond", 1, emb_w.shape[1], B=B)
+        b._emit("SLIDE_OP_GATHER_ROWS", {"GA_SRC": table.off, "GA_LDS": table.ld, "GA_N": table.R, "GA_IDX": labels.off,
+                                         "GA_M": B, "GA_DST": class_src.off, "GA_LDD": class_src.ld,
+                                         "GA_NCOLS": table.C, "GA_B": 1}, note=name + ".class_emb")
+    Fin = X.C - 3
+    assert X.R == n_points and Fin == cfg["in_fea_dim"]
+    xyz = X.cols(0, 3)
+    if cfg["attach_position_to_input_feature"]:
+        feats = b.tensor(name + ".feat0", n_points, Fin + 3, B=B)
+        if Fin > 0:
+            b.copy_cols(X.cols(3, Fin), feats.cols(0, Fin), note=name + ".in_feat")
+        b.copy_cols(X.cols(0, 3), feats.cols(Fin, 3), note=name + ".in_xyz")
+    else:
+        feats = X.cols(3, Fin)
+    ctx = _Ctx(b, cfg, None, class_src, None, inline=True)
+    if cfg.get("include_global_feature", False):
+        if cfg.get("global_feature_remove_last_activation", True):
+            raise NotImplementedError("global_feature_remove_last_activation")
+        # global_pnet input = [xyz, input features] = the raw cloud rows (pointnet2_feature_extractor.py:186-193)
+        g = _lower_pnet2stage(ctx, P.sub("global_pnet"), X, n_points, name + ".pnet")
+        ctx.cond_src, ctx.cond2_src = g, class_src
+    l_xyz, l_feat = [xyz], [feats]
+    for i, (npoint, nsample) in enumerate(zip(arch["npoint"], arch["nsample"])):
+        nx, nf = _lower_sa(ctx, P.sub("SA_modules.%d" % i), l_xyz[i], l_feat[i], npoint, nsample, "%s.SA%d" % (name, i))
+        l_xyz.append(nx)
+        l_feat.append(nf)
+    tables = [(table, emb_w)] if class_src is not None else []
+    return dict(out=l_feat[-1], xyz=l_xyz[-1], class_tables=tables)
+
+
+def lower_encode(b, P, enc_cfg, kp_cfg, cloud, keypoint, labels, noises=None, name="enc"):
+    """PointAutoencoder.encode (pointnet2/models/autoencoder.py:37-40; keypoint_encoder.propagate_feature with the KL
+    branch, point_upsample_decoder.py:106-147).  cloud [B*N, 6], keypoint [B*16, 3]; noises = (n1 [B*16, C1],
+    n2 [B*16, C2]) arena tensors holding the two posterior draws, or None for the posterior mode.
+    Returns dict(out=[B*16, C1 + C2], class_tables)."""
+    B = cloud.B
+    enc = lower_encoder_net(b, P.sub("encoder"), enc_cfg, cloud, cloud.R, name + ".encoder", labels)
+    Pk = P.sub("keypoint_encoder")
+    fx = lower_encoder_net(b, Pk.sub("feature_extractor"), kp_cfg, keypoint, keypoint.R, name + ".kp_fx", labels)
+    C1 = fx["out"].C // 2
+    C2 = kp_cfg["feature_mapper_setting"]["out_dim"]
+    latent = b.tensor(name + ".latent", keypoint.R, C1 + C2, B=B)
+    b.kl(fx["out"], latent.cols(0, C1), noise=None if noises is None else noises[0], note=name + ".kl_extractor")
+    ctx = _Ctx(b, kp_cfg)
+    mapped = b.tensor(name + ".mapped", keypoint.R, 2 * C2, B=B)
+    _lower_feature_map(ctx, Pk.sub("feature_mapper"), enc["xyz"], enc["out"], keypoint.cols(0, 3), latent.cols(0, C1),
+                       kp_cfg["feature_mapper_setting"]["nsample"], name + ".fm", mapped)
+    assert not ctx.setup
+    b.kl(mapped, latent.cols(C1, C2), noise=None if noises is None else noises[1], note=name + ".kl_mapper")
+    return dict(out=latent, class_tables=enc["class_tables"] + fx["class_tables"])
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -97,6 +97,46 @@ class Decoder(object):
         return self.prog.launches(*self.builder.segments["decode"]) + self.prog.launches(*self.builder.segments["setup"])
 
 
+class Encoder(object):
+    """PointAutoencoder.encode in chunks: clouds (B,N,6) + keypoints (B,16,3) -> latent features (B,16,48)."""
+
+    def __init__(self, enc_cfg, kp_cfg, sd, chunk, n_points, device, sample_posterior=False, backend="auto"):
+        self.chunk, self.sample = chunk, sample_posterior
+        self.builder, self.h = engine.build_encode(enc_cfg, kp_cfg, sd, chunk, n_points, sample_posterior)
+        self.prog = Program(self.builder, device)
+        self.prog.set_gemm_backend(backend)
+        engine.init_constants(self.prog, self.h)
+        self.out_dim = self.h["out"].C
+
+    def run(self, cloud, keypoint, labels, out, noises=None):
+        B = cloud.shape[0]
+        assert B % self.chunk == 0
+        for c0 in range(0, B, self.chunk):
+            sl = slice(c0, c0 + self.chunk)
+            self.prog.upload(self.h["labels"], labels[sl].to(torch.int32))
+            self.prog.upload(self.h["cloud"], cloud[sl])
+            self.prog.upload(self.h["keypoint"], keypoint[sl])
+            if self.sample:
+                self.prog.upload(self.h["noises"][0], noises[0][sl])
+                self.prog.upload(self.h["noises"][1], noises[1][sl])
+            self.prog.run_segment("encode")
+            out[sl].copy_(self.prog.view(self.h["out"])[:, :self.out_dim].view(self.chunk, 16, self.out_dim))
+
+    def launches_per_chunk(self):
+        return self.prog.launches(*self.builder.segments["encode"])
+
+
+def sample_keypoints(points, K=16):
+    """data_utils/points_sampling.py:156-187 with add_centroid=True: FPS over [centroid; points] from index 0, so the
+    centroid is always the first keypoint.  points (B,N,3) on the GPU -> (B,K,3)."""
+    from . import install_dropin
+    install_dropin()
+    from pytorch3d.ops import sample_farthest_points
+    x = torch.cat([points.mean(dim=1, keepdim=True), points], dim=1).contiguous()
+    sel, _ = sample_farthest_points(x, K=K, random_start_point=False)
+    return sel
+
+
 def default_state_dicts(seed=0):
     return {"position": weights.random_state_dict(weights.load_json("schema_position_ddpm.json"), seed + 1),
             "latent": weights.random_state_dict(weights.load_json("schema_latent_ddpm.json"), seed + 2),

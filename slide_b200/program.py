@@ -293,6 +293,21 @@ class Builder(object):
                                          "UP_ROWS": coarse.rows, "UP_FACTOR": factor, "UP_F": Fd},
                    floats=[np.float32(1 / np.sqrt(factor)), np.float32(scale)], note=note)
 
+    def colmax(self, X, xf, R, out, note=""):
+        assert out.C == X.C and X.rows == out.rows * R
+        f = {"CM_X": X.off, "CM_LDX": X.ld, "CM_R": R, "CM_C": X.C, "CM_OUT": out.off, "CM_LDO": out.ld,
+             "CM_B": out.rows, "CM_STEP": self.step.off}
+        for i, val in enumerate(xf.fields()):
+            f[("CM_XF", i)] = val
+        self._emit("SLIDE_OP_COLMAX", f, note=note)
+
+    def kl(self, P, out, noise=None, note=""):
+        C = out.C
+        assert P.C == 2 * C and P.rows == out.rows
+        self._emit("SLIDE_OP_KL", {"KL_P": P.off, "KL_LDP": P.ld, "KL_C": C, "KL_NOISE": noise.off if noise is not None else -1,
+                                   "KL_LDN": noise.ld if noise is not None else 0, "KL_OUT": out.off, "KL_LDO": out.ld,
+                                   "KL_ROWS": out.rows}, note=note)
+
     def temb(self, ts, freq_off, half, out, note=""):
         assert out.C == 2 * half and ts.C == out.rows
         self._emit("SLIDE_OP_TEMB", {"TE_TS": ts.off, "TE_FREQ_W": freq_off, "TE_HALF": half, "TE_OUT": out.off,

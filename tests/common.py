@@ -54,3 +54,13 @@ def compare_tensors(builder, cpu, gpu_arena, rtol, note="", only=None):
         if err > rtol * max(scale, 1e-6) + 1e-7:
             bad.append((t.name, err, scale))
     return bad
+
+
+def load_encode_inputs(m, h, golden, sample):
+    engine.init_constants(m, h)
+    m.upload(h["labels"], np.asarray(golden["label"], dtype=np.int32))
+    m.upload(h["cloud"], golden["enc_cloud"])
+    m.upload(h["keypoint"], golden["enc_kp"])
+    if sample:
+        m.upload(h["noises"][0], golden["enc_n1"])
+        m.upload(h["noises"][1], golden["enc_n2"])

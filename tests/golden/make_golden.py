@@ -106,6 +106,26 @@ def main():
     assert torch.equal(out, out2), "oracle/ref_model.decode deviates from the reference"
     gold.update(dec_kp=kp.numpy(), dec_feat=feat.numpy(), dec_out=out.numpy(), dec_l1=levels[1].numpy(),
                 dec_l2=levels[2].numpy(), dec_starts=torch.stack(starts).numpy(), label=label.numpy())
+    # encode (BASELINE config 5 input shape at N=2048): posterior mode and a pinned posterior sample.  The reference
+    # draws torch.randn(mean.shape) with mean of shape (B, C, N) on the CPU generator (distributions.py:15-17).
+    N = 2048
+    pts = torch.rand(B, N, 3, generator=g) - 0.5
+    nrm = torch.nn.functional.normalize(torch.randn(B, N, 3, generator=g), dim=2)
+    cloud = torch.cat([pts, nrm], dim=2)
+    ekp = pts[:, :16].contiguous()
+    with torch.no_grad():
+        e_mode = ae_net.encode(cloud, ekp, label=label, sample_posterior=False)
+        torch.manual_seed(99)
+        e_samp = ae_net.encode(cloud, ekp, label=label, sample_posterior=True)
+    torch.manual_seed(99)
+    n1 = torch.randn(B, 16, 16).transpose(1, 2).contiguous()
+    n2 = torch.randn(B, 32, 16).transpose(1, 2).contiguous()
+    P = ref_model.Params(sd)
+    with torch.no_grad():
+        assert torch.equal(e_mode, ref_model.encode(cloud, ekp, P, aec["encoder"], aec["decoders"][0], label))
+        assert torch.equal(e_samp, ref_model.encode(cloud, ekp, P, aec["encoder"], aec["decoders"][0], label, noises=(n1, n2)))
+    gold.update(enc_cloud=cloud.numpy(), enc_kp=ekp.numpy(), enc_mode=e_mode.numpy(), enc_sample=e_samp.numpy(),
+                enc_n1=n1.numpy(), enc_n2=n2.numpy())
     # config 1: FPS + ball query on a 1x2048x3 cloud (C oracle; the reference CUDA kernels cannot run without a GPU)
     xyz = torch.rand(1, 2048, 3, generator=torch.Generator().manual_seed(0)) * 2 - 1
     fps = ops.furthest_point_sampling(xyz, 1024)

@@ -193,3 +193,38 @@ def test_decode_records_teacher_forced(golden, pipeline_cfg):
     with open("gpurun_out/records_decode_simt.log", "w") as f:
         f.write("\n".join(log) + "\n")
     assert not bad, bad[:6]
+
+
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+@pytest.mark.parametrize("sample", [False, True])
+def test_encode_golden(backend, sample, golden, pipeline_cfg):
+    B = 2
+    sd = common.state_dict("ae")
+    aec = pipeline_cfg["autoencoder"]
+    b, h = engine.build_encode(aec["encoder"], aec["decoders"][0], sd, B, 2048, sample_posterior=sample)
+    prog = Program(b)
+    prog.set_gemm_backend(backend)
+    common.load_encode_inputs(prog, h, {k: torch.from_numpy(np.asarray(v)) for k, v in golden.items()}, sample)
+    prog.run_segment("encode")
+    torch.cuda.synchronize()
+    got = prog.download(h["out"]).cpu().numpy().reshape(B, 16, 48)
+    want = golden["enc_sample" if sample else "enc_mode"]
+    # FPS picks inside the encoder are discrete: identical inputs -> identical picks; features then differ by GEMM precision
+    assert np.abs(got - want).max() < (1e-4 if backend == "simt" else 3e-2) * max(1.0, np.abs(want).max())
+    assert lib.load().slide_tc_error() == 0
+
+
+def test_encode_records_teacher_forced(golden, pipeline_cfg):
+    B = 2
+    sd = common.state_dict("ae")
+    aec = pipeline_cfg["autoencoder"]
+    b, h = engine.build_encode(aec["encoder"], aec["decoders"][0], sd, B, 2048, sample_posterior=True)
+    m = ir_exec.Machine(b)
+    common.load_encode_inputs(m, h, golden, True)
+    prog = Program(b)
+    prog.set_gemm_backend("simt")
+    log = []
+    bad = _teacher_forced(b, m, prog, *b.segments["encode"], rtol=2e-4, log=log)
+    with open("gpurun_out/records_encode_simt.log", "w") as f:
+        f.write("\n".join(log) + "\n")
+    assert not bad, bad[:6]

@@ -86,3 +86,17 @@ def test_decode_records_match_reference(golden, pipeline_cfg):
     want = torch.from_numpy(golden["dec_out"])
     for i in range(B):
         assert _chamfer(out[i, :, :3], want[i, :, :3]) < 2e-3
+
+
+@pytest.mark.parametrize("sample", [False, True])
+def test_encode_records_match_reference(sample, golden, pipeline_cfg):
+    B = 2
+    sd = common.state_dict("ae")
+    aec = pipeline_cfg["autoencoder"]
+    b, h = engine.build_encode(aec["encoder"], aec["decoders"][0], sd, B, 2048, sample_posterior=sample)
+    m = ir_exec.Machine(b)
+    common.load_encode_inputs(m, h, golden, sample)
+    m.run_segment("encode")
+    got = m.download(h["out"]).numpy().reshape(B, 16, 48)
+    want = golden["enc_sample" if sample else "enc_mode"]
+    assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max())

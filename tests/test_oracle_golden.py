@@ -76,6 +76,17 @@ def test_ref_model_decode(golden, pipeline_cfg):
     assert np.array_equal(out.numpy(), golden["dec_out"])
 
 
+def test_ref_model_encode(golden, pipeline_cfg):
+    sd = common.state_dict("ae")
+    aec = pipeline_cfg["autoencoder"]
+    args = (torch.from_numpy(golden["enc_cloud"]), torch.from_numpy(golden["enc_kp"]), ref_model.Params(sd),
+            aec["encoder"], aec["decoders"][0], torch.from_numpy(golden["label"]).long())
+    with torch.no_grad():
+        assert np.array_equal(ref_model.encode(*args).numpy(), golden["enc_mode"])
+        noises = (torch.from_numpy(golden["enc_n1"]), torch.from_numpy(golden["enc_n2"]))
+        assert np.array_equal(ref_model.encode(*args, noises=noises).numpy(), golden["enc_sample"])
+
+
 def test_schedules_match_reference_formulas(pipeline_cfg):
     from slide_b200 import engine
     d = pipeline_cfg["position_ddpm"]["diffusion_config"]

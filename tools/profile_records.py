@@ -44,7 +44,9 @@ def main():
     if only:
         # ncu mode: `ncu --profile-from-start off ...` captures just these records (one launch each, cold L2)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        for i in [int(v) for v in only.split(",")]:
+        notes = {b.ops[first + j][3]: j for j in range(count)}
+        for key in only.split(","):
+            i = int(key) if key.isdigit() else notes[key]
             flush.zero_()
             torch.cuda.synchronize()
             torch.cuda.profiler.start()

@@ -41,8 +41,9 @@ def launches(tag):
         n += 1
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(P, "%s_launches.txt" % tag), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 400 python bench.py --steps 1 "
-                "--warmup 0 --ddpm-steps 40\n# (cold-cache, serialised: compare SHARES)  launches=%d total=%.1f us\n" % (n, tot))
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python tools/one_step.py\n"
+                "# = one position-DDPM step + one feature-DDPM step (each repeats 1000x in the benchmark) + one 32-shape decode "
+                "chunk, batch 256\n# (cold-cache, serialised: compare SHARES)  launches=%d total=%.1f us\n" % (n, tot))
         f.write("%-72s %6s %12s %10s %7s\n" % ("kernel", "n", "total_us", "avg_us", "share"))
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("%-72s %6d %12.1f %10.2f %6.1f%%\n" % (k[:72], a[0], a[1], a[1] / a[0], 100 * a[1] / tot))
@@ -56,8 +57,8 @@ def ncu_full(tag):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, body = rows[0], rows[1], rows[2:]
     with open(os.path.join(P, "%s_gemm_tc_ncu_full.txt" % tag), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on --profile-from-start off  (records 27, 26, 21 of the "
-                "feature-DDPM step at batch 256: SA1.att.v, SA1.att.w2, SA1.mlp.res; one cold launch each)\n")
+        f.write("# ncu --set full --clock-control none --import-source on --profile-from-start off  (feature-DDPM step at "
+                "batch 256, records SA1.att.v [TMA A], SA1.att.w2+softmax, SA1.mlp.res [TMA A], SA1.mlp.conv1; one cold launch each)\n")
         for m in METRICS:
             if m in hdr:
                 i = hdr.index(m)
