@@ -112,7 +112,7 @@ def main():
     ap.add_argument("--category", default="airplane")
     ap.add_argument("--ddpm-steps", type=int, default=None, help="DEBUG ONLY: truncate both DDPM loops (invalid as a benchmark)")
     ap.add_argument("--backend", default="auto", choices=["auto", "simt"])
-    ap.add_argument("--decode-chunk", type=int, default=32)
+    ap.add_argument("--decode-chunk", type=int, default=128)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

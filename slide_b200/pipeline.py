@@ -146,7 +146,7 @@ def default_state_dicts(seed=0):
 class SlidePipeline(object):
     """position DDPM -> latent DDPM -> decode for `local_batch` shapes on this GPU (rank `rank` of `world`)."""
 
-    def __init__(self, cfg, global_batch, rank=0, world=1, device=None, state_dicts=None, decode_chunk=32,
+    def __init__(self, cfg, global_batch, rank=0, world=1, device=None, state_dicts=None, decode_chunk=128,
                  ddpm_steps=None, backend="auto"):
         assert global_batch % world == 0
         self.cfg, self.B, self.rank, self.world = cfg, global_batch, rank, world
