@@ -38,10 +38,17 @@ extern "C" {
 
 struct slide_op {
   int32_t kind;  /* enum slide_op_kind */
-  int32_t flags; /* reserved */
+  int32_t flags; /* SLIDE_OPF_* */
   int64_t p[SLIDE_OP_NPARAM];
   float f[SLIDE_OP_NFPARAM];
 };
+
+/* Record flags.  SIDE: the record belongs to the side branch of a two-branch region (AttentionModule's key/query
+ * branch runs next to the shared MLP, they only meet at the soft-max).  The executor enqueues SIDE records on a
+ * second stream that first waits for everything enqueued before the region's first SIDE record; a SLIDE_OP_JOIN
+ * record makes the main stream wait for the side branch.  Records are stored in an order that is also a valid
+ * sequential order, so an executor may ignore the flag. */
+#define SLIDE_OPF_SIDE 1
 
 enum slide_op_kind {
   SLIDE_OP_NOP = 0,
@@ -59,6 +66,7 @@ enum slide_op_kind {
   SLIDE_OP_TEMB = 11,        /* sinusoidal timestep embedding (calc_t_emb) */
   SLIDE_OP_COLMAX = 12,      /* out[s,c] = max_r xf(X)[s*R + r, c]  (Pnet2Stage's global max-pool) */
   SLIDE_OP_KL = 13,          /* DiagonalGaussianDistribution: mode, or mean + exp(0.5*clamp(logvar)) * noise */
+  SLIDE_OP_JOIN = 14,        /* main branch waits for the side branch (no kernel) */
   SLIDE_OP_KIND_COUNT
 };
 

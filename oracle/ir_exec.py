@@ -105,6 +105,9 @@ class Machine(object):
     def op_nop(self, p, f):
         pass
 
+    def op_join(self, p, f):
+        pass  # records are stored in a valid sequential order
+
     def op_step_begin(self, p, f):
         off, n = int(p[V["SB_ZERO_OFF"]]), int(p[V["SB_ZERO_BYTES"]])
         if n > 0:

@@ -345,6 +345,10 @@ struct slide_program {
   cudaGraphExec_t graphs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int graph_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int gemm_backend = 0;  // 0 = auto (tcgen05 where eligible), 1 = fp32 FFMA everywhere
+  // two-branch regions (SLIDE_OPF_SIDE): a second stream plus fork / join events
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int use_side = 1;  // SLIDE_SIDE_BRANCH=0 runs everything on one stream
 };
 
 namespace {
@@ -384,6 +388,7 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
   const int64_t *q = op.p;
   switch (op.kind) {
     case SLIDE_OP_NOP:
+    case SLIDE_OP_JOIN:
       return SLIDE_OK;
     case SLIDE_OP_STEP_BEGIN: {
       const size_t n16 = (size_t)q[SB_ZERO_BYTES] / 16;
@@ -527,13 +532,40 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
   }
 }
 
+// Main-stream records go to `st`; SIDE records go to p->side.  The side stream forks lazily (it waits for everything
+// enqueued on `st` before the region's first SIDE record) and is joined at a JOIN record or at the end of the range,
+// so any sub-range (the tests run single records) is self-contained.
 int run_range(slide_program *p, int first, int count, cudaStream_t st) {
   if (!p || first < 0 || count < 0 || (size_t)(first + count) > p->ops.size()) return SLIDE_ERR_INVALID;
+  bool side_live = false;
+  auto join = [&]() -> int {
+    if (!side_live) return SLIDE_OK;
+    side_live = false;
+    int rc = cuda_rc(cudaEventRecord(p->ev_join, p->side));
+    if (rc == SLIDE_OK) rc = cuda_rc(cudaStreamWaitEvent(st, p->ev_join, 0));
+    return rc;
+  };
   for (int i = first; i < first + count; ++i) {
-    const int rc = run_op(p, p->ops[i], st);
-    if (rc != SLIDE_OK) return rc;
+    const slide_op &op = p->ops[i];
+    int rc = SLIDE_OK;
+    if (op.kind == SLIDE_OP_JOIN) {
+      rc = join();
+    } else if ((op.flags & SLIDE_OPF_SIDE) && p->use_side && p->side) {
+      if (!side_live) {
+        rc = cuda_rc(cudaEventRecord(p->ev_fork, st));
+        if (rc == SLIDE_OK) rc = cuda_rc(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+        side_live = true;
+      }
+      if (rc == SLIDE_OK) rc = run_op(p, op, p->side);
+    } else {
+      rc = run_op(p, op, st);
+    }
+    if (rc != SLIDE_OK) {
+      join();
+      return rc;
+    }
   }
-  return SLIDE_OK;
+  return join();
 }
 
 }  // namespace
@@ -549,11 +581,16 @@ int slide_program_create(const struct slide_op *ops, int n_ops, size_t arena_byt
   p->weights_bytes = weights_bytes;
   const char *be = getenv("SLIDE_GEMM_BACKEND");
   if (be && strcmp(be, "simt") == 0) p->gemm_backend = 1;
+  const char *sb = getenv("SLIDE_SIDE_BRANCH");
+  if (sb && atoi(sb) == 0) p->use_side = 0;
   int rc = cuda_rc(cudaMalloc((void **)&p->arena, arena_bytes > 0 ? arena_bytes : 256));
   if (rc == SLIDE_OK) rc = cuda_rc(cudaMemset(p->arena, 0, arena_bytes));
   if (rc == SLIDE_OK) rc = cuda_rc(cudaMalloc((void **)&p->weights, weights_bytes > 0 ? weights_bytes : 256));
   if (rc == SLIDE_OK && weights && weights_bytes)
     rc = cuda_rc(cudaMemcpy(p->weights, weights, weights_bytes, cudaMemcpyHostToDevice));
+  if (rc == SLIDE_OK) rc = cuda_rc(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+  if (rc == SLIDE_OK) rc = cuda_rc(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  if (rc == SLIDE_OK) rc = cuda_rc(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   if (rc != SLIDE_OK) {
     slide_program_destroy(p);
     return rc;
@@ -566,6 +603,9 @@ void slide_program_destroy(slide_program *p) {
   if (!p) return;
   for (int i = 0; i < 8; ++i)
     if (p->graphs[i]) cudaGraphExecDestroy(p->graphs[i]);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->side) cudaStreamDestroy(p->side);
   if (p->arena) cudaFree(p->arena);
   if (p->weights) cudaFree(p->weights);
   delete p;
@@ -633,7 +673,7 @@ int slide_program_launches(slide_program *p, int first, int count) {
   if (!p || first < 0 || count < 0 || (size_t)(first + count) > p->ops.size()) return SLIDE_ERR_INVALID;
   int n = 0;
   for (int i = first; i < first + count; ++i)
-    if (p->ops[i].kind != SLIDE_OP_NOP) ++n;
+    if (p->ops[i].kind != SLIDE_OP_NOP && p->ops[i].kind != SLIDE_OP_JOIN) ++n;
   return n;
 }
 

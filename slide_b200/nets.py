@@ -163,6 +163,12 @@ def _lower_mlp(ctx, P, G, R, name, out=None, use_t=False, use_cond=False, res=Tr
 
 def _lower_attention(ctx, P, q_feat, G, H, npnt, K, out, name):
     """AttentionModule(attention_bn=True, transform_grouped_feat_out=True); counts == K ('nn' neighbours)."""
+    return _attention_tail(ctx, P, _attention_keys(ctx, P, q_feat, G, npnt, K, name), H, npnt, K, out, name)
+
+
+def _attention_keys(ctx, P, q_feat, G, npnt, K, name):
+    """Query / key branch of AttentionModule up to the input of weight_conv.5: depends only on the query features and
+    the grouped tensor, NOT on the shared MLP's output, so callers emit it on the side branch next to that MLP."""
     b = ctx.b
     att = ctx.cfg["attention_setting"]
     assert att["attention_bn"] and att["transform_grouped_feat_out"]
@@ -190,6 +196,15 @@ def _lower_attention(ctx, P, q_feat, G, H, npnt, K, out, name):
     b.gemm(k, W1k, s1, bias=b1, act="relu", ev=qp, ev_div=K, stats=st2, st_R=npnt * K,
            xfa=XF(stats=st1.tensor, cg=cg1, nnorm=nn1, choff=C1, gamma=g1, beta=be1, R=npnt * K,
                   count=npnt * K * cg1), note=name + ".w1k")
+    return s1, st2, nn2, cg2
+
+
+def _attention_tail(ctx, P, keys, H, npnt, K, out, name):
+    """Value projection + weight_conv.5 + soft-max over the neighbours + weighted sum."""
+    b = ctx.b
+    att = ctx.cfg["attention_setting"]
+    B = H.B
+    s1, st2, nn2, cg2 = keys
     W2, b2 = _conv(b, P.sub("weight_conv.5"))
     Co = W2[2]
     Wv, bv = _conv(b, P.sub("feat_out_conv.0"))
@@ -244,9 +259,13 @@ def _lower_sa(ctx, P, xyz, feats, npoint, nsample, name):
     G = b.tensor(name + ".grouped", npnt * K, Cg, B=B)
     b.group(0, feats, feats.C, xyz, new_xyz, idx, K, G, include_abs=inc_abs, include_center=inc_ctr,
             note=name + ".group")
+    Pa = P.sub("attention_modules.0")
+    with b.side_branch():
+        keys = _attention_keys(ctx, Pa, q_feat, G, npnt, K, name + ".att")
     H = _lower_mlp(ctx, P.sub("mlps.0"), G, npnt * K, name + ".mlp", use_t=True, use_cond=True)
+    b.join(name + ".join")
     out = b.tensor(name + ".out", npnt, H.C, B=B)
-    _lower_attention(ctx, P.sub("attention_modules.0"), q_feat, G, H, npnt, K, out, name + ".att")
+    _attention_tail(ctx, Pa, keys, H, npnt, K, out, name + ".att")
     return new_xyz, out
 
 
@@ -258,10 +277,14 @@ def _lower_fp(ctx, P, unknown, known, unknow_feats, known_feats, K, name, out=No
     b.knn(unknown, known, K, idx, d2=d2, note=name + ".knn")
     G = b.tensor(name + ".grouped", n * K, known_feats.C + 11, B=B)
     b.group(1, known_feats, known_feats.C, known, unknown, idx, K, G, d2=d2, note=name + ".group")
+    Pa = P.sub("attention_module")
+    with b.side_branch():
+        keys = _attention_keys(ctx, Pa, unknow_feats, G, n, K, name + ".att")
     H1 = _lower_mlp(ctx, P.sub("mlp1"), G, n * K, name + ".mlp1")
+    b.join(name + ".join")
     d = H1.C
     cat = b.tensor(name + ".cat", n, d + unknow_feats.C + 3, B=B)
-    _lower_attention(ctx, P.sub("attention_module"), unknow_feats, G, H1, n, K, cat.cols(0, d), name + ".att")
+    _attention_tail(ctx, Pa, keys, H1, n, K, cat.cols(0, d), name + ".att")
     b.copy_cols(unknow_feats, cat.cols(d, unknow_feats.C), note=name + ".cat_skip")
     b.copy_cols(unknown.cols(0, 3), cat.cols(d + unknow_feats.C, 3), note=name + ".cat_xyz")
     return _lower_mlp(ctx, P.sub("mlp2"), cat, n, name + ".mlp2", out=out, use_t=True, use_cond=True)
@@ -278,8 +301,12 @@ def _lower_feature_map(ctx, P, xyz, feats, new_xyz, q_feat, nsample, name, out):
     G = b.tensor(name + ".grouped", npnt * K, Cg, B=B)
     b.group(0, feats, feats.C, xyz, new_xyz, idx, K, G, include_abs=inc_abs, include_center=inc_ctr,
             note=name + ".group")
+    Pa = P.sub("attention_module")
+    with b.side_branch():
+        keys = _attention_keys(ctx, Pa, q_feat, G, npnt, K, name + ".att")
     H = _lower_mlp(ctx, P.sub("mlp"), G, npnt * K, name + ".mlp")
-    return _lower_attention(ctx, P.sub("attention_module"), q_feat, G, H, npnt, K, out, name + ".att")
+    b.join(name + ".join")
+    return _attention_tail(ctx, Pa, keys, H, npnt, K, out, name + ".att")
 
 
 def t_embedding_source(b, P, cfg, T, name):

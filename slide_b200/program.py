@@ -41,6 +41,7 @@ def _parse_header():
 
 
 CONSTS, ENUMS, V = _parse_header()
+CONSTS_FLAGS = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(SLIDE_OPF_\w+)\s+(\d+)", open(_HEADER).read())}
 NPARAM = CONSTS["SLIDE_OP_NPARAM"]
 NFPARAM = CONSTS["SLIDE_OP_NFPARAM"]
 OP_DTYPE = np.dtype([("kind", "<i4"), ("flags", "<i4"), ("p", "<i8", (NPARAM,)), ("f", "<f4", (NFPARAM,))])
@@ -125,6 +126,7 @@ class Builder(object):
         self.step = Tensor("step", 1, 1, 1, 1, 0, "i32")
         self.segments = {}      # name -> (first_op, n_ops)
         self._seg_open = None
+        self._side = False      # records emitted while True carry SLIDE_OPF_SIDE
 
     # ---- allocation ------------------------------------------------------------------------------
     def tensor(self, name, R, C, B=None, dtype="f32", ld=None):
@@ -200,7 +202,26 @@ class Builder(object):
 
     # ---- op emitters -----------------------------------------------------------------------------
     def _emit(self, kind, fields, floats=(), note=""):
-        self.ops.append((KIND[kind], dict(fields), list(floats), note))
+        f = dict(fields)
+        if self._side:
+            f["__flags__"] = CONSTS_FLAGS["SLIDE_OPF_SIDE"]
+        self.ops.append((KIND[kind], f, list(floats), note))
+
+    def side_branch(self):
+        """Context manager: records emitted inside run on the side branch (see SLIDE_OPF_SIDE)."""
+        builder = self
+
+        class _Side(object):
+            def __enter__(self):
+                assert not builder._side
+                builder._side = True
+
+            def __exit__(self, *exc):
+                builder._side = False
+        return _Side()
+
+    def join(self, note="join"):
+        self._emit("SLIDE_OP_JOIN", {}, note=note)
 
     def step_begin(self):
         """Must be emitted AFTER every statistics buffer of the program has been allocated... the byte count is
@@ -321,6 +342,9 @@ class Builder(object):
             if kind == KIND["SLIDE_OP_STEP_BEGIN"]:
                 fields = dict(fields, SB_ZERO_BYTES=self.stats_end - self.stats_begin)
             for key, val in fields.items():
+                if key == "__flags__":
+                    rec[i]["flags"] = int(val)
+                    continue
                 idx = V[key[0]] + key[1] if isinstance(key, tuple) else V[key]
                 rec[i]["p"][idx] = int(val)
             for j, fv in enumerate(floats):
