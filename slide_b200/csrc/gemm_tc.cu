@@ -707,7 +707,17 @@ int launch_gemm_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t s
   // loop), so they take the narrowest tile that still fits in ONE wave: same critical path, less epilogue each.
   const int mt = ceil_div(a.M, TBM);
   const int wave = 2 * 148;
-  const int widest = a.N > 128 ? 256 : a.N > 64 ? 128 : a.N > 32 ? 64 : 32;
+#ifndef TC_MAX_BN
+#define TC_MAX_BN 256
+#endif
+#ifndef TC_STAGES_256
+#define TC_STAGES_256 2
+#endif
+#ifndef TC_STAGES_128
+#define TC_STAGES_128 3
+#endif
+  int widest = a.N > 128 ? 256 : a.N > 64 ? 128 : a.N > 32 ? 64 : 32;
+  if (widest > TC_MAX_BN) widest = TC_MAX_BN;
   int bn = widest;
   if (mt * ceil_div(a.N, widest) < wave) {
     for (int c = 32; c <= widest; c <<= 1) {
@@ -718,8 +728,8 @@ int launch_gemm_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t s
     }
   }
   switch (bn) {
-    case 256: return launch_tc<256, 2>(a, Wp, wp_na, st);
-    case 128: return launch_tc<128, 3>(a, Wp, wp_na, st);
+    case 256: return launch_tc<256, TC_STAGES_256>(a, Wp, wp_na, st);
+    case 128: return launch_tc<128, TC_STAGES_128>(a, Wp, wp_na, st);
     case 64: return launch_tc<64, 4>(a, Wp, wp_na, st);
     default: return launch_tc<32, 4>(a, Wp, wp_na, st);
   }
