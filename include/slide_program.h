@@ -67,6 +67,7 @@ enum slide_op_kind {
   SLIDE_OP_COLMAX = 12,      /* out[s,c] = max_r xf(X)[s*R + r, c]  (Pnet2Stage's global max-pool) */
   SLIDE_OP_KL = 13,          /* DiagonalGaussianDistribution: mode, or mean + exp(0.5*clamp(logvar)) * noise */
   SLIDE_OP_JOIN = 14,        /* main branch waits for the side branch (no kernel) */
+  SLIDE_OP_PAIR = 15,        /* a 1x1 conv over grouped rows, factored through the gather ("conv before gather") */
   SLIDE_OP_KIND_COUNT
 };
 
@@ -160,6 +161,20 @@ enum slide_upsample_field {
 
 /* out[i, 0:half] = sin(ts[i] * freq[j]), out[i, half:2*half] = cos(...); ts f32 [ROWS], FREQ_W f32 [half] */
 enum slide_temb_field { TE_TS = 0, TE_FREQ_W, TE_HALF, TE_OUT, TE_LDO, TE_ROWS };
+
+/* A 1x1 conv W over the grouped row of pair (i, j) -- QueryAndGroup's [f_j | x_j - c_i | x_j | c_i] or group_knn's
+ * [f_j | d2 | w | x_j | x_j - c_i | c_i] -- is linear in its parts, so the grouped tensor is never built:
+ *   out[(s,i,k), n] = act( U[(s, j), n] + x_j . WX[n, 0:3] + c_i . WC[n, 0:3] + bias[n]
+ *                          + d2_ik * WD[n] + w_ik * WW[n] + xfR(RES)[(s,i,k), n] ),      j = IDX[s,i,k]
+ * where U = f W_f^T comes from ONE GEMM over the NSRC source points (not over the NP*K pairs), WX = W_abs + W_rel,
+ * WC = W_ctr - W_rel (host-combined, [N,3] row-major in WEIGHTS), WD / WW the d2 / w columns (group_knn only, else -1),
+ * w_ik = (1/(d2_ik+1e-8)) / sum_k(1/(d2_ik+1e-8)).  Statistics of out as for GEMM (ST_* fields). */
+enum slide_pair_field {
+  PR_U = 0, PR_LDU, PR_NSRC, PR_XYZ, PR_LDX, PR_CTR, PR_LDCTR, PR_NP, PR_IDX, PR_K, PR_D2,
+  PR_WX_W, PR_WC_W, PR_WD_W, PR_WW_W, PR_BIAS_W, PR_N, PR_OUT, PR_LDO, PR_ACT, PR_RES, PR_LDR,
+  PR_ST_STATS, PR_ST_CG, PR_ST_NNORM, PR_ST_CHOFF, PR_ST_WEIGHT, PR_B, PR_STEP,
+  PR_XFR, PR_NFIELD = PR_XFR + XF_NFIELD
+};
 
 /* out f32 [B, C] (row stride LDO); X f32 [B*R, C]; XF block = transform applied to X before the max
  * (pointnet2/models/pnet.py:32-39: F.max_pool2d over the points after the shared MLP's GroupNorm + ReLU) */

@@ -265,6 +265,48 @@ class Machine(object):
         out = coarse[:, None, :] + (disp * np.float32(f[0])) * np.float32(f[1])
         self.A(g("UP_OUT"), rows * fac, g("UP_LDO"), Fd)[...] = out.reshape(rows * fac, Fd).astype(np.float32)
 
+    def op_pair(self, p, f):
+        g = lambda k: int(p[V[k]])
+        B, Ns, npnt, K, N = g("PR_B"), g("PR_NSRC"), g("PR_NP"), g("PR_K"), g("PR_N")
+        idx = self.A(g("PR_IDX"), B * npnt, K, None, np.int32).reshape(B, npnt, K).astype(np.int64)
+        U = self.A(g("PR_U"), B * Ns, g("PR_LDU"), N).reshape(B, Ns, N)
+        xyz = self.A(g("PR_XYZ"), B * Ns, g("PR_LDX"), 3).reshape(B, Ns, 3)
+        ctr = self.A(g("PR_CTR"), B * npnt, g("PR_LDCTR"), 3).reshape(B, npnt, 3)
+        bi = np.arange(B)[:, None, None]
+        wx = self.W(g("PR_WX_W"), N, 3)
+        wc = self.W(g("PR_WC_W"), N, 3)
+        out = U[bi, idx] + xyz[bi, idx] @ wx.T + (ctr @ wc.T)[:, :, None, :]
+        if g("PR_BIAS_W") >= 0:
+            out = out + self.Wv(g("PR_BIAS_W"), N)
+        if g("PR_D2") >= 0:
+            d2 = self.A(g("PR_D2"), B * npnt, K).reshape(B, npnt, K, 1)
+            inv = (np.float32(1.0) / (d2 + np.float32(1e-8))).astype(np.float32)
+            w = inv / inv.sum(axis=2, keepdims=True, dtype=np.float32)
+            out = out + d2 * self.Wv(g("PR_WD_W"), N) + w * self.Wv(g("PR_WW_W"), N)
+        M = B * npnt * K
+        c = out.reshape(M, N).astype(np.float32)
+        if g("PR_RES") >= 0:
+            c = c + self.xf(np.array(self.A(g("PR_RES"), M, g("PR_LDR"), N)), p, V["PR_XFR"], g("PR_STEP"))
+        act = g("PR_ACT")
+        if act == 1:
+            c = np.maximum(c, 0)
+        c = c.astype(np.float32)
+        self.A(g("PR_OUT"), M, g("PR_LDO"), N)[...] = c
+        if g("PR_ST_STATS") >= 0:
+            cg, nnorm, choff, wgt = g("PR_ST_CG"), g("PR_ST_NNORM"), g("PR_ST_CHOFF"), g("PR_ST_WEIGHT")
+            G = nnorm // cg
+            R = npnt * K
+            st = self.A(g("PR_ST_STATS"), B, 2 * G, None, np.float64).reshape(B, G, 2)
+            ch = choff + np.arange(N)
+            sel = ch < nnorm
+            if sel.any():
+                v = c[:, sel].astype(np.float64).reshape(B, R, -1)
+                grp = ch[sel] // cg
+                for gi in np.unique(grp):
+                    cols = grp == gi
+                    st[:, gi, 0] += wgt * v[:, :, cols].sum(axis=(1, 2))
+                    st[:, gi, 1] += wgt * (v[:, :, cols] ** 2).sum(axis=(1, 2))
+
     def op_colmax(self, p, f):
         g = lambda k: int(p[V[k]])
         B, R, C = g("CM_B"), g("CM_R"), g("CM_C")

@@ -276,6 +276,131 @@ __global__ void temb_kernel(const float *__restrict__ ts, const float *__restric
   out[(size_t)r * ldo + half + j] = cosf(arg);
 }
 
+// =====================================================================================================
+// PAIR: a 1x1 conv over grouped rows, factored through the gather (see slide_program.h)
+// =====================================================================================================
+// CTA = (block of PB points of one sample) x all N columns; thread = column (coalesced U gathers / stores / residual
+// loads), loop over the block's points and their K neighbours.  Index, coordinate and distance loads are warp-uniform
+// broadcasts.  Per-column statistics stay in registers and leave the CTA as one fp64 atomic per (group, moment).
+struct PairArgs {
+  const float *U;
+  int ldu, nsrc;
+  const float *xyz;
+  int ldx;
+  const float *ctr;
+  int ldctr, np;
+  const int *idx;
+  int K;
+  const float *d2;
+  const float *wx, *wc, *wd, *ww, *bias;
+  int N;
+  float *out;
+  int ldo, act;
+  const float *res;
+  int ldr;
+  double *st_stats;
+  int st_cg, st_nnorm, st_choff;
+  float st_weight;
+  XFd xfr;
+  const int *step;
+  int pb;  // points per CTA
+};
+
+__global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
+  const int s = blockIdx.y;
+  const int p0 = blockIdx.x * a.pb;
+  const int p1 = min(p0 + a.pb, a.np);
+  const int lane = threadIdx.x & 31;
+  const int step = a.step ? *a.step : 0;
+  const int R = a.np * a.K;
+  for (int n0 = 0; n0 < a.N; n0 += blockDim.x) {
+    const int n = n0 + threadIdx.x;
+    const bool on = n < a.N;
+    const int nn = on ? n : 0;
+    const float wx0 = __ldg(a.wx + nn * 3), wx1 = __ldg(a.wx + nn * 3 + 1), wx2 = __ldg(a.wx + nn * 3 + 2);
+    const float wc0 = __ldg(a.wc + nn * 3), wc1 = __ldg(a.wc + nn * 3 + 1), wc2 = __ldg(a.wc + nn * 3 + 2);
+    const float bias = a.bias ? __ldg(a.bias + nn) : 0.f;
+    const float wd = a.d2 ? __ldg(a.wd + nn) : 0.f, ww = a.d2 ? __ldg(a.ww + nn) : 0.f;
+    // resid transform for this (sample, column)
+    float rsc = 1.f, rsh = 0.f, radd = 0.f;
+    if (a.res) {
+      if (a.xfr.stats) {
+        const int ch = a.xfr.choff + nn;
+        if (ch < a.xfr.nnorm) {
+          const int G = a.xfr.nnorm / a.xfr.cg;
+          const double *st = a.xfr.stats + ((size_t)s * G + ch / a.xfr.cg) * 2;
+          const double m = st[0] * (double)a.xfr.inv_count;
+          double var = st[1] * (double)a.xfr.inv_count - m * m;
+          var = var < 0.0 ? 0.0 : var;
+          rsc = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS)) * __ldg(a.xfr.gamma + ch);
+          rsh = __ldg(a.xfr.beta + ch) - (float)m * rsc;
+        }
+      }
+      if (a.xfr.addvec) {
+        const long long arow = a.xfr.addmode == 0 ? s : (a.xfr.addmode == 1 ? step : 0);
+        radd = a.xfr.addvec[arow * a.xfr.addld + nn];
+      }
+    }
+    float ssum = 0.f, ssq = 0.f;
+    for (int i = p0; i < p1; ++i) {
+      const float *c = a.ctr + ((size_t)s * a.np + i) * a.ldctr;
+      const float vterm = fmaf(__ldg(c + 2), wc2, fmaf(__ldg(c + 1), wc1, fmaf(__ldg(c), wc0, bias)));
+      const size_t prow = ((size_t)s * a.np + i) * a.K;
+      float inv_sum = 0.f;
+      if (a.d2)
+        for (int k = 0; k < a.K; ++k) inv_sum = __fadd_rn(inv_sum, __fdiv_rn(1.0f, __fadd_rn(__ldg(a.d2 + prow + k), 1e-8f)));
+#pragma unroll 4
+      for (int k = 0; k < a.K; ++k) {
+        const size_t row = prow + k;
+        const int j = __ldg(a.idx + row);
+        const float *x = a.xyz + ((size_t)s * a.nsrc + j) * a.ldx;
+        float v = on ? a.U[((size_t)s * a.nsrc + j) * a.ldu + n] : 0.f;
+        v = fmaf(__ldg(x + 2), wx2, fmaf(__ldg(x + 1), wx1, fmaf(__ldg(x), wx0, v))) + vterm;
+        if (a.d2) {
+          const float dk = __ldg(a.d2 + row);
+          const float w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(dk, 1e-8f)), inv_sum);
+          v = fmaf(w, ww, fmaf(dk, wd, v));
+        }
+        if (a.res && on) {
+          float r = fmaf(a.res[row * a.ldr + n], rsc, rsh);
+          if (a.xfr.relu) r = fmaxf(r, 0.f);
+          v += r + radd;
+        }
+        if (a.act == 1) v = fmaxf(v, 0.f);
+        if (on) {
+          a.out[row * a.ldo + n] = v;
+          ssum += v;
+          ssq = fmaf(v, v, ssq);
+        }
+      }
+    }
+    if (a.st_stats) {
+      const int ch = a.st_choff + nn;
+      bool dost = on && ch < a.st_nnorm;
+      const int seg = a.st_cg < 32 ? a.st_cg : 32;
+      const bool pow2 = (a.st_cg & (a.st_cg - 1)) == 0 && ((a.st_choff + n0) % seg) == 0 && (a.st_nnorm % seg) == 0;
+      if (!dost) {
+        ssum = 0.f;
+        ssq = 0.f;
+      }
+      if (pow2) {  // the lanes of one GroupNorm group are consecutive and aligned: butterfly sum, one atomic per group
+        for (int d = 1; d < seg; d <<= 1) {
+          ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
+          ssq += __shfl_xor_sync(0xffffffffu, ssq, d);
+        }
+        dost = dost && (lane & (seg - 1)) == 0;
+      }
+      if (dost) {
+        const int G = a.st_nnorm / a.st_cg;
+        double *slot = a.st_stats + ((size_t)s * G + ch / a.st_cg) * 2;
+        atomicAdd(slot, (double)ssum * (double)a.st_weight);
+        atomicAdd(slot + 1, (double)ssq * (double)a.st_weight);
+      }
+    }
+  }
+  (void)R;
+}
+
 // out[s,c] = max_r xf(X)[s*R + r, c]: thread per (sample, column), coalesced in c (Pnet2Stage's global max-pool)
 __global__ void colmax_kernel(const float *__restrict__ X, int ldx, int R, int C, XFd xf,
                               const int *__restrict__ step_ptr, float *__restrict__ out, int ldo, int B) {
@@ -508,6 +633,50 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       const int rows = (int)q[TE_ROWS], half = (int)q[TE_HALF];
       temb_kernel<<<grid_for((long long)rows * half, 256), 256, 0, st>>>(
           AP<float>(p, q[TE_TS]), WP<float>(p, q[TE_FREQ_W]), half, AP<float>(p, q[TE_OUT]), (int)q[TE_LDO], rows);
+      return after_launch();
+    }
+    case SLIDE_OP_PAIR: {
+      PairArgs a;
+      a.U = AP<float>(p, q[PR_U]);
+      a.ldu = (int)q[PR_LDU];
+      a.nsrc = (int)q[PR_NSRC];
+      a.xyz = AP<float>(p, q[PR_XYZ]);
+      a.ldx = (int)q[PR_LDX];
+      a.ctr = AP<float>(p, q[PR_CTR]);
+      a.ldctr = (int)q[PR_LDCTR];
+      a.np = (int)q[PR_NP];
+      a.idx = AP<int>(p, q[PR_IDX]);
+      a.K = (int)q[PR_K];
+      a.d2 = AP<float>(p, q[PR_D2]);
+      a.wx = WP<float>(p, q[PR_WX_W]);
+      a.wc = WP<float>(p, q[PR_WC_W]);
+      a.wd = WP<float>(p, q[PR_WD_W]);
+      a.ww = WP<float>(p, q[PR_WW_W]);
+      a.bias = WP<float>(p, q[PR_BIAS_W]);
+      a.N = (int)q[PR_N];
+      a.out = AP<float>(p, q[PR_OUT]);
+      a.ldo = (int)q[PR_LDO];
+      a.act = (int)q[PR_ACT];
+      a.res = AP<float>(p, q[PR_RES]);
+      a.ldr = (int)q[PR_LDR];
+      a.st_stats = AP<double>(p, q[PR_ST_STATS]);
+      a.st_cg = (int)q[PR_ST_CG] > 0 ? (int)q[PR_ST_CG] : 1;
+      a.st_nnorm = (int)q[PR_ST_NNORM];
+      a.st_choff = (int)q[PR_ST_CHOFF];
+      a.st_weight = (float)q[PR_ST_WEIGHT];
+      a.xfr = make_xf(p, q + PR_XFR);
+      a.step = AP<int>(p, q[PR_STEP]);
+      const int B = (int)q[PR_B];
+      if (!a.U || !a.out || !a.idx || a.K <= 0 || B <= 0 || B > 65535) return SLIDE_ERR_INVALID;
+      if (a.d2 && (!a.wd || !a.ww)) return SLIDE_ERR_INVALID;
+      if (a.res && a.xfr.stats && a.xfr.R != a.np * a.K) return SLIDE_ERR_UNSUPPORTED;
+      // points per CTA: aim for >= ~4 CTAs per SM overall, at least 64 rows per CTA
+      int pb = a.np;
+      while (pb > 1 && (long long)B * ceil_div(a.np, pb) < 592 && pb * a.K > 64) pb = (pb + 1) / 2;
+      a.pb = pb;
+      const int threads = a.N >= 256 ? 256 : ((a.N + 31) / 32) * 32;
+      dim3 grid(ceil_div(a.np, pb), B);
+      pair_kernel<<<grid, threads, 0, st>>>(a);
       return after_launch();
     }
     case SLIDE_OP_COLMAX: {

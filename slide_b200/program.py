@@ -314,6 +314,23 @@ class Builder(object):
                                          "UP_ROWS": coarse.rows, "UP_FACTOR": factor, "UP_F": Fd},
                    floats=[np.float32(1 / np.sqrt(factor)), np.float32(scale)], note=note)
 
+    def pair(self, U, xyz, ctr, idx, K, out, wx, wc, bias=-1, d2=None, wd=-1, ww=-1, act=None, resid=None, xfr=NO_XF,
+             stats=None, st_choff=0, st_weight=1, note=""):
+        """Factored conv over grouped rows (SLIDE_OP_PAIR).  U: [B*Nsrc, N] view; out: [B*np*K, N]."""
+        npnt = ctr.R
+        assert out.R == npnt * K and out.C == U.C and idx.C == K and U.R == xyz.R
+        f = {"PR_U": U.off, "PR_LDU": U.ld, "PR_NSRC": U.R, "PR_XYZ": xyz.off, "PR_LDX": xyz.ld, "PR_CTR": ctr.off,
+             "PR_LDCTR": ctr.ld, "PR_NP": npnt, "PR_IDX": idx.off, "PR_K": K, "PR_D2": d2.off if d2 is not None else -1,
+             "PR_WX_W": wx, "PR_WC_W": wc, "PR_WD_W": wd, "PR_WW_W": ww, "PR_BIAS_W": bias, "PR_N": out.C,
+             "PR_OUT": out.off, "PR_LDO": out.ld, "PR_ACT": ACT[act], "PR_RES": resid.off if resid is not None else -1,
+             "PR_LDR": resid.ld if resid is not None else 0,
+             "PR_ST_STATS": stats.tensor.off if stats is not None else -1, "PR_ST_CG": stats.cg if stats is not None else 1,
+             "PR_ST_NNORM": stats.nnorm if stats is not None else 0, "PR_ST_CHOFF": st_choff, "PR_ST_WEIGHT": st_weight,
+             "PR_B": out.B, "PR_STEP": self.step.off}
+        for i, val in enumerate(xfr.fields()):
+            f[("PR_XFR", i)] = val
+        self._emit("SLIDE_OP_PAIR", f, note=note)
+
     def colmax(self, X, xf, R, out, note=""):
         assert out.C == X.C and X.rows == out.rows * R
         f = {"CM_X": X.off, "CM_LDX": X.ld, "CM_R": R, "CM_C": X.C, "CM_OUT": out.off, "CM_LDO": out.ld,
