@@ -307,98 +307,148 @@ struct PairArgs {
 };
 
 __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
+  // thread = 4 consecutive columns (128-bit U gathers / residual loads / stores); the per-row index, coordinate and
+  // distance loads are amortised over the 4 outputs
   const int s = blockIdx.y;
   const int p0 = blockIdx.x * a.pb;
   const int p1 = min(p0 + a.pb, a.np);
   const int lane = threadIdx.x & 31;
   const int step = a.step ? *a.step : 0;
-  const int R = a.np * a.K;
-  for (int n0 = 0; n0 < a.N; n0 += blockDim.x) {
-    const int n = n0 + threadIdx.x;
-    const bool on = n < a.N;
-    const int nn = on ? n : 0;
-    const float wx0 = __ldg(a.wx + nn * 3), wx1 = __ldg(a.wx + nn * 3 + 1), wx2 = __ldg(a.wx + nn * 3 + 2);
-    const float wc0 = __ldg(a.wc + nn * 3), wc1 = __ldg(a.wc + nn * 3 + 1), wc2 = __ldg(a.wc + nn * 3 + 2);
-    const float bias = a.bias ? __ldg(a.bias + nn) : 0.f;
-    const float wd = a.d2 ? __ldg(a.wd + nn) : 0.f, ww = a.d2 ? __ldg(a.ww + nn) : 0.f;
-    // resid transform for this (sample, column)
-    float rsc = 1.f, rsh = 0.f, radd = 0.f;
-    if (a.res) {
-      if (a.xfr.stats) {
-        const int ch = a.xfr.choff + nn;
-        if (ch < a.xfr.nnorm) {
-          const int G = a.xfr.nnorm / a.xfr.cg;
-          const double *st = a.xfr.stats + ((size_t)s * G + ch / a.xfr.cg) * 2;
-          const double m = st[0] * (double)a.xfr.inv_count;
-          double var = st[1] * (double)a.xfr.inv_count - m * m;
-          var = var < 0.0 ? 0.0 : var;
-          rsc = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS)) * __ldg(a.xfr.gamma + ch);
-          rsh = __ldg(a.xfr.beta + ch) - (float)m * rsc;
+  for (int n0 = 0; n0 < a.N; n0 += 4 * blockDim.x) {
+    const int n = n0 + 4 * threadIdx.x;
+    bool on[4];
+    float wx[4][3], wc[4][3], bias[4], wd[4], ww[4], rsc[4], rsh[4], radd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      on[u] = n + u < a.N;
+      const int nn = on[u] ? n + u : 0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        wx[u][d] = __ldg(a.wx + nn * 3 + d);
+        wc[u][d] = __ldg(a.wc + nn * 3 + d);
+      }
+      bias[u] = a.bias ? __ldg(a.bias + nn) : 0.f;
+      wd[u] = a.d2 ? __ldg(a.wd + nn) : 0.f;
+      ww[u] = a.d2 ? __ldg(a.ww + nn) : 0.f;
+      rsc[u] = 1.f;
+      rsh[u] = 0.f;
+      radd[u] = 0.f;
+      if (a.res) {
+        if (a.xfr.stats) {
+          const int ch = a.xfr.choff + nn;
+          if (ch < a.xfr.nnorm) {
+            const int G = a.xfr.nnorm / a.xfr.cg;
+            const double *st = a.xfr.stats + ((size_t)s * G + ch / a.xfr.cg) * 2;
+            const double m = st[0] * (double)a.xfr.inv_count;
+            double var = st[1] * (double)a.xfr.inv_count - m * m;
+            var = var < 0.0 ? 0.0 : var;
+            rsc[u] = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS)) * __ldg(a.xfr.gamma + ch);
+            rsh[u] = __ldg(a.xfr.beta + ch) - (float)m * rsc[u];
+          }
+        }
+        if (a.xfr.addvec) {
+          const long long arow = a.xfr.addmode == 0 ? s : (a.xfr.addmode == 1 ? step : 0);
+          radd[u] = a.xfr.addvec[arow * a.xfr.addld + nn];
         }
       }
-      if (a.xfr.addvec) {
-        const long long arow = a.xfr.addmode == 0 ? s : (a.xfr.addmode == 1 ? step : 0);
-        radd = a.xfr.addvec[arow * a.xfr.addld + nn];
-      }
     }
-    float ssum = 0.f, ssq = 0.f;
+    const bool any = on[0];
+    const bool full = on[3];
+    float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = p0; i < p1; ++i) {
       const float *c = a.ctr + ((size_t)s * a.np + i) * a.ldctr;
-      const float vterm = fmaf(__ldg(c + 2), wc2, fmaf(__ldg(c + 1), wc1, fmaf(__ldg(c), wc0, bias)));
+      const float c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+      float vterm[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) vterm[u] = fmaf(c2, wc[u][2], fmaf(c1, wc[u][1], fmaf(c0, wc[u][0], bias[u])));
       const size_t prow = ((size_t)s * a.np + i) * a.K;
       float inv_sum = 0.f;
       if (a.d2)
         for (int k = 0; k < a.K; ++k) inv_sum = __fadd_rn(inv_sum, __fdiv_rn(1.0f, __fadd_rn(__ldg(a.d2 + prow + k), 1e-8f)));
-#pragma unroll 4
+#pragma unroll 2
       for (int k = 0; k < a.K; ++k) {
         const size_t row = prow + k;
         const int j = __ldg(a.idx + row);
         const float *x = a.xyz + ((size_t)s * a.nsrc + j) * a.ldx;
-        float v = on ? a.U[((size_t)s * a.nsrc + j) * a.ldu + n] : 0.f;
-        v = fmaf(__ldg(x + 2), wx2, fmaf(__ldg(x + 1), wx1, fmaf(__ldg(x), wx0, v))) + vterm;
+        const float x0 = __ldg(x), x1 = __ldg(x + 1), x2 = __ldg(x + 2);
+        float4 uu = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (any) uu = *reinterpret_cast<const float4 *>(a.U + ((size_t)s * a.nsrc + j) * a.ldu + n);
+        float v[4] = {uu.x, uu.y, uu.z, uu.w};
+        float dk = 0.f, w = 0.f;
         if (a.d2) {
-          const float dk = __ldg(a.d2 + row);
-          const float w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(dk, 1e-8f)), inv_sum);
-          v = fmaf(w, ww, fmaf(dk, wd, v));
+          dk = __ldg(a.d2 + row);
+          w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(dk, 1e-8f)), inv_sum);
         }
-        if (a.res && on) {
-          float r = fmaf(a.res[row * a.ldr + n], rsc, rsh);
-          if (a.xfr.relu) r = fmaxf(r, 0.f);
-          v += r + radd;
+        float rr[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.res && any) {
+          if (full) {
+            const float4 r4 = *reinterpret_cast<const float4 *>(a.res + row * a.ldr + n);
+            rr[0] = r4.x; rr[1] = r4.y; rr[2] = r4.z; rr[3] = r4.w;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (on[u]) rr[u] = a.res[row * a.ldr + n + u];
+          }
         }
-        if (a.act == 1) v = fmaxf(v, 0.f);
-        if (on) {
-          a.out[row * a.ldo + n] = v;
-          ssum += v;
-          ssq = fmaf(v, v, ssq);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float t = fmaf(x2, wx[u][2], fmaf(x1, wx[u][1], fmaf(x0, wx[u][0], v[u]))) + vterm[u];
+          if (a.d2) t = fmaf(w, ww[u], fmaf(dk, wd[u], t));
+          if (a.res) {
+            float r = fmaf(rr[u], rsc[u], rsh[u]);
+            if (a.xfr.relu) r = fmaxf(r, 0.f);
+            t += r + radd[u];
+          }
+          if (a.act == 1) t = fmaxf(t, 0.f);
+          v[u] = on[u] ? t : 0.f;
+          ssum[u] += v[u];
+          ssq[u] = fmaf(v[u], v[u], ssq[u]);
+        }
+        if (full) {
+          *reinterpret_cast<float4 *>(a.out + row * a.ldo + n) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (on[u]) a.out[row * a.ldo + n + u] = v[u];
         }
       }
     }
     if (a.st_stats) {
-      const int ch = a.st_choff + nn;
-      bool dost = on && ch < a.st_nnorm;
-      const int seg = a.st_cg < 32 ? a.st_cg : 32;
-      const bool pow2 = (a.st_cg & (a.st_cg - 1)) == 0 && ((a.st_choff + n0) % seg) == 0 && (a.st_nnorm % seg) == 0;
-      if (!dost) {
-        ssum = 0.f;
-        ssq = 0.f;
-      }
-      if (pow2) {  // the lanes of one GroupNorm group are consecutive and aligned: butterfly sum, one atomic per group
-        for (int d = 1; d < seg; d <<= 1) {
-          ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
-          ssq += __shfl_xor_sync(0xffffffffu, ssq, d);
+      const int G = a.st_nnorm / a.st_cg;
+      const int ch0 = a.st_choff + n;
+      const bool pow2 = (a.st_cg & (a.st_cg - 1)) == 0 && (a.st_choff % a.st_cg) == 0 && (n0 % a.st_cg) == 0;
+      if (pow2 && a.st_cg >= 4) {
+        // the thread's 4 columns lie in one GroupNorm group; the group's threads are st_cg/4 consecutive, aligned lanes
+        float ts = 0.f, tq = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (on[u] && ch0 + u < a.st_nnorm) {
+            ts += ssum[u];
+            tq += ssq[u];
+          }
         }
-        dost = dost && (lane & (seg - 1)) == 0;
-      }
-      if (dost) {
-        const int G = a.st_nnorm / a.st_cg;
-        double *slot = a.st_stats + ((size_t)s * G + ch / a.st_cg) * 2;
-        atomicAdd(slot, (double)ssum * (double)a.st_weight);
-        atomicAdd(slot + 1, (double)ssq * (double)a.st_weight);
+        const int seg = min(a.st_cg / 4, 32);
+        for (int d = 1; d < seg; d <<= 1) {
+          ts += __shfl_xor_sync(0xffffffffu, ts, d);
+          tq += __shfl_xor_sync(0xffffffffu, tq, d);
+        }
+        if ((lane & (seg - 1)) == 0 && any && ch0 < a.st_nnorm) {
+          double *slot = a.st_stats + ((size_t)s * G + ch0 / a.st_cg) * 2;
+          atomicAdd(slot, (double)ts * (double)a.st_weight);
+          atomicAdd(slot + 1, (double)tq * (double)a.st_weight);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (on[u] && ch0 + u < a.st_nnorm) {
+            double *slot = a.st_stats + ((size_t)s * G + (ch0 + u) / a.st_cg) * 2;
+            atomicAdd(slot, (double)ssum[u] * (double)a.st_weight);
+            atomicAdd(slot + 1, (double)ssq[u] * (double)a.st_weight);
+          }
+        }
       }
     }
   }
-  (void)R;
 }
 
 // out[s,c] = max_r xf(X)[s*R + r, c]: thread per (sample, column), coalesced in c (Pnet2Stage's global max-pool)
@@ -674,7 +724,11 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       int pb = a.np;
       while (pb > 1 && (long long)B * ceil_div(a.np, pb) < 592 && pb * a.K > 64) pb = (pb + 1) / 2;
       a.pb = pb;
-      const int threads = a.N >= 256 ? 256 : ((a.N + 31) / 32) * 32;
+      if (((uintptr_t)a.U & 15) || (a.ldu & 3) || ((uintptr_t)a.out & 15) || (a.ldo & 3) ||
+          (a.res && (((uintptr_t)a.res & 15) || (a.ldr & 3))))
+        return SLIDE_ERR_UNSUPPORTED;  // 128-bit row accesses
+      const int cols4 = ceil_div(a.N, 4);
+      const int threads = cols4 >= 256 ? 256 : ((cols4 + 31) / 32) * 32;
       dim3 grid(ceil_div(a.np, pb), B);
       pair_kernel<<<grid, threads, 0, st>>>(a);
       return after_launch();
