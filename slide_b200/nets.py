@@ -26,6 +26,8 @@ import numpy as np
 from .program import XF, NO_XF, Builder  # noqa: F401
 
 
+FACTOR_MIN_WORK = 250000  # see _Grouped.plan
+
 # contractions at least this large get a tensor-core weight copy (the kernel applies further shape tests)
 TC_MIN_K, TC_MIN_N = 32, 32
 
@@ -113,14 +115,15 @@ class _Grouped(object):
         self.R = self.np * K
         self.C = feats.C
         self.Ctot = self.C + (11 if mode == 1 else 3 + 3 * int(inc_abs) + 3 * int(inc_ctr))
-        self.factored = os.environ.get("SLIDE_FACTOR_GROUP", "1") != "0"
+        self.factored = None  # decided in plan(): depends on how wide the convs reading the group are
         self.G = None
         self.U = None
         self.slices = {}
-        if not self.factored:
-            self.G = self.b.tensor(name + ".grouped", self.R, self.Ctot, B=self.B)
-            self.b.group(mode, feats, self.C, xyz, ctr, idx, K, self.G, d2=d2, include_abs=inc_abs, include_center=inc_ctr,
-                         note=name + ".group")
+
+    def _materialise(self):
+        self.G = self.b.tensor(self.name + ".grouped", self.R, self.Ctot, B=self.B)
+        self.b.group(self.mode, self.feats, self.C, self.xyz, self.ctr, self.idx, self.K, self.G, d2=self.d2,
+                     include_abs=self.inc_abs, include_center=self.inc_ctr, note=self.name + ".group")
 
     def _split(self, w):
         """(N, Ctot) conv weight -> (W_f, WX, WC, wd, ww) for the factored form."""
@@ -140,8 +143,15 @@ class _Grouped(object):
         return w[:, :C], ab + rel, ct - rel, wd, ww
 
     def plan(self, convs):
-        """convs: list of Params of every conv that reads the group.  Emits the shared U GEMM (factored form)."""
+        """convs: list of Params of every conv that reads the group.  Chooses the form and emits the GROUP record
+        (materialised) or the shared U GEMM (factored).  A/B on B200 (feature / position DDPM, batch 256): factoring pays
+        once the pair-level GEMMs it removes are large -- Ctot x (sum of conv widths) above ~2.5e5 -- below that the
+        tcgen05 GEMMs over the grouped tensor are cheaper than the extra U GEMM + the gather-bound PAIR kernels."""
+        ntot = sum(int(Pc["weight"].shape[0]) for Pc in convs)
+        mode = os.environ.get("SLIDE_FACTOR_GROUP", "auto")
+        self.factored = (mode == "1") or (mode == "auto" and self.Ctot * ntot >= FACTOR_MIN_WORK)
         if not self.factored:
+            self._materialise()
             return
         b = self.b
         parts, off = [], 0
