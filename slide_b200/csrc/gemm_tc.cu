@@ -601,6 +601,308 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
   }
 }
 
+// =====================================================================================================
+// Persistent variant (TMA for both operands): one CTA per SM loops over output tiles; a 3-stage operand ring and a
+// DOUBLE-BUFFERED accumulator in tensor memory let the MMAs of tile i+1 run while eight epilogue warps drain tile i.
+//   warp 0   : TMA producer (A tensor copy + W bulk copy per K block)
+//   warp 1   : TMEM allocation (2 x BN columns) + tcgen05.mma issue
+//   warps 2-9: epilogue (TMEM -> registers -> smem transpose -> coalesced stores, statistics)
+// Used when A needs no transform, every row tile lies inside one sample (R % 128 == 0) and M % 128 == 0.
+// =====================================================================================================
+constexpr int TCP_EPI_WARPS = 8;
+constexpr int TCP_THREADS = 32 * (2 + TCP_EPI_WARPS);
+
+__host__ __device__ constexpr int tcp_smem_bytes(int BN, int STAGES) {
+  return STAGES * tc_stage_bytes(BN) + TCP_EPI_WARPS * 32 * 33 * 4 + 2 * BN * 16 + 512 /*barriers*/ + 2 * XF_MAXG * 2 * 4;
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TCP_EPI_WARPS * 32) : "memory"); }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
+                                                                  const __grid_constant__ CUtensorMap tmA) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int STAGE_BYTES = tc_stage_bytes(BN);
+  constexpr int W_BYTES = BN * TBK * 4;
+  constexpr uint32_t A_BYTES = TBM * TBK * 4;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // BN in {32,...,256}: a power of two
+  float *tbuf_all = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
+  float4 *tabR_all = reinterpret_cast<float4 *>(smem + STAGES * STAGE_BYTES + TCP_EPI_WARPS * 32 * 33 * 4);
+  uint8_t *ctrl = reinterpret_cast<uint8_t *>(tabR_all) + 2 * BN * 16;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(ctrl);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tfull_bar = empty_bar + STAGES;
+  uint64_t *tempty_bar = tfull_bar + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+  float *stacc_all = reinterpret_cast<float *>(ctrl + 512);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int step = a.step ? *a.step : 0;
+  const int num_kb = (a.K + TBK - 1) / TBK;
+  const int tiles_n = (a.N + BN - 1) / BN;
+  const int tiles = (a.M / TBM) * tiles_n;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(tfull_bar + b), 1);
+      mbar_init(smem_u32(tempty_bar + b), TCP_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  bool ok = true;
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint64_t tmap = reinterpret_cast<uint64_t>(&tmA);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * TBM, n0 = (t % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          if (ok) ok = mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t bar = smem_u32(full_bar + s);
+          mbar_arrive_expect_tx(bar, A_BYTES + (uint32_t)W_BYTES);
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(sa),
+              "l"(tmap), "r"(kb * TBK), "r"(m0), "r"(bar)
+              : "memory");
+          const float *src = Wp + ((size_t)kb * wp_na + (size_t)(n0 >> 3)) * 256;
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                  sa + TBM * TBK * 4),
+              "l"(src), "r"((uint32_t)W_BYTES), "r"(bar)
+              : "memory");
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      uint32_t it = 0, tc = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++tc) {
+        const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
+        if (ok) ok = mbar_wait(smem_u32(tempty_bar + buf), tph ^ 1u);  // epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          if (ok) ok = mbar_wait(smem_u32(full_bar + s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sa + TBM * TBK * 4);
+          if (ok) {
+#pragma unroll
+            for (int kk = 0; kk < TBK / 8; ++kk) {
+              const uint32_t accum = (kb > 0 || kk > 0) ? 1u : 0u;
+              asm volatile(
+                  "{\n"
+                  ".reg .pred p;\n"
+                  "setp.ne.b32 p, %4, 0;\n"
+                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+                  "}\n" ::"r"(tacc),
+                  "l"(da + (uint64_t)(kk * 2)), "l"(db + (uint64_t)(kk * 2)), "r"(idesc), "r"(accum)
+                  : "memory");
+            }
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(empty_bar + s))
+                       : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(tfull_bar + buf))
+                     : "memory");
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;              // 0..7
+    const int etid = tid - 64;            // 0..255
+    const int lq = warp & 3;              // TMEM lane window of this warp (hardware: warp id % 4)
+    const int cpar = ew >> 2;             // which half of the 32-column chunks
+    float *tbuf = tbuf_all + ew * (32 * 33);
+    const bool has_xfr = a.res && (a.xfr.stats != nullptr || a.xfr.addvec != nullptr || a.xfr.relu != 0);
+    const bool xr_relu = a.xfr.relu != 0;
+    const int st_seg = a.st_cg < 32 ? a.st_cg : 32;
+    uint32_t tc = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++tc) {
+      const int m0 = (t / tiles_n) * TBM, n0 = (t % tiles_n) * BN;
+      const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
+      float4 *tabR = tabR_all + buf * BN;
+      float *stacc = stacc_all + buf * (XF_MAXG * 2);
+      // per-tile set-up: statistics accumulators, resid transform for this (sample, column range)
+      if (a.st_stats && etid < XF_MAXG * 2) stacc[etid] = 0.f;
+      if (has_xfr && etid < BN) {
+        const int n = n0 + etid;
+        float scale = 1.f, shift = 0.f, add = 0.f;
+        if (n < a.N) {
+          const int sR = m0 / a.xfr.R;
+          if (a.xfr.stats) {
+            const int ch = a.xfr.choff + n;
+            if (ch < a.xfr.nnorm) {
+              const int G = a.xfr.nnorm / a.xfr.cg;
+              const double *st = a.xfr.stats + ((size_t)sR * G + ch / a.xfr.cg) * 2;
+              const double m = st[0] * (double)a.xfr.inv_count;
+              double var = st[1] * (double)a.xfr.inv_count - m * m;
+              var = var < 0.0 ? 0.0 : var;
+              scale = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS)) * __ldg(a.xfr.gamma + ch);
+              shift = __ldg(a.xfr.beta + ch) - (float)m * scale;
+            }
+          }
+          if (a.xfr.addvec) {
+            const long long arow = a.xfr.addmode == 0 ? sR : (a.xfr.addmode == 1 ? step : 0);
+            add = __ldg(a.xfr.addvec + arow * a.xfr.addld + n);
+          }
+        }
+        tabR[etid] = make_float4(scale, shift, add, 0.f);
+      }
+      epi_bar_sync();
+      if (ok) ok = mbar_wait(smem_u32(tfull_bar + buf), tph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int mw = m0 + lq * 32;
+      const bool st_pow2 = a.st_stats && (a.st_cg & (a.st_cg - 1)) == 0 && ((a.st_choff + n0) % st_seg) == 0 &&
+                           (a.st_nnorm % st_seg) == 0;
+      for (int c0 = 32 * cpar; c0 < BN; c0 += 64) {
+        if (n0 + c0 >= a.N) break;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
+        if (ok) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int n = n0 + c0 + lane;
+        const bool ncol = n < a.N;
+        const float bias = (ncol && a.bias) ? __ldg(a.bias + n) : 0.f;
+        const int stch = a.st_choff + n;
+        const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
+        const int stg = dost ? stch / a.st_cg : 0;
+        float4 c = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (has_xfr) c = tabR[c0 + lane];
+        float ssum = 0.f, ssq = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int mb = mw + 8 * q;
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = tbuf[(8 * q + i) * 33 + lane] + bias;
+          if (a.ev) {
+            const float e = ncol ? a.ev[(size_t)(mb / a.evdiv) * a.evld + n] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += e;
+          }
+          if (a.res) {
+            float x[8];
+            const float *rp = a.res + (size_t)mb * a.ldr + n;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = ncol ? rp[(size_t)i * a.ldr] : 0.f;
+            if (has_xfr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float y = fmaf(x[i], c.x, c.y);
+                if (xr_relu) y = fmaxf(y, 0.f);
+                x[i] = y + c.z;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += x[i];
+          }
+          if (a.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (a.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = act_apply(2, v[i]);
+          }
+          if (ncol) {
+            float *cp = a.C + (size_t)mb * a.ldc + n;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cp[(size_t)i * a.ldc] = v[i];
+          }
+          if (dost) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              ssum += v[i];
+              ssq = fmaf(v[i], v[i], ssq);
+            }
+          }
+        }
+        if (a.st_stats) {  // warp-uniform; the whole tile belongs to one sample
+          float rs = ssum, rq = ssq;
+          bool leader = dost;
+          if (st_pow2) {
+            for (int d = 1; d < st_seg; d <<= 1) {
+              rs += __shfl_xor_sync(0xffffffffu, rs, d);
+              rq += __shfl_xor_sync(0xffffffffu, rq, d);
+            }
+            leader = dost && (lane & (st_seg - 1)) == 0;
+          }
+          if (leader) {
+            atomicAdd(stacc + stg * 2, rs);
+            atomicAdd(stacc + stg * 2 + 1, rq);
+          }
+        }
+        __syncwarp();
+      }
+      // this warp has finished reading the accumulator: hand the TMEM buffer back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + buf));
+      if (a.st_stats) {
+        epi_bar_sync();
+        const int G = a.st_nnorm / a.st_cg;
+        if (etid < G * 2) {
+          const float v = stacc[etid];
+          if (v != 0.f)
+            atomicAdd(a.st_stats + ((size_t)(m0 / a.st_R) * G) * 2 + etid, (double)v * (double)a.st_weight);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // A row tile must map onto whole samples (or lie inside one): then it touches at most XF_MAXS of them.
 static bool spans_ok_tc(int R) { return R % TBM == 0 || (TBM % R == 0 && TBM / R <= XF_MAXS); }
 static int tc_rows_per_tile(int R) { return R % TBM == 0 ? 1 : TBM / R; }
@@ -697,7 +999,31 @@ static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t
   memset(&tm, 0, sizeof(tm));
   if (a.smk > 0) return launch_tc_impl<BN, STAGES, true, false>(a, Wp, wp_na, st, tm);
   // A needs no transform and its rows are 16-byte aligned with a 16-byte pitch: let TMA fetch it
-  if (use_tma && !has_xf(a.xfa) && make_a_map(a, &tm)) return launch_tc_impl<BN, STAGES, false, true>(a, Wp, wp_na, st, tm);
+  if (use_tma && !has_xf(a.xfa) && make_a_map(a, &tm)) {
+    static int persist = -1;
+    if (persist < 0) {
+      const char *e = getenv("SLIDE_TC_PERSIST");
+      persist = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const bool one_sample = (!a.res || !has_xf(a.xfr) || a.xfr.R % TBM == 0) && (!a.st_stats || a.st_R % TBM == 0);
+    const int tiles = (a.M / TBM) * ceil_div(a.N, BN);
+    if (persist && one_sample && a.M % TBM == 0 && tiles >= 2 * 148 && BN >= 128) {
+      constexpr int PSTAGES = BN == 256 ? 3 : 5;
+      const int total = tcp_smem_bytes(BN, PSTAGES) + 1024;
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<BN, PSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             TC_MAX_DYN_SMEM);
+        if (e != cudaSuccess) return cuda_rc(e);
+        configured = true;
+      }
+      if (total <= TC_MAX_DYN_SMEM) {
+        gemm_tcp_kernel<BN, PSTAGES><<<148, TCP_THREADS, total, st>>>(a, Wp, wp_na, tm);
+        return after_launch();
+      }
+    }
+    return launch_tc_impl<BN, STAGES, false, true>(a, Wp, wp_na, st, tm);
+  }
   return launch_tc_impl<BN, STAGES, false, false>(a, Wp, wp_na, st, tm);
 }
 

@@ -1,7 +1,9 @@
 mkdir -p gpurun_out
-for v in default bn128 s4 bn128s6; do
-    if [ $v = default ]; then unset SLIDE_B200_LIB; else export SLIDE_B200_LIB=$PWD/slide_b200/libslide_b200_$v.so; fi
-    python tools/profile_records.py lat 256 auto > gpurun_out/ab_lat_${v}.txt 2>&1
-    echo "$v: $(head -1 gpurun_out/ab_lat_${v}.txt)"
-    grep -E "SA1.att.v |SA1.att.w2|SA1.mlp.res |SA1.mlp.conv2 |SA1.att.w1k " gpurun_out/ab_lat_${v}.txt | cut -c1-100
+timeout 900 python -m pytest tests/test_gpu_program.py -m gpu -q --timeout 600 -p no:cacheprovider -k "golden or (teacher_forced and auto)" > gpurun_out/t_prog.log 2>&1; echo "prog rc=$?"; tail -n 3 gpurun_out/t_prog.log | cut -c1-300
+for v in 1 0; do
+    SLIDE_TC_PERSIST=$v timeout 300 python tools/profile_records.py lat 256 auto > gpurun_out/ab_lat_p$v.txt 2>&1
+    SLIDE_TC_PERSIST=$v timeout 300 python tools/profile_records.py pos 256 auto > gpurun_out/ab_pos_p$v.txt 2>&1
+    echo "persist=$v: $(head -1 gpurun_out/ab_lat_p$v.txt)"
+    echo "persist=$v: $(head -1 gpurun_out/ab_pos_p$v.txt)"
+    grep -E "att.v |att.q |mlp.conv0 |\.res " gpurun_out/ab_lat_p$v.txt | cut -c1-100
 done
