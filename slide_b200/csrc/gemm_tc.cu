@@ -40,6 +40,31 @@ constexpr int TC_MAX_DYN_SMEM = 227 * 1024;
 
 __device__ int g_tc_error = 0;  // set when a barrier wait times out (never in a correct run)
 
+// Phase stamps of every CTA (tuning builds only: -DTC_TIMELINE, see tools/tc_timeline.py).  Slot layout per CTA:
+// 0 start | 1 prologue done | 2 first A loads issued | 3 first stage published | 4 last stage published |
+// 5 first stage seen by the MMA thread | 6 last commit issued | 7 accumulator ready | 8 resid table done |
+// 9 chunks drained | 10 after the closing barrier | 11 end | 12 globaltimer at start | 13 SM id
+#ifdef TC_TIMELINE
+constexpr int TL_SLOTS = 16, TL_CTAS = 8192;
+__device__ unsigned long long g_tc_tl[TL_SLOTS * TL_CTAS];
+__device__ __forceinline__ void tl_stamp(int slot) {
+  const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+  if (cta < TL_CTAS) g_tc_tl[cta * TL_SLOTS + slot] = (unsigned long long)clock64();
+}
+#define TL(slot, cond) do { if (cond) tl_stamp(slot); } while (0)
+// persistent kernel: per-role cycle accumulators (slot layout in tools/tc_timeline.py)
+#define TLP_DECL long long tlp_t0 = 0, tlp_acc[4] = {0, 0, 0, 0}
+#define TLP_BEGIN() (tlp_t0 = clock64())
+#define TLP_END(i) do { const long long now_ = clock64(); tlp_acc[i] += now_ - tlp_t0; tlp_t0 = now_; } while (0)
+#define TLP_FLUSH(slot, i, cond) do { if ((cond) && blockIdx.x < TL_CTAS) g_tc_tl[blockIdx.x * TL_SLOTS + (slot)] = (unsigned long long)tlp_acc[i]; } while (0)
+#else
+#define TL(slot, cond) do { } while (0)
+#define TLP_DECL
+#define TLP_BEGIN()
+#define TLP_END(i)
+#define TLP_FLUSH(slot, i, cond)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -156,6 +181,43 @@ __device__ __forceinline__ void fill_xf_table(const XFd &x, float4 *tab, float2 
   }
 }
 
+// Fused AttentionModule tail for one 32-row x 32-column chunk with a compile-time neighbour count.  x = the 32
+// value rows of the chunk, fetched by the caller with 32 independent loads issued BEFORE the accumulator chunk is
+// read from tensor memory (the dependent per-neighbour loads of the generic loop left ~0.5 KB per warp in flight
+// and made the epilogue latency-bound).
+__device__ __forceinline__ void load_rows32(float (&x)[32], const float *__restrict__ p, int ld, bool on) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = on ? __ldcs(p + (size_t)i * ld) : 0.f;
+}
+
+template <int KK>
+__device__ __forceinline__ void smk_chunk(const float *tbuf, int lane, const float (&x)[32], bool has_xfr, bool xr_relu,
+                                          const float4 *tabR, const int (&xr_off)[4], int ccol,
+                                          float *__restrict__ outp, int ldc) {
+#pragma unroll
+  for (int g0 = 0; g0 < 32; g0 += KK) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < KK; ++k) mx = fmaxf(mx, tbuf[(g0 + k) * 33 + lane]);
+    float4 c = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (has_xfr) c = tabR[xr_off[g0 >> 3] + ccol];
+    float den = 0.f, o = 0.f;
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      const float w = __expf(tbuf[(g0 + k) * 33 + lane] - mx);
+      float xv = x[g0 + k];
+      if (has_xfr) {
+        xv = fmaf(xv, c.x, c.y);
+        if (xr_relu) xv = fmaxf(xv, 0.f);
+        xv += c.z;
+      }
+      den += w;
+      o = fmaf(xv, w, o);
+    }
+    outp[(size_t)(g0 / KK) * ldc] = o / den;
+  }
+}
+
 #ifndef TC_MAXNREG
 #define TC_MAXNREG 96  // measured on B200: 96 keeps two 288-thread CTAs per SM (112 and 128 run ~25% slower)
 #endif
@@ -184,6 +246,20 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;  // N tiles of one row tile are adjacent: A stays in L2
+  TL(0, tid == 0);
+#ifdef TC_TIMELINE
+  if (tid == 0) {
+    unsigned long long gt;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (cta < TL_CTAS) {
+      g_tc_tl[cta * TL_SLOTS + 12] = gt;
+      g_tc_tl[cta * TL_SLOTS + 13] = smid;
+    }
+  }
+#endif
   const int mlast = min(m0 + TBM, a.M) - 1;
   const int step = a.step ? *a.step : 0;
   const int num_kb = (a.K + TBK - 1) / TBK;
@@ -212,6 +288,7 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  TL(1, tid == 0);
 
   bool ok = true;
   if (TMA_A && warp < TC_PWARPS) {
@@ -328,16 +405,19 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
     float4 bufA[4], bufB[4];
     load(bufA, 0);
     load(bufB, 1);
+    TL(2, tid == 0);
     for (int kb = 0; kb < num_kb; kb += 2) {
       process(bufA, kb);
       load(bufA, kb + 2);
       publish(kb);
+      TL(3, tid == 0 && kb == 0);
       if (kb + 1 < num_kb) {
         process(bufB, kb + 1);
         load(bufB, kb + 3);
         publish(kb + 1);
       }
     }
+    TL(4, tid == 0);
   } else {
     // ------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
@@ -347,6 +427,7 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         if (ok) ok = mbar_wait(smem_u32(full_bar + s), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        TL(5, kb == 0);
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const uint64_t da = make_smem_desc(sa);
         const uint64_t db = make_smem_desc(sa + TBM * TBK * 4);
@@ -373,15 +454,33 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                        smem_u32(accum_bar))
                    : "memory");
+      TL(6, true);
     }
     __syncwarp();
   }
 
   // ------------------------------------------------------------------------------------------- epilogue
+  // bias and the ev rows of every chunk this warp will drain are requested BEFORE the wait for the accumulator:
+  // inside the chunk loop each of them would cost a serialised L2 round trip (measured: ~1000 cycles apiece)
+  // (the chunk loop stays rolled -- unrolling it made the kernel instruction-fetch bound -- so the values for chunk
+  // i+1 are requested at the top of chunk i and the first chunk's before the wait)
+  float bias_nx = 0.f, ev_nx[4] = {0.f, 0.f, 0.f, 0.f};
+  auto prefetch_vec = [&](int c0_) {
+    const int mw_ = m0 + (warp & 3) * 32;
+    const int n_ = n0 + c0_ + lane;
+    const bool on_ = warp < TC_PWARPS && c0_ < BN && n_ < a.N;
+    bias_nx = (on_ && a.bias) ? __ldg(a.bias + n_) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      ev_nx[q] = (!SMK && on_ && a.ev && mw_ + 32 <= a.M) ? __ldg(a.ev + (size_t)((mw_ + 8 * q) / a.evdiv) * a.evld + n_)
+                                                         : 0.f;
+  };
+  prefetch_vec(32 * (warp >> 2));
   if (warp < TC_PWARPS) {
     if (ok) ok = mbar_wait(smem_u32(accum_bar), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
+  TL(7, tid == 0);
   // every stage buffer is dead now (all MMAs completed before accum_bar fired): reuse the area
   float *tbuf = reinterpret_cast<float *>(smem) + (warp < TC_PWARPS ? warp : 0) * (32 * 33);
   float4 *tabR = reinterpret_cast<float4 *>(smem + TC_PWARPS * 32 * 33 * 4);
@@ -393,6 +492,7 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
     fill_xf_table(a.xfr, tabR, mrbuf, sR0, mlast / a.xfr.R - sR0 + 1, ncols, n0, BN, step, tid, TC_THREADS);
     __syncthreads();  // has_xfr is uniform over the CTA
   }
+  TL(8, tid == 0);
 
   if (warp < TC_PWARPS) {
     // warp w drains TMEM lanes 32 (w & 3) .. +31 (the hardware's lane window of warp w % 4); the two warps that share
@@ -421,6 +521,9 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
     }
     for (int c0 = 32 * cpar; c0 < BN; c0 += 64) {
       if (n0 + c0 >= a.N || (dbg & 4)) break;
+      const float bias = bias_nx;
+      const float evc[4] = {ev_nx[0], ev_nx[1], ev_nx[2], ev_nx[3]};
+      prefetch_vec(c0 + 64);
       uint32_t r[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
       if (ok) {
@@ -446,7 +549,6 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
       __syncwarp();
       const int n = n0 + c0 + lane;
       const bool ncol = n < a.N;
-      const float bias = (ncol && a.bias) ? __ldg(a.bias + n) : 0.f;
       const int stch = a.st_choff + n;
       const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
       const int stg = dost ? stch / a.st_cg : 0;
@@ -454,7 +556,16 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
         // fused AttentionModule tail: soft-max down each group of smk rows (the neighbours of one point), applied
         // to the transformed value rows; one output row per group.  (bias is constant down a column: it cancels.)
         const int K = a.smk;
-        if (ncol) {
+        const bool smk_fast = rr_end == 32 && (K == 4 || K == 8 || K == 16 || K == 32);  // warp-uniform
+        if (ncol && smk_fast) {
+          float x[32];
+          load_rows32(x, a.res + (size_t)mw * a.ldr + n, a.ldr, true);
+          float *op = a.C + (size_t)(mw / K) * a.ldc + n;
+          if (K == 16) smk_chunk<16>(tbuf, lane, x, has_xfr, xr_relu, tabR, xr_off, c0 + lane, op, a.ldc);
+          else if (K == 8) smk_chunk<8>(tbuf, lane, x, has_xfr, xr_relu, tabR, xr_off, c0 + lane, op, a.ldc);
+          else if (K == 32) smk_chunk<32>(tbuf, lane, x, has_xfr, xr_relu, tabR, xr_off, c0 + lane, op, a.ldc);
+          else smk_chunk<4>(tbuf, lane, x, has_xfr, xr_relu, tabR, xr_off, c0 + lane, op, a.ldc);
+        } else if (ncol) {
           for (int g0 = 0; g0 < 32; g0 += K) {
             float mx = -INFINITY;
             for (int k = 0; k < K; ++k) mx = fmaxf(mx, tbuf[(g0 + k) * 33 + lane]);
@@ -480,6 +591,13 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
       } else if (!SMK && fast) {
         float ssum = 0.f, ssq = 0.f;
         {
+          // all 32 residual rows of the chunk are requested up front (32 independent 128-byte row segments per warp)
+          float xres[32];
+          if (a.res) {
+            const float *rp0 = a.res + (size_t)mw * a.ldr + n;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xres[i] = ncol ? __ldcs(rp0 + (size_t)i * a.ldr) : 0.f;
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int rb = 8 * q;
@@ -488,15 +606,14 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = tbuf[(rb + i) * 33 + lane] + bias;
             if (a.ev) {
-              const float e = ncol ? a.ev[(size_t)ev_off[q] + n] : 0.f;
+              const float e = evc[q];  // fast path: the warp's 32 rows exist, 8-row blocks lie inside one ev row
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += e;
             }
             if (a.res) {
               float x[8];
-              const float *rp = a.res + (size_t)mb * a.ldr + n;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = ncol ? rp[(size_t)i * a.ldr] : 0.f;
+              for (int i = 0; i < 8; ++i) x[i] = xres[rb + i];
               if (has_xfr) {
                 const float4 c = tabR[xr_off[q] + c0 + lane];
 #pragma unroll
@@ -582,8 +699,10 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
       __syncwarp();
     }
   }
+  TL(9, tid == 0);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  TL(10, tid == 0);
   if (a.st_stats) {
     const int G = a.st_nnorm / a.st_cg;
     const int sS0 = m0 / a.st_R;
@@ -599,28 +718,36 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
                  "r"((uint32_t)(BN < 32 ? 32 : BN))
                  : "memory");
   }
+  TL(11, tid == 0);
 }
 
 // =====================================================================================================
-// Persistent variant (TMA for both operands): one CTA per SM loops over output tiles; a 3-stage operand ring and a
-// DOUBLE-BUFFERED accumulator in tensor memory let the MMAs of tile i+1 run while eight epilogue warps drain tile i.
-//   warp 0   : TMA producer (A tensor copy + W bulk copy per K block)
-//   warp 1   : TMEM allocation (2 x BN columns) + tcgen05.mma issue
-//   warps 2-9: epilogue (TMEM -> registers -> smem transpose -> coalesced stores, statistics)
-// Used when A needs no transform, every row tile lies inside one sample (R % 128 == 0) and M % 128 == 0.
+// Persistent, warp-specialised variant: one CTA per SM loops over output tiles; an operand ring and a
+// DOUBLE-BUFFERED accumulator in tensor memory let the loads and MMAs of tile i+1 run while eight epilogue warps
+// drain tile i, so the L2->SM operand stream, the tensor pipe and the HBM write burst of the epilogue overlap
+// (the one-tile-per-CTA kernel above runs them one after another, and its co-resident CTAs move in lock step).
+//   warp 0     : bulk-copy producer (W per K block; with !XFA also the A tensor copy)
+//   warp 1     : TMEM allocation (2 x BN columns) + tcgen05.mma issue
+//   warps 2-9  : epilogue (TMEM -> registers -> smem transpose -> coalesced stores, statistics; SMK: fused soft-max)
+//   warps 10-17: (XFA only) A producers: global -> registers (GroupNorm / ReLU / add, TF32 rounding) -> swizzled smem
+// Used when every row tile lies inside one sample (R % 128 == 0) and M % 128 == 0.
 // =====================================================================================================
 constexpr int TCP_EPI_WARPS = 8;
 constexpr int TCP_THREADS = 32 * (2 + TCP_EPI_WARPS);
+constexpr int TCP_XFA_THREADS = TCP_THREADS + TC_PRODUCERS;
 
 __host__ __device__ constexpr int tcp_smem_bytes(int BN, int STAGES) {
-  return STAGES * tc_stage_bytes(BN) + TCP_EPI_WARPS * 32 * 33 * 4 + 2 * BN * 16 + 512 /*barriers*/ + 2 * XF_MAXG * 2 * 4;
+  // operand ring | per-warp transpose tiles | resid table x2 | barriers | statistics x2
+  return STAGES * tc_stage_bytes(BN) + TCP_EPI_WARPS * 32 * 33 * 4 + 2 * BN * 16 + 512 + 2 * XF_MAXG * 2 * 4;
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TCP_EPI_WARPS * 32) : "memory"); }
+__device__ __forceinline__ void prod_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCERS) : "memory"); }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na,
-                                                                  const __grid_constant__ CUtensorMap tmA) {
+template <int BN, int STAGES, bool XFA, bool SMK>
+__global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
+    gemm_tcp_kernel(GemmArgs a, const float *__restrict__ Wp, int wp_na, int table_stride,
+                    const __grid_constant__ CUtensorMap tmA) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int STAGE_BYTES = tc_stage_bytes(BN);
@@ -632,10 +759,13 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
   uint8_t *ctrl = reinterpret_cast<uint8_t *>(tabR_all) + 2 * BN * 16;
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(ctrl);
   uint64_t *empty_bar = full_bar + STAGES;
-  uint64_t *tfull_bar = empty_bar + STAGES;
+  uint64_t *raw_bar = empty_bar + STAGES;  // XFA: the untransformed A tile (+ W) of a stage has landed
+  uint64_t *tfull_bar = raw_bar + STAGES;
   uint64_t *tempty_bar = tfull_bar + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
   float *stacc_all = reinterpret_cast<float *>(ctrl + 512);
+  float2 *mrA = reinterpret_cast<float2 *>(ctrl + 512 + 2 * XF_MAXG * 2 * 4);  // XFA: (mean, rstd) per group
+  float4 *tabA = reinterpret_cast<float4 *>(ctrl + 512 + 2 * XF_MAXG * 2 * 4 + XF_MAXG * 8);  // XFA: per K column
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int step = a.step ? *a.step : 0;
@@ -645,7 +775,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(full_bar + s), 1);
+      // XFA: the 256 transform threads arrive; otherwise only the copy engine's expect_tx arrive
+      mbar_init(smem_u32(full_bar + s), XFA ? TC_PRODUCERS : 1);
+      mbar_init(smem_u32(raw_bar + s), 1);
       mbar_init(smem_u32(empty_bar + s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -664,6 +796,19 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  TL(0, tid == 0);
+#ifdef TC_TIMELINE
+  if (tid == 0 && blockIdx.x < TL_CTAS) {
+    unsigned long long gt;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_tc_tl[blockIdx.x * TL_SLOTS + 12] = gt;
+    g_tc_tl[blockIdx.x * TL_SLOTS + 13] = smid;
+    g_tc_tl[blockIdx.x * TL_SLOTS + 10] = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  }
+#endif
+  TLP_DECL;
 
   bool ok = true;
   if (warp == 0) {
@@ -676,9 +821,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
+          TLP_BEGIN();
           if (ok) ok = mbar_wait(smem_u32(empty_bar + s), ph ^ 1u);
+          TLP_END(0);
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint32_t bar = smem_u32(full_bar + s);
+          // XFA: the tensor map is plain fp32 and the tile lands on raw_bar: the transform warps rewrite it in place
+          const uint32_t bar = smem_u32((XFA ? raw_bar : full_bar) + s);
           mbar_arrive_expect_tx(bar, A_BYTES + (uint32_t)W_BYTES);
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(sa),
@@ -692,6 +840,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
               : "memory");
         }
       }
+      TLP_FLUSH(9, 0, true);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -701,13 +850,17 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
       uint32_t it = 0, tc = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++tc) {
         const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
+        TLP_BEGIN();
         if (ok) ok = mbar_wait(smem_u32(tempty_bar + buf), tph ^ 1u);  // epilogue has drained this accumulator
+        TLP_END(1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + buf * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
+          TLP_BEGIN();
           if (ok) ok = mbar_wait(smem_u32(full_bar + s), ph);
+          TLP_END(0);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
           const uint64_t da = make_smem_desc(sa);
@@ -734,8 +887,91 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
                          smem_u32(tfull_bar + buf))
                      : "memory");
       }
+      TLP_FLUSH(1, 0, true);
+      TLP_FLUSH(2, 1, true);
     }
     __syncwarp();
+  } else if (XFA && warp >= 2 + TCP_EPI_WARPS) {
+    // ------------------------------------------------------------------------------------------ A transform warps
+    // The copy engine has written the raw fp32 tile in the SWIZZLE_128B layout; each thread rewrites 4 of its
+    // 16-byte chunks in place: y = relu?(x * scale + shift) + add, rounded to TF32.  No global-memory latency sits
+    // on this path: the tensor copies run up to STAGES K blocks ahead.
+    const int ptid = tid - TCP_THREADS;  // 0..255
+    const int pchunk = ptid & 7;         // physical 16-byte chunk within the 128-byte row
+    const int rbase = ptid >> 3;         // 0..31; this thread owns rows rbase + 32 i, i = 0..3
+    const int lchunk = pchunk ^ (rbase & 7);  // logical K chunk stored there ((r & 7) is the same for the 4 rows)
+    const bool relu = a.xfa.relu != 0;
+    const int G = a.xfa.stats ? a.xfa.nnorm / a.xfa.cg : 0;
+    uint32_t it = 0;
+    int cur_m0 = -1;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int m0 = (t / tiles_n) * TBM;
+      if (m0 != cur_m0) {
+        // (scale, shift, add) per K column for this tile's sample; fp64 only once per group.  Columns >= K get
+        // (0, 0, 0): the copy engine zero-fills them and they must stay zero.
+        cur_m0 = m0;
+        const int sA = m0 / a.xfa.R;
+        prod_bar_sync();  // everyone has finished reading the previous table
+        if (ptid < G) {
+          const double *st = a.xfa.stats + ((size_t)sA * G + ptid) * 2;
+          const double m = st[0] * (double)a.xfa.inv_count;
+          double var = st[1] * (double)a.xfa.inv_count - m * m;
+          var = var < 0.0 ? 0.0 : var;
+          mrA[ptid] = make_float2((float)m, (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS)));
+        }
+        prod_bar_sync();
+        for (int k = ptid; k < table_stride; k += TC_PRODUCERS) {
+          float scale = 0.f, shift = 0.f, add = 0.f;
+          if (k < a.K) {
+            scale = 1.f;
+            if (a.xfa.stats) {
+              const int ch = a.xfa.choff + k;
+              if (ch < a.xfa.nnorm) {
+                const float2 v = mrA[ch / a.xfa.cg];
+                scale = v.y * __ldg(a.xfa.gamma + ch);
+                shift = __ldg(a.xfa.beta + ch) - v.x * scale;
+              }
+            }
+            if (a.xfa.addvec) {
+              const long long arow_ = a.xfa.addmode == 0 ? sA : (a.xfa.addmode == 1 ? step : 0);
+              add = __ldg(a.xfa.addvec + arow_ * a.xfa.addld + k);
+            }
+          }
+          tabA[k] = make_float4(scale, shift, add, 0.f);
+        }
+        prod_bar_sync();
+      }
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        float4 tc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) tc[u] = tabA[kb * TBK + lchunk * 4 + u];
+        TLP_BEGIN();
+        if (ok) ok = mbar_wait(smem_u32(raw_bar + s), ph);
+        TLP_END(0);
+        uint8_t *sa = smem + (size_t)s * STAGE_BYTES + rbase * 128 + (pchunk << 4);
+        float4 x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4 *>(sa + i * (32 * 128));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float y = fmaf(v[u], tc[u].x, tc[u].y);
+            if (relu) y = fmaxf(y, 0.f);
+            v[u] = y + tc[u].z;
+          }
+          *reinterpret_cast<uint4 *>(sa + i * (32 * 128)) =
+              make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+        }
+        // make the generic-proxy writes visible to the tensor core (async proxy), then signal
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(smem_u32(full_bar + s));
+      }
+    }
+    TLP_FLUSH(8, 0, ptid == 0);
   } else {
     // ------------------------------------------------------------------------------------------ epilogue warps
     const int ew = warp - 2;              // 0..7
@@ -752,40 +988,63 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
       const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
       float4 *tabR = tabR_all + buf * BN;
       float *stacc = stacc_all + buf * (XF_MAXG * 2);
-      // per-tile set-up: statistics accumulators, resid transform for this (sample, column range)
+      // per-tile set-up (runs while the tile's MMAs are still in flight): statistics accumulators, and one
+      // (scale, shift, add, bias) entry per column: the resid transform of this (sample, column range) + the bias
       if (a.st_stats && etid < XF_MAXG * 2) stacc[etid] = 0.f;
-      if (has_xfr && etid < BN) {
+      if (etid < BN) {
         const int n = n0 + etid;
-        float scale = 1.f, shift = 0.f, add = 0.f;
+        float scale = 1.f, shift = 0.f, add = 0.f, bias = 0.f;
         if (n < a.N) {
-          const int sR = m0 / a.xfr.R;
-          if (a.xfr.stats) {
-            const int ch = a.xfr.choff + n;
-            if (ch < a.xfr.nnorm) {
-              const int G = a.xfr.nnorm / a.xfr.cg;
-              const double *st = a.xfr.stats + ((size_t)sR * G + ch / a.xfr.cg) * 2;
-              const double m = st[0] * (double)a.xfr.inv_count;
-              double var = st[1] * (double)a.xfr.inv_count - m * m;
-              var = var < 0.0 ? 0.0 : var;
-              scale = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS)) * __ldg(a.xfr.gamma + ch);
-              shift = __ldg(a.xfr.beta + ch) - (float)m * scale;
+          if (a.bias) bias = __ldg(a.bias + n);
+          if (has_xfr) {
+            const int sR = m0 / a.xfr.R;
+            if (a.xfr.stats) {
+              const int ch = a.xfr.choff + n;
+              if (ch < a.xfr.nnorm) {
+                const int G = a.xfr.nnorm / a.xfr.cg;
+                const double *st = a.xfr.stats + ((size_t)sR * G + ch / a.xfr.cg) * 2;
+                const double m = st[0] * (double)a.xfr.inv_count;
+                double var = st[1] * (double)a.xfr.inv_count - m * m;
+                var = var < 0.0 ? 0.0 : var;
+                scale = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS)) * __ldg(a.xfr.gamma + ch);
+                shift = __ldg(a.xfr.beta + ch) - (float)m * scale;
+              }
+            }
+            if (a.xfr.addvec) {
+              const long long arow = a.xfr.addmode == 0 ? sR : (a.xfr.addmode == 1 ? step : 0);
+              add = __ldg(a.xfr.addvec + arow * a.xfr.addld + n);
             }
           }
-          if (a.xfr.addvec) {
-            const long long arow = a.xfr.addmode == 0 ? sR : (a.xfr.addmode == 1 ? step : 0);
-            add = __ldg(a.xfr.addvec + arow * a.xfr.addld + n);
-          }
         }
-        tabR[etid] = make_float4(scale, shift, add, 0.f);
+        tabR[etid] = make_float4(scale, shift, add, bias);
       }
-      epi_bar_sync();
-      if (ok) ok = mbar_wait(smem_u32(tfull_bar + buf), tph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int mw = m0 + lq * 32;
+      // the ev rows (one per 8-row block) of the first chunk are requested now and used after the wait; inside
+      // the (rolled) chunk loop the rows of chunk i+1 are requested at the top of chunk i
+      float ev_nx[4];
+      auto prefetch_ev = [&](int c0_) {
+        const int n_ = n0 + c0_ + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          ev_nx[q] = (!SMK && a.ev && c0_ < BN && n_ < a.N) ? __ldg(a.ev + (size_t)((mw + 8 * q) / a.evdiv) * a.evld + n_) : 0.f;
+      };
+      prefetch_ev(32 * cpar);
+      epi_bar_sync();
+      TLP_BEGIN();
+      if (ok) ok = mbar_wait(smem_u32(tfull_bar + buf), tph);
+      TLP_END(0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool st_pow2 = a.st_stats && (a.st_cg & (a.st_cg - 1)) == 0 && ((a.st_choff + n0) % st_seg) == 0 &&
                            (a.st_nnorm % st_seg) == 0;
       for (int c0 = 32 * cpar; c0 < BN; c0 += 64) {
         if (n0 + c0 >= a.N) break;
+        const int n = n0 + c0 + lane;
+        const bool ncol = n < a.N;
+        const float evc[4] = {ev_nx[0], ev_nx[1], ev_nx[2], ev_nx[3]};
+        prefetch_ev(c0 + 64);
+        // the chunk's 32 value / residual rows: in flight while the accumulator chunk is read and transposed
+        float xres[32];
+        if (SMK || a.res) load_rows32(xres, a.res + (size_t)mw * a.ldr + n, a.ldr, ncol);
         uint32_t r[32];
         const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
         if (ok) {
@@ -803,19 +1062,32 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
+          for (int jj = 0; jj < 32; ++jj) r[jj] = 0u;
         }
+        TLP_END(1);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+        for (int jj = 0; jj < 32; ++jj) tbuf[lane * 33 + jj] = __uint_as_float(r[jj]);
         __syncwarp();
-        const int n = n0 + c0 + lane;
-        const bool ncol = n < a.N;
-        const float bias = (ncol && a.bias) ? __ldg(a.bias + n) : 0.f;
+        TLP_END(2);
+        const float4 c = tabR[c0 + lane];  // (resid scale, shift, add, bias)
+        const float bias = c.w;
         const int stch = a.st_choff + n;
         const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
         const int stg = dost ? stch / a.st_cg : 0;
-        float4 c = make_float4(1.f, 0.f, 0.f, 0.f);
-        if (has_xfr) c = tabR[c0 + lane];
+        if (SMK) {
+          // fused AttentionModule tail (see smk_chunk); the whole tile is one sample: a single resid-table row
+          if (ncol) {
+            const int zoff[4] = {0, 0, 0, 0};
+            float *op = a.C + (size_t)(mw / a.smk) * a.ldc + n;
+            if (a.smk == 16) smk_chunk<16>(tbuf, lane, xres, has_xfr, xr_relu, tabR, zoff, c0 + lane, op, a.ldc);
+            else if (a.smk == 8) smk_chunk<8>(tbuf, lane, xres, has_xfr, xr_relu, tabR, zoff, c0 + lane, op, a.ldc);
+            else if (a.smk == 32) smk_chunk<32>(tbuf, lane, xres, has_xfr, xr_relu, tabR, zoff, c0 + lane, op, a.ldc);
+            else smk_chunk<4>(tbuf, lane, xres, has_xfr, xr_relu, tabR, zoff, c0 + lane, op, a.ldc);
+          }
+          __syncwarp();
+          TLP_END(3);
+          continue;
+        }
         float ssum = 0.f, ssq = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -824,15 +1096,13 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = tbuf[(8 * q + i) * 33 + lane] + bias;
           if (a.ev) {
-            const float e = ncol ? a.ev[(size_t)(mb / a.evdiv) * a.evld + n] : 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += e;
+            for (int i = 0; i < 8; ++i) v[i] += evc[q];
           }
           if (a.res) {
             float x[8];
-            const float *rp = a.res + (size_t)mb * a.ldr + n;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = ncol ? rp[(size_t)i * a.ldr] : 0.f;
+            for (int i = 0; i < 8; ++i) x[i] = xres[8 * q + i];
             if (has_xfr) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -880,6 +1150,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
           }
         }
         __syncwarp();
+        TLP_END(3);
       }
       // this warp has finished reading the accumulator: hand the TMEM buffer back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -896,11 +1167,18 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(GemmArgs a, co
       }
     }
   }
+  if (warp == 2) {
+    TLP_FLUSH(3, 0, lane == 0);
+    TLP_FLUSH(4, 1, lane == 0);
+    TLP_FLUSH(5, 2, lane == 0);
+    TLP_FLUSH(6, 3, lane == 0);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+  TL(11, tid == 0);
 }
 
 // A row tile must map onto whole samples (or lie inside one): then it touches at most XF_MAXS of them.
@@ -952,14 +1230,16 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // A as a 2-D TFLOAT32 tensor [M rows, K columns] with row pitch lda: box = 128 rows x 32 columns, SWIZZLE_128B.
-static bool make_a_map(const GemmArgs &a, CUtensorMap *m) {
+static bool make_a_map(const GemmArgs &a, CUtensorMap *m, bool raw = false) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
   const cuuint64_t strides[1] = {(cuuint64_t)a.lda * 4};
   const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)TBM};
   const cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float *>(a.A), dims, strides, box, estr,
+  // raw: plain fp32 (the transform warps round to TF32 themselves); otherwise the copy engine rounds
+  return fn(m, raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float *>(a.A), dims,
+            strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -988,39 +1268,71 @@ static int launch_tc_impl(const GemmArgs &a, const float *Wp, int wp_na, cudaStr
   return after_launch();
 }
 
+constexpr int TCP_NOT_APPLICABLE = 1;  // internal: take the one-tile-per-CTA kernel instead
+
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+template <int BN, bool XFA, bool SMK>
+static int launch_tcp(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st, const CUtensorMap &tm) {
+  constexpr int PSTAGES = BN == 256 ? 3 : 5;
+  const int stride = XFA ? tc_table_stride(a) : 0;
+  const int total = tcp_smem_bytes(BN, PSTAGES) + (XFA ? XF_MAXG * 8 + stride * 16 : 0) + 1024 /* alignment slack */;
+  if (total > TC_MAX_DYN_SMEM) return TCP_NOT_APPLICABLE;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<BN, PSTAGES, XFA, SMK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM);
+    if (e != cudaSuccess) return cuda_rc(e);
+    configured = true;
+  }
+  const int tiles = (a.M / TBM) * ceil_div(a.N, BN);
+  const int max_grid = env_int("SLIDE_TC_PERSIST_GRID", sm_count());  // tests shrink it: many tiles per CTA
+  const int grid = tiles < max_grid ? tiles : max_grid;
+  gemm_tcp_kernel<BN, PSTAGES, XFA, SMK><<<grid, XFA ? TCP_XFA_THREADS : TCP_THREADS, total, st>>>(a, Wp, wp_na, stride, tm);
+  return after_launch();
+}
+
 template <int BN, int STAGES>
 static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
-  static int use_tma = -1;
-  if (use_tma < 0) {
-    const char *e = getenv("SLIDE_TC_TMA");
-    use_tma = (e && atoi(e) == 0) ? 0 : 1;
-  }
+  static const int use_tma = env_int("SLIDE_TC_TMA", 1);
+  // persistent kernel: 0 = never, 1 = TMA-fed operands only, 2 = also with transform producers / fused soft-max
+  const int persist = env_int("SLIDE_TC_PERSIST", 2);  // read per launch: tests flip these
+  const int persist_min_tiles = env_int("SLIDE_TC_PERSIST_MIN_TILES", 2 * 148);
+  const int persist_min_k = env_int("SLIDE_TC_PERSIST_MIN_K", 256);
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
+  // every row tile inside one sample, whole row tiles, 8-row blocks inside one ev row
+  const bool one_sample = (!a.res || !has_xf(a.xfr) || a.xfr.R % TBM == 0) && (!a.st_stats || a.st_R % TBM == 0) &&
+                          a.M % TBM == 0 && (!a.ev || a.evdiv % 8 == 0);
+  const int tiles = (a.M / TBM) * ceil_div(a.N, BN);
+  const bool xfa = has_xf(a.xfa);
+  if (persist >= 2 && one_sample && tiles >= persist_min_tiles && (xfa || a.smk > 0) &&
+      (!xfa || a.xfa.R % TBM == 0) && (a.smk == 0 || (xfa && a.res)) && use_tma && make_a_map(a, &tm, true)) {
+    const int rc = a.smk > 0 ? launch_tcp<BN, true, true>(a, Wp, wp_na, st, tm) : launch_tcp<BN, true, false>(a, Wp, wp_na, st, tm);
+    if (rc != TCP_NOT_APPLICABLE) return rc;
+  }
   if (a.smk > 0) return launch_tc_impl<BN, STAGES, true, false>(a, Wp, wp_na, st, tm);
   // A needs no transform and its rows are 16-byte aligned with a 16-byte pitch: let TMA fetch it
-  if (use_tma && !has_xf(a.xfa) && make_a_map(a, &tm)) {
-    static int persist = -1;
-    if (persist < 0) {
-      const char *e = getenv("SLIDE_TC_PERSIST");
-      persist = (e && atoi(e) == 0) ? 0 : 1;
-    }
-    const bool one_sample = (!a.res || !has_xf(a.xfr) || a.xfr.R % TBM == 0) && (!a.st_stats || a.st_R % TBM == 0);
-    const int tiles = (a.M / TBM) * ceil_div(a.N, BN);
-    if (persist && one_sample && a.M % TBM == 0 && tiles >= 2 * 148 && BN >= 128) {
-      constexpr int PSTAGES = BN == 256 ? 3 : 5;
-      const int total = tcp_smem_bytes(BN, PSTAGES) + 1024;
-      static bool configured = false;
-      if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<BN, PSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             TC_MAX_DYN_SMEM);
-        if (e != cudaSuccess) return cuda_rc(e);
-        configured = true;
-      }
-      if (total <= TC_MAX_DYN_SMEM) {
-        gemm_tcp_kernel<BN, PSTAGES><<<148, TCP_THREADS, total, st>>>(a, Wp, wp_na, tm);
-        return after_launch();
-      }
+  if (use_tma && !xfa && make_a_map(a, &tm)) {
+    // short K loops are epilogue-bound: two resident CTAs drain faster than one persistent CTA (measured on B200:
+    // K=60 N=256 60 -> 85 us persistent, K=512 N=512 109 -> 90 us)
+    if (persist >= 1 && one_sample && tiles >= persist_min_tiles && BN >= 128 && a.K >= persist_min_k) {
+      const int rc = launch_tcp<BN, false, false>(a, Wp, wp_na, st, tm);
+      if (rc != TCP_NOT_APPLICABLE) return rc;
     }
     return launch_tc_impl<BN, STAGES, false, true>(a, Wp, wp_na, st, tm);
   }
@@ -1060,6 +1372,19 @@ int launch_gemm_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t s
     default: return launch_tc<32, 4>(a, Wp, wp_na, st);
   }
 }
+
+#ifdef TC_TIMELINE
+extern "C" int slide_debug_tc_timeline(unsigned long long *out, int n_ctas, int clear) {
+  if (n_ctas > TL_CTAS) n_ctas = TL_CTAS;
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_tc_tl, (size_t)n_ctas * TL_SLOTS * 8);
+  if (e == cudaSuccess && clear) {
+    void *p = nullptr;
+    e = cudaGetSymbolAddress(&p, g_tc_tl);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, sizeof(unsigned long long) * TL_SLOTS * TL_CTAS);
+  }
+  return e == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int tc_error_flag() {
   int v = 0;

@@ -306,6 +306,10 @@ struct PairArgs {
   int pb;  // points per CTA
 };
 
+// RB = rows in flight per thread.  The neighbour indices (and squared distances) of a point are fetched ONCE as a
+// lane-parallel row and broadcast with shuffles, so a batch of RB rows costs one memory latency (the U gathers,
+// coordinate and residual loads of the whole batch are independent) instead of index -> gather chains per row.
+template <int RB, bool HAS_RES>
 __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
   // thread = 4 consecutive columns (128-bit U gathers / residual loads / stores); the per-row index, coordinate and
   // distance loads are amortised over the 4 outputs
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
       rsc[u] = 1.f;
       rsh[u] = 0.f;
       radd[u] = 0.f;
-      if (a.res) {
+      if (HAS_RES) {
         if (a.xfr.stats) {
           const int ch = a.xfr.choff + nn;
           if (ch < a.xfr.nnorm) {
@@ -363,53 +367,77 @@ __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
       for (int u = 0; u < 4; ++u) vterm[u] = fmaf(c2, wc[u][2], fmaf(c1, wc[u][1], fmaf(c0, wc[u][0], bias[u])));
       const size_t prow = ((size_t)s * a.np + i) * a.K;
       float inv_sum = 0.f;
-      if (a.d2)
-        for (int k = 0; k < a.K; ++k) inv_sum = __fadd_rn(inv_sum, __fdiv_rn(1.0f, __fadd_rn(__ldg(a.d2 + prow + k), 1e-8f)));
-#pragma unroll 2
-      for (int k = 0; k < a.K; ++k) {
-        const size_t row = prow + k;
-        const int j = __ldg(a.idx + row);
-        const float *x = a.xyz + ((size_t)s * a.nsrc + j) * a.ldx;
-        const float x0 = __ldg(x), x1 = __ldg(x + 1), x2 = __ldg(x + 2);
-        float4 uu = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (any) uu = *reinterpret_cast<const float4 *>(a.U + ((size_t)s * a.nsrc + j) * a.ldu + n);
-        float v[4] = {uu.x, uu.y, uu.z, uu.w};
-        float dk = 0.f, w = 0.f;
-        if (a.d2) {
-          dk = __ldg(a.d2 + row);
-          w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(dk, 1e-8f)), inv_sum);
+      if (a.d2) {
+        // the reference's left-to-right fp32 sum over the K neighbours (terms computed lane-parallel)
+        for (int kc = 0; kc < a.K; kc += 32) {
+          const int kn = min(32, a.K - kc);
+          const float term = lane < kn ? __fdiv_rn(1.0f, __fadd_rn(__ldg(a.d2 + prow + kc + lane), 1e-8f)) : 0.f;
+          for (int k = 0; k < kn; ++k) inv_sum = __fadd_rn(inv_sum, __shfl_sync(0xffffffffu, term, k));
         }
-        float rr[4] = {0.f, 0.f, 0.f, 0.f};
-        if (a.res && any) {
-          if (full) {
-            const float4 r4 = *reinterpret_cast<const float4 *>(a.res + row * a.ldr + n);
-            rr[0] = r4.x; rr[1] = r4.y; rr[2] = r4.z; rr[3] = r4.w;
-          } else {
+      }
+      for (int kc = 0; kc < a.K; kc += 32) {
+        const int kn = min(32, a.K - kc);  // warp-uniform
+        const int jrow = lane < kn ? __ldg(a.idx + prow + kc + lane) : 0;
+        const float drow = (a.d2 && lane < kn) ? __ldg(a.d2 + prow + kc + lane) : 0.f;
+        for (int k0 = 0; k0 < kn; k0 += RB) {
+          float4 uu[RB], r4[RB];
+          float xs[RB][3], dk[RB];
+          bool kon[RB];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (on[u]) rr[u] = a.res[row * a.ldr + n + u];
+          for (int b = 0; b < RB; ++b) {
+            kon[b] = k0 + b < kn;
+            const int j = __shfl_sync(0xffffffffu, jrow, (k0 + b) & 31);
+            dk[b] = __shfl_sync(0xffffffffu, drow, (k0 + b) & 31);
+            const size_t row = prow + kc + k0 + b;
+            const float *x = a.xyz + ((size_t)s * a.nsrc + j) * a.ldx;
+            xs[b][0] = __ldg(x);
+            xs[b][1] = __ldg(x + 1);
+            xs[b][2] = __ldg(x + 2);
+            uu[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (any) uu[b] = __ldg(reinterpret_cast<const float4 *>(a.U + ((size_t)s * a.nsrc + j) * a.ldu + n));
+            r4[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_RES && any && kon[b]) {
+              if (full) {
+                r4[b] = __ldcs(reinterpret_cast<const float4 *>(a.res + row * a.ldr + n));
+              } else {
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (on[u]) t[u] = a.res[row * a.ldr + n + u];
+                r4[b] = make_float4(t[0], t[1], t[2], t[3]);
+              }
+            }
           }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float t = fmaf(x2, wx[u][2], fmaf(x1, wx[u][1], fmaf(x0, wx[u][0], v[u]))) + vterm[u];
-          if (a.d2) t = fmaf(w, ww[u], fmaf(dk, wd[u], t));
-          if (a.res) {
-            float r = fmaf(rr[u], rsc[u], rsh[u]);
-            if (a.xfr.relu) r = fmaxf(r, 0.f);
-            t += r + radd[u];
+          for (int b = 0; b < RB; ++b) {
+            if (!kon[b]) continue;
+            const size_t row = prow + kc + k0 + b;
+            float v[4] = {uu[b].x, uu[b].y, uu[b].z, uu[b].w};
+            const float rr[4] = {r4[b].x, r4[b].y, r4[b].z, r4[b].w};
+            float w = 0.f;
+            if (a.d2) w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(dk[b], 1e-8f)), inv_sum);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float t = fmaf(xs[b][2], wx[u][2], fmaf(xs[b][1], wx[u][1], fmaf(xs[b][0], wx[u][0], v[u]))) + vterm[u];
+              if (a.d2) t = fmaf(w, ww[u], fmaf(dk[b], wd[u], t));
+              if (HAS_RES) {
+                float r = fmaf(rr[u], rsc[u], rsh[u]);
+                if (a.xfr.relu) r = fmaxf(r, 0.f);
+                t += r + radd[u];
+              }
+              if (a.act == 1) t = fmaxf(t, 0.f);
+              v[u] = on[u] ? t : 0.f;
+              ssum[u] += v[u];
+              ssq[u] = fmaf(v[u], v[u], ssq[u]);
+            }
+            if (full) {
+              *reinterpret_cast<float4 *>(a.out + row * a.ldo + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (on[u]) a.out[row * a.ldo + n + u] = v[u];
+            }
           }
-          if (a.act == 1) t = fmaxf(t, 0.f);
-          v[u] = on[u] ? t : 0.f;
-          ssum[u] += v[u];
-          ssq[u] = fmaf(v[u], v[u], ssq[u]);
-        }
-        if (full) {
-          *reinterpret_cast<float4 *>(a.out + row * a.ldo + n) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (on[u]) a.out[row * a.ldo + n + u] = v[u];
         }
       }
     }
@@ -730,7 +758,10 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       const int cols4 = ceil_div(a.N, 4);
       const int threads = cols4 >= 256 ? 256 : ((cols4 + 31) / 32) * 32;
       dim3 grid(ceil_div(a.np, pb), B);
-      pair_kernel<<<grid, threads, 0, st>>>(a);
+      if (a.res)
+        pair_kernel<4, true><<<grid, threads, 0, st>>>(a);
+      else
+        pair_kernel<8, false><<<grid, threads, 0, st>>>(a);
       return after_launch();
     }
     case SLIDE_OP_COLMAX: {

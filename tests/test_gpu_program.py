@@ -46,8 +46,16 @@ def _teacher_forced(b, m, prog, first, count, rtol, log):
     return worst
 
 
-@pytest.mark.parametrize("which,backend,B", [("pos", "simt", 8), ("lat", "simt", 8), ("pos", "auto", 8), ("lat", "auto", 8)])
-def test_records_teacher_forced(which, backend, B, pipeline_cfg):
+@pytest.mark.parametrize("which,backend,B", [("pos", "simt", 8), ("lat", "simt", 8), ("pos", "auto", 8), ("lat", "auto", 8),
+                                             ("pos", "auto-persist", 8), ("lat", "auto-persist", 8)])
+def test_records_teacher_forced(which, backend, B, pipeline_cfg, monkeypatch):
+    if backend == "auto-persist":
+        # force the persistent warp-specialised tcgen05 kernel (normally chosen from 296 tiles up) onto these small
+        # problems, with 3 CTAs so that every CTA walks several tiles (operand ring wrap, both TMEM buffers)
+        monkeypatch.setenv("SLIDE_TC_PERSIST_MIN_TILES", "1")
+        monkeypatch.setenv("SLIDE_TC_PERSIST_MIN_K", "32")
+        monkeypatch.setenv("SLIDE_TC_PERSIST_GRID", "3")
+        backend = "auto"
     b, h, pc, sd = common.ddpm_program(pipeline_cfg, which, B, with_noise=True, T=4)
     m = ir_exec.Machine(b)
     labels = np.arange(B) % 13
@@ -62,7 +70,7 @@ def test_records_teacher_forced(which, backend, B, pipeline_cfg):
     bad = _teacher_forced(b, m, prog, *b.segments["setup"], rtol=TOL[backend], log=log)
     bad += _teacher_forced(b, m, prog, *b.segments["step"], rtol=TOL[backend], log=log)
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/records_%s_%s.log" % (which, backend), "w") as f:
+    with open("gpurun_out/records_%s_%s%s.log" % (which, backend, "_persist" if os.environ.get("SLIDE_TC_PERSIST_GRID") else ""), "w") as f:
         f.write("\n".join(log) + "\n")
     assert lib.load().slide_tc_error() == 0, "tcgen05 pipeline wait timed out"
     assert not bad, bad[:6]

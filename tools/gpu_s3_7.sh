@@ -1,0 +1,12 @@
+mkdir -p gpurun_out
+rm -f gpurun_out/summary.txt
+timeout 900 python -m pytest tests/test_gpu_program.py -x -q -m gpu -p no:cacheprovider --timeout 600 -k "teacher_forced" > gpurun_out/t_prog.log 2>&1; echo "pytest teacher rc=$?" >> gpurun_out/summary.txt
+for mt in 296 148; do
+  SLIDE_TC_PERSIST_MIN_TILES=$mt timeout 300 python tools/profile_records.py lat 256 auto > gpurun_out/s7_lat_mt$mt.txt 2>&1
+  SLIDE_TC_PERSIST_MIN_TILES=$mt timeout 300 python tools/profile_records.py pos 256 auto > gpurun_out/s7_pos_mt$mt.txt 2>&1
+  echo "min_tiles=$mt $(head -1 gpurun_out/s7_lat_mt$mt.txt)" >> gpurun_out/summary.txt
+  echo "min_tiles=$mt $(head -1 gpurun_out/s7_pos_mt$mt.txt)" >> gpurun_out/summary.txt
+done
+SLIDE_B200_LIB=$PWD/slide_b200/libslide_b200_tl.so timeout 300 python tools/tc_timeline.py lat 256 net.SA1.att.w1k,net.SA1.mlp.conv2,net.SA1.att.w2+softmax,net.SA1.att.v,net.FP1.att.w1k,net.FP1.mlp2.conv1 > gpurun_out/tl_lat3.txt 2>&1
+cat gpurun_out/summary.txt; tail -n 6 gpurun_out/t_prog.log | cut -c1-400
+cat gpurun_out/tl_lat3.txt
