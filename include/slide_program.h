@@ -138,12 +138,16 @@ enum slide_softmax_field {
 enum slide_copy_field { CP_SRC = 0, CP_LDS, CP_DST, CP_LDD, CP_ROWS, CP_NCOLS };
 
 /* MODE 0 (pointnet2/util.py:240-253):  x = (x - k1*eps) / sqrt_alpha ; if t > 0: x += sigma * noise
- * MODE 1 (diffusion_utils/diffusion.py:68-92): x0 = c1*x - c2*eps ; [clamp] ; mean = pm1*x0 + pm2*x ;
+ * MODE 1 (diffusion_utils/diffusion.py:68-92): x0 = c1*x - c2*eps ; [clamp] ;
+ *         [local resampling, :76-79: x0 = x0 * mask + X0C * (1 - mask)] ; mean = pm1*x0 + pm2*x ;
  *         x = mean + (t != 0) * sig * noise
  * Only columns [COL0, NCOLS) of x are written (keypoint-conditional sampling keeps the xyz columns).
- * TABLE_W: f32 [T, 8] per-timestep coefficients; NOISE: f32 [T, ROWS, NCOLS] (row stride NCOLS). */
+ * TABLE_W: f32 [T, 8] per-timestep coefficients; NOISE: f32 [T, ROWS, NCOLS] (row stride NCOLS).
+ * X0C (-1 = no local resampling): f32 [ROWS, NCOLS] (row stride LDX0C), the complete x0 whose features are kept where
+ * MASK f32 [ROWS] is 0 and re-sampled where it is 1. */
 enum slide_ddpm_field {
-  DD_MODE = 0, DD_X, DD_LDX, DD_EPS, DD_LDE, DD_NOISE, DD_ROWS, DD_NCOLS, DD_COL0, DD_TABLE_W, DD_STEP
+  DD_MODE = 0, DD_X, DD_LDX, DD_EPS, DD_LDE, DD_NOISE, DD_ROWS, DD_NCOLS, DD_COL0, DD_TABLE_W, DD_STEP,
+  DD_X0C, DD_LDX0C, DD_MASK
 };
 
 /* MODE 0: pointnet2_ops._ext (start 0, |p|^2 <= 1e-3 skipped, i32 out); MODE 1: pytorch3d (start index from

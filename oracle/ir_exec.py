@@ -228,6 +228,10 @@ class Machine(object):
             x0 = c1 * x - c2 * eps
             if f[0] > 0:
                 x0 = np.clip(x0, -f[0], f[0])
+            if g("DD_X0C") >= 0:  # local resampling (diffusion.py:76-79)
+                x0c = self.A(g("DD_X0C"), rows, g("DD_LDX0C"), nc)
+                m = self.A(g("DD_MASK"), rows, 1, 1)
+                x0 = x0 * m + x0c * (f32(1.0) - m)
             new = pm1 * x0 + pm2 * x
             m = f32(0.0 if t == 0 else 1.0)
             new = new + (m * sig) * noise

@@ -1311,7 +1311,7 @@ static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t
   static const int use_tma = env_int("SLIDE_TC_TMA", 1);
   // persistent kernel: 0 = never, 1 = TMA-fed operands only, 2 = also with transform producers / fused soft-max
   const int persist = env_int("SLIDE_TC_PERSIST", 2);  // read per launch: tests flip these
-  const int persist_min_tiles = env_int("SLIDE_TC_PERSIST_MIN_TILES", 2 * 148);
+  const int persist_min_tiles = env_int("SLIDE_TC_PERSIST_MIN_TILES", 148);
   const int persist_min_k = env_int("SLIDE_TC_PERSIST_MIN_K", 256);
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));

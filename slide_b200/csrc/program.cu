@@ -215,7 +215,8 @@ __global__ void copy_cols_kernel(const float *__restrict__ src, int lds, float *
 // evaluates the expression op by op), so given the same eps the update is bit-exact.
 __global__ void ddpm_update_kernel(int mode, float *__restrict__ x, int ldx, const float *__restrict__ eps, int lde,
                                    const float *__restrict__ noise, long long rows, int ncols, int col0,
-                                   const float *__restrict__ table, const int *__restrict__ step_ptr, float clamp) {
+                                   const float *__restrict__ table, const int *__restrict__ step_ptr, float clamp,
+                                   const float *__restrict__ x0c, int ldx0c, const float *__restrict__ mask) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * ncols) return;
   const long long r = e / ncols;
@@ -234,6 +235,11 @@ __global__ void ddpm_update_kernel(int mode, float *__restrict__ x, int ldx, con
     // x0 = c1*x - c2*eps ; clamp ; mean = pm1*x0 + pm2*x ; x = mean + (t != 0) * sig * z   (diffusion.py:71-92)
     float x0 = __fsub_rn(__fmul_rn(tab[0], xv), __fmul_rn(tab[1], ev));
     if (clamp > 0.f) x0 = fminf(fmaxf(x0, -clamp), clamp);
+    if (x0c) {
+      // local resampling: pred_xstart * keypoint_mask + complete_x0 * (1 - keypoint_mask)   (diffusion.py:76-79)
+      const float m = mask[r];
+      x0 = __fadd_rn(__fmul_rn(x0, m), __fmul_rn(x0c[r * ldx0c + c], __fsub_rn(1.0f, m)));
+    }
     const float mean = __fadd_rn(__fmul_rn(tab[2], x0), __fmul_rn(tab[3], xv));
     const float m = t == 0 ? 0.f : 1.f;
     res = __fadd_rn(mean, __fmul_rn(__fmul_rn(m, tab[4]), nz));
@@ -685,7 +691,7 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       ddpm_update_kernel<<<grid_for(rows * n, 256), 256, 0, st>>>(
           (int)q[DD_MODE], AP<float>(p, q[DD_X]), (int)q[DD_LDX], AP<float>(p, q[DD_EPS]), (int)q[DD_LDE],
           AP<float>(p, q[DD_NOISE]), rows, n, (int)q[DD_COL0], WP<float>(p, q[DD_TABLE_W]), AP<int>(p, q[DD_STEP]),
-          op.f[0]);
+          op.f[0], AP<float>(p, q[DD_X0C]), (int)q[DD_LDX0C], AP<float>(p, q[DD_MASK]));
       return after_launch();
     }
     case SLIDE_OP_FPS:

@@ -63,11 +63,14 @@ def latent_table(dcfg):
 # ---------------------------------------------------------------------------------------------------
 # builders
 # ---------------------------------------------------------------------------------------------------
-def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0, with_noise=True):
+def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0, with_noise=True,
+               local_resampling=False):
     """One program = setup segment + step segment (+ forward-only segment) for a DDPM denoiser.
 
     mode 0: position sampler (util.sampling), mode 1: latent sampler (denoising_step).
     keep_cols: leading columns of x the update must not touch (3 for keypoint-conditional sampling).
+    local_resampling (latent sampler only, diffusion.py:76-79): adds the handles x0c [B*n, C] (complete x0) and
+    mask [B*n, 1] (1 = re-sample this point's features); with an all-ones mask the update equals the plain one.
     Handles: x, eps, labels, noise [T*B*n, C], ts_table, class_emb.
     """
     b = Builder(B)
@@ -77,12 +80,15 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
     labels = b.tensor("labels", 1, B, B=1, dtype="i32")
     noise = b.tensor("noise", T * B * n_points if with_noise else 1, C, B=1, ld=C)
     table_off = b.weight(np.asarray(table, dtype=np.float32).reshape(-1, 8)[:T])
+    x0c = b.tensor("x0c", n_points, C) if local_resampling else None
+    mask = b.tensor("mask", n_points, 1, ld=1) if local_resampling else None
     P = nets.Params(sd)
     b.begin_segment("step")
     b.step_begin()
     net = nets.lower_cloud_net(b, P, cfg, X, n_points, "net", T=T, labels=labels)
     fwd_count = len(b.ops) - b._seg_open[1]
-    b.ddpm_update(mode, X, net["out"], noise, table_off, col0=keep_cols, clamp=clamp, note="ddpm_update")
+    b.ddpm_update(mode, X, net["out"], noise, table_off, col0=keep_cols, clamp=clamp, x0c=x0c, mask=mask,
+                  note="ddpm_update")
     b.end_segment()
     first = b.segments["step"][0]
     b.segments["forward"] = (first, fwd_count)
@@ -90,6 +96,8 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
     net["emit_setup"]()
     b.end_segment()
     h = dict(x=X, eps=net["out"], labels=labels, noise=noise, T=T, C=C, n_points=n_points)
+    if local_resampling:
+        h.update(x0c=x0c, mask=mask)
     h.update(net["inputs"])
     return b, h
 

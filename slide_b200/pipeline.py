@@ -23,9 +23,12 @@ from .program import Program
 class DDPMSampler(object):
     """One denoiser + its ancestral sampling loop, resident on one GPU."""
 
-    def __init__(self, pointnet_cfg, sd, B, table, mode, keep_cols, T, device, graph_steps=20, backend="auto"):
+    def __init__(self, pointnet_cfg, sd, B, table, mode, keep_cols, T, device, graph_steps=20, backend="auto",
+                 local_resampling=False, clamp=-1.0):
         self.B, self.T, self.mode = B, T, mode
-        self.builder, self.h = engine.build_ddpm(pointnet_cfg, sd, B, T, table, mode, keep_cols=keep_cols)
+        self.builder, self.h = engine.build_ddpm(pointnet_cfg, sd, B, T, table, mode, keep_cols=keep_cols, clamp=clamp,
+                                                 local_resampling=local_resampling)
+        self.local_resampling = local_resampling
         self.prog = Program(self.builder, device)
         self.prog.set_gemm_backend(backend)
         self.C = self.h["C"]
@@ -39,6 +42,13 @@ class DDPMSampler(object):
         """labels: int tensor (B,).  Recomputes the per-module condition vectors (setup segment)."""
         self.prog.upload(self.h["labels"], labels.to(torch.int32))
         self.prog.run_segment("setup")
+
+    def set_local_resampling(self, complete_x0, keypoint_mask):
+        """complete_x0 (B,16,C), keypoint_mask (B,16) of 0/1: features of points with mask 0 are pinned to complete_x0
+        at every step, the others are re-sampled (denoising_step, diffusion.py:76-79)."""
+        assert self.local_resampling, "build the sampler with local_resampling=True"
+        self.prog.upload(self.h["x0c"], complete_x0.reshape(-1, self.C).float())
+        self.prog.upload(self.h["mask"], keypoint_mask.reshape(-1, 1).float())
 
     def noise_view(self):
         """(T, B*16, C) device view; noise_view()[t] is what the update of step t adds."""
@@ -147,7 +157,7 @@ class SlidePipeline(object):
     """position DDPM -> latent DDPM -> decode for `local_batch` shapes on this GPU (rank `rank` of `world`)."""
 
     def __init__(self, cfg, global_batch, rank=0, world=1, device=None, state_dicts=None, decode_chunk=128,
-                 ddpm_steps=None, backend="auto"):
+                 ddpm_steps=None, backend="auto", local_resampling=False):
         assert global_batch % world == 0
         self.cfg, self.B, self.rank, self.world = cfg, global_batch, rank, world
         self.Bl = global_batch // world
@@ -162,7 +172,8 @@ class SlidePipeline(object):
                                backend=backend)
         self.lat = DDPMSampler(lat["pointnet_config"], sds["latent"], self.Bl,
                                engine.latent_table(lat["standard_diffusion_config"]), 1, 3, self.T_lat, self.device,
-                               backend=backend)
+                               backend=backend, local_resampling=local_resampling,
+                               clamp=float(lat["standard_diffusion_config"].get("data_clamp_range", -1)))
         chunk = min(decode_chunk, self.Bl)
         while self.Bl % chunk:
             chunk -= 1
@@ -203,13 +214,27 @@ class SlidePipeline(object):
         self._lat_xT_dev = self._lat_xT_host.to(dev, non_blocking=True)
         self._starts_dev = self._starts_host.to(dev, non_blocking=True)
 
-    def sample_resident(self):
-        """The three stages on inputs that stage_inputs() already put in HBM; returns the (Bl, 2048, 6) device tensor."""
+    def sample_resident(self, keypoints=None, complete_x0=None, keypoint_mask=None):
+        """The three stages on inputs that stage_inputs() already put in HBM; returns the (Bl, 2048, 6) device tensor.
+
+        keypoints (Bl,16,3) device tensor: external keypoints -- the position DDPM is skipped (the reference's
+        latent_ddpm_keypoint_conditional_generation.py with --keypoint_file).  complete_x0 (Bl,16,3+F) + keypoint_mask
+        (Bl,16): local resampling (--local_resampling; the pipeline must have been built with local_resampling=True)."""
         dev = self.device
-        # 1. position DDPM
-        self.pos.x_view().copy_(self._pos_xT_dev.view(-1, 3))
-        self.pos.run(self.ddpm_steps)
-        kp = self.pos.x_view().view(self.Bl, 16, 3)
+        if keypoints is None:
+            # 1. position DDPM
+            self.pos.x_view().copy_(self._pos_xT_dev.view(-1, 3))
+            self.pos.run(self.ddpm_steps)
+            kp = self.pos.x_view().view(self.Bl, 16, 3)
+        else:
+            kp = keypoints.to(dev).float().view(self.Bl, 16, 3)
+        if self.lat.local_resampling:
+            if complete_x0 is None:  # plain sampling through a resampling-capable program: re-sample everything
+                complete_x0 = torch.zeros(self.Bl, 16, self.lat.C, device=dev)
+                keypoint_mask = torch.ones(self.Bl, 16, device=dev)
+            self.lat.set_local_resampling(complete_x0.to(dev), keypoint_mask.to(dev))
+        else:
+            assert complete_x0 is None, "local resampling needs SlidePipeline(..., local_resampling=True)"
         # 2. latent DDPM on the generated keypoints (keypoint-conditional: xyz columns are never updated)
         x = self.lat.x_view().view(self.Bl, 16, self.lat.C)
         x.copy_(self._lat_xT_dev)
@@ -226,6 +251,7 @@ class SlidePipeline(object):
                 nz[i].copy_(full[lo:lo + self.Bl])
         self.lat.run(self.ddpm_steps)
         feat = x[:, :, 3:].contiguous()
+        self.keypoint, self.keypoint_feature = kp, feat  # (Bl,16,3), (Bl,16,F): what the reference also returns
         # 3. decode
         self.dec.run(kp.contiguous(), feat, self._labels, self._starts_dev, self.out)
         return self.out

@@ -287,12 +287,20 @@ class Builder(object):
         self._emit("SLIDE_OP_COPY_COLS", {"CP_SRC": src.off, "CP_LDS": src.ld, "CP_DST": dst.off, "CP_LDD": dst.ld,
                                           "CP_ROWS": src.rows, "CP_NCOLS": src.C}, note=note)
 
-    def ddpm_update(self, mode, x, eps, noise, table_off, col0=0, clamp=-1.0, note=""):
+    def ddpm_update(self, mode, x, eps, noise, table_off, col0=0, clamp=-1.0, x0c=None, mask=None, note=""):
+        """x0c / mask: local resampling (diffusion.py:76-79), latent sampler only."""
         assert eps.rows == x.rows and eps.C == x.C
+        assert (x0c is None) == (mask is None)
+        if x0c is not None:
+            assert mode == 1 and x0c.rows == x.rows and x0c.C == x.C and mask.rows == x.rows and mask.ld == 1
         self._emit("SLIDE_OP_DDPM_UPDATE", {"DD_MODE": mode, "DD_X": x.off, "DD_LDX": x.ld, "DD_EPS": eps.off,
                                             "DD_LDE": eps.ld, "DD_NOISE": noise.off, "DD_ROWS": x.rows,
                                             "DD_NCOLS": x.C, "DD_COL0": col0, "DD_TABLE_W": table_off,
-                                            "DD_STEP": self.step.off}, floats=[clamp], note=note)
+                                            "DD_STEP": self.step.off,
+                                            "DD_X0C": x0c.off if x0c is not None else -1,
+                                            "DD_LDX0C": x0c.ld if x0c is not None else 0,
+                                            "DD_MASK": mask.off if mask is not None else -1},
+                   floats=[clamp], note=note)
 
     def fps(self, mode, xyz, m, out, start=None, note=""):
         assert out.R == 1 and out.C == m and out.dtype == "i32"

@@ -1,0 +1,120 @@
+"""SURVEY.md 8(f) rows f1 / f2 on CPU: the local-resampling update (oracle and program record) against golden vectors
+made by the REAL reference (tests/golden/make_golden_sampler.py), and the npz formats of the generation driver."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ir_exec, ref_model
+from slide_b200 import engine, generation
+from slide_b200.program import KIND
+from tests import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gs():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_sampler.npz")))
+
+
+def _stand_in(T):
+    return lambda x, ts: 0.5 * torch.tanh(x) + 0.01 * (ts / T).reshape(-1, 1, 1)
+
+
+CASES = [("top", [999, 998, 997]), ("bottom", [2, 1, 0])]
+
+
+@pytest.mark.parametrize("tag,t_list", CASES)
+@pytest.mark.parametrize("local", [False, True])
+def test_oracle_update_matches_reference_golden(tag, t_list, local, gs, pipeline_cfg):
+    sch = ref_model.latent_schedule(pipeline_cfg["latent_ddpm"]["standard_diffusion_config"])
+    noises = {t: torch.from_numpy(gs["noise_" + tag][i]) for i, t in enumerate(t_list)}
+    got = ref_model.latent_denoise(_stand_in(sch["T"]), torch.from_numpy(gs["x_T"]), torch.from_numpy(gs["keypoint"]),
+                                   noises, sch, t_start=t_list[0], n_steps=len(t_list),
+                                   complete_x0=torch.from_numpy(gs["complete_x0"]) if local else None,
+                                   keypoint_mask=torch.from_numpy(gs["mask"]) if local else None)
+    assert np.array_equal(got.numpy(), gs["out_%s_%s" % (tag, "local" if local else "plain")])
+
+
+@pytest.mark.parametrize("tag,t_list", CASES)
+@pytest.mark.parametrize("local", [False, True])
+def test_update_record_matches_reference_golden(tag, t_list, local, gs, pipeline_cfg):
+    """The SLIDE_OP_DDPM_UPDATE record (interpreter of the program the GPU executes) with the stand-in eps uploaded:
+    bit-exact against the reference's loop, including the keypoint columns the update must not touch."""
+    B, T = 3, 1000
+    lat = pipeline_cfg["latent_ddpm"]
+    b, h = engine.build_ddpm(lat["pointnet_config"], common.state_dict("lat"), B, T,
+                             engine.latent_table(lat["standard_diffusion_config"]), 1, keep_cols=3,
+                             local_resampling=local)
+    upd = [i for i, op in enumerate(b.ops) if op[0] == KIND["SLIDE_OP_DDPM_UPDATE"]]
+    assert len(upd) == 1
+    m = ir_exec.Machine(b)
+    kp = torch.from_numpy(gs["keypoint"])
+    x = torch.cat([kp, torch.from_numpy(gs["x_T"])[:, :, 3:]], dim=2)
+    m.upload(h["x"], x)
+    if local:
+        m.upload(h["x0c"], torch.from_numpy(gs["complete_x0"]))
+        m.upload(h["mask"], torch.from_numpy(gs["mask"]).reshape(-1, 1))
+    nz = m.view(h["noise"]).reshape(T, B * 16, h["C"])
+    model = _stand_in(T)
+    for i, t in enumerate(t_list):
+        nz[t] = gs["noise_" + tag][i].reshape(B * 16, -1)
+        xin = m.download(h["x"]).reshape(B, 16, -1)
+        m.upload(h["eps"], model(xin, torch.ones(B) * t))
+        m.set_step(t)
+        m.run(upd[0], 1)
+    got = m.download(h["x"]).reshape(B, 16, -1).numpy()
+    assert np.array_equal(got, gs["out_%s_%s" % (tag, "local" if local else "plain")])
+
+
+def test_all_ones_mask_is_plain_sampling(gs, pipeline_cfg):
+    sch = ref_model.latent_schedule(pipeline_cfg["latent_ddpm"]["standard_diffusion_config"])
+    noises = {t: torch.from_numpy(gs["noise_top"][i]) for i, t in enumerate([999, 998, 997])}
+    args = (_stand_in(sch["T"]), torch.from_numpy(gs["x_T"]), torch.from_numpy(gs["keypoint"]), noises, sch)
+    plain = ref_model.latent_denoise(*args, n_steps=3)
+    ones = ref_model.latent_denoise(*args, n_steps=3, complete_x0=torch.from_numpy(gs["complete_x0"]),
+                                    keypoint_mask=torch.ones(3, 16))
+    assert torch.equal(plain, ones)
+
+
+def test_keypoint_file_and_result_formats(tmp_path):
+    B = 5
+    g = np.random.RandomState(0)
+    kp_file = str(tmp_path / "keypoints.npz")
+    np.savez(kp_file, points=g.rand(B, 16, 3).astype(np.float32), label=np.arange(B) % 13,
+             category=np.array(["02691156"] * B), category_name=np.array(["airplane"] * B),
+             keypoint_feature=g.randn(B, 16, 48).astype(np.float32), keypoint_mask=(g.rand(B, 16) < 0.5).astype(np.float32))
+    whole = generation.load_keypoint_file(kp_file, local_resampling=True)
+    assert whole["points"].shape == (B, 16, 3) and whole["complete_x0"].shape == (B, 16, 51)
+    assert torch.equal(whole["complete_x0"][:, :, :3], whole["points"])
+    # GeneralNpzDataset slicing: ceil(B / W) per rank, the last rank takes the remainder
+    parts = [generation.load_keypoint_file(kp_file, rank=r, world_size=2, local_resampling=True) for r in range(2)]
+    assert [p["points"].shape[0] for p in parts] == [3, 2]
+    assert torch.equal(torch.cat([p["points"] for p in parts]), whole["points"])
+    assert parts[0]["category"] + parts[1]["category"] == whole["category"]
+    # result files: per-rank names, keys and the points / normals split of evaluate_per_rank, then the rank-0 gather
+    save_dir = str(tmp_path / "out")
+    os.makedirs(save_dir)
+    clouds = g.randn(B, 2048, 6).astype(np.float32)
+    lo = 0
+    for r, p in enumerate(parts):
+        n = p["points"].shape[0]
+        res = generation.pack_results(clouds[lo:lo + n], p["label"].numpy(), p["category"], p["category_name"],
+                                      [0.1] * n, keypoint=p["points"].numpy(),
+                                      keypoint_feature=np.zeros((n, 16, 48), np.float32))
+        assert res["points"].shape == (n, 2048, 3) and res["normals"].shape == (n, 2048, 3)
+        f = generation.result_file(save_dir, 2048, r, 2)
+        assert os.path.basename(f) == "shapenet_psr_generated_data_2048_pts_rank_%d.npz" % r
+        np.savez(f, **res)
+        lo += n
+    out = generation.gather_generated_results(save_dir, 2, num_points=2048)
+    assert os.path.basename(out) == "shapenet_psr_generated_data_2048_pts.npz"
+    assert sorted(os.listdir(save_dir)) == ["shapenet_psr_generated_data_2048_pts.npz"]
+    data = np.load(out)
+    assert sorted(data.files) == sorted(["points", "normals", "label", "category", "category_name", "timing", "keypoint",
+                                         "keypoint_feature"])
+    assert np.array_equal(data["points"], clouds[:, :, :3]) and np.array_equal(data["normals"], clouds[:, :, 3:])
+    assert np.array_equal(data["keypoint"], whole["points"].numpy())
+    assert list(data["category_name"]) == ["airplane"] * B
