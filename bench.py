@@ -67,6 +67,31 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the tcgen05 GEMM from the committed `ncu --set full`
+    capture (profiles/r01_gemm_tc_ncu_full.txt, one cold launch per record), next to the algorithmic bytes of the same
+    launches; None when the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_tc_ncu_full.txt")
+    try:
+        rows = {}
+        for line in open(path):
+            if line.startswith("#") or "|" not in line:
+                continue
+            head, rest = line[:76].strip(), line[76:]
+            rows[head.split("  ")[0].strip()] = [c.strip() for c in rest.split("|")]
+        names = rows["Kernel Name"]
+        rd = [c.split()[-1] for c in rows["dram__bytes_read.sum"]]
+        wr = [c.split()[-1] for c in rows["dram__bytes_write.sum"]]
+        out = []
+        for n, r, w in zip(names, rd, wr):
+            if "gemm_tc" in n:
+                out.append({"kernel": n.replace("void ", "").split("(")[0], "dram_mbytes": float(r) + float(w)})
+        return {"per_launch": out, "source": "profiles/r01_gemm_tc_ncu_full.txt",
+                "records": "SA1.att.v, SA1.att.w2+softmax, SA1.mlp.conv1 of the feature-DDPM step (algorithmic MB: 269.5, 277.9, 134.5)"}
+    except Exception:
+        return None
+
+
 def cpu_path(cfg, seconds_budget=20.0):
     """The reference's CPU path for this pipeline: its python modules as restated in oracle/ref_model.py (checked
     bit-for-bit against the real modules by tests/golden/make_golden.py) over the C oracle ops, all host cores.
@@ -223,12 +248,16 @@ def main():
         lat.prog.set_step(lat.T)
         lat.prog.run(first, count)
         torch.cuda.synchronize()
-        flops = t_us = 0.0
+        flops = t_us = abytes = 0.0
         n_launch = 0
         for i in range(first, first + count):
             kind, f, _fl, _note = lat.builder.ops[i]
             if kind != KIND["SLIDE_OP_GEMM"] or f.get("GEMM_WP_W", -1) < 0 or f["GEMM_M"] < 128:
                 continue
+            # algorithmic bytes of the launch: A in, W in, C out (+ the residual / soft-max value rows it reads); fp32
+            rows_out = f["GEMM_M"] // f["GEMM_SMK"] if f.get("GEMM_SMK", 0) > 0 else f["GEMM_M"]
+            abytes += 4.0 * (f["GEMM_M"] * f["GEMM_K"] + f["GEMM_N"] * f["GEMM_K"] + rows_out * f["GEMM_N"] +
+                             (f["GEMM_M"] * f["GEMM_N"] if f.get("GEMM_RES", -1) >= 0 else 0))
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             for _ in range(3):
@@ -240,8 +269,19 @@ def main():
             n_launch += 1
         achieved = flops / t_us / 1e6  # TFLOP/s
         whole = (Bl / (ms_value / 1e3)) * GFLOP_PER_SHAPE / 1e3
+        traffic = ncu_traffic()
+        traffic_mean = (1e6 * sum(x["dram_mbytes"] for x in traffic["per_launch"]) / len(traffic["per_launch"])
+                        if traffic and traffic["per_launch"] else None)
+        hbm_peak = peaks.get("hbm_gbs", 6500.0)
+        hbm_gbs = abytes / t_us / 1e3
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": which, "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32)",
+                "traffic": traffic_mean, "traffic_unit": "bytes per launch (mean of the ncu-captured GEMM launches)",
+                "traffic_detail": traffic, "peak_source": which,
+                "kernel": "gemm_tcp_kernel / gemm_tc_kernel (tcgen05.mma kind::tf32, persistent + one-tile variants)",
+                # the same launches against the HBM roofline: with fp32 activations in HBM most of these GEMMs
+                # (K, N <= 256: < 64 FLOP/B) sit left of the TF32 ridge, so this is the view that bounds them
+                "hbm_view": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                             "algorithmic_bytes_per_launch_set": abytes},
                 "launches_timed": n_launch, "avg_launch_us": t_us / max(n_launch, 1),
                 "executed_gflop_per_launch_set": flops / 1e9,
                 "whole_step_achieved": whole, "whole_step_frac": whole / peak,

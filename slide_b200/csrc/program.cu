@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(128) knn_prog_kernel(const float *__restrict__
 }
 
 // =====================================================================================================
-// GROUP: one warp per grouped row; channels-last makes the feature part a contiguous row copy
+// GROUP (wide rows): one warp per grouped row; channels-last makes the feature part a contiguous row copy
 // =====================================================================================================
-__global__ void __launch_bounds__(256) group_kernel(int mode, const float *__restrict__ F, int ldf, int C,
+__global__ void __launch_bounds__(256) group_rows_kernel(int mode, const float *__restrict__ F, int ldf, int C,
                                                     const float *__restrict__ xyz, int ldx, int N,
                                                     const float *__restrict__ ctr, int ldc, int np,
                                                     const int *__restrict__ idx, int K, const float *__restrict__ d2,
@@ -145,6 +145,56 @@ __global__ void __launch_bounds__(256) group_kernel(int mode, const float *__res
       }
     }
   }
+}
+
+// =====================================================================================================
+// GROUP (narrow rows, W <= 16: the xyz-only inputs): one thread per output element.  Every element is an independent
+// index -> gather -> store chain, so the whole tensor is in flight at once (measured on B200, 65536 rows x 12:
+// 24.6 -> 12.3 us; for wide rows the warp-per-row kernel above wins: 28.7 vs 65.5 us at 278 columns).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) group_elem_kernel(int mode, const float *__restrict__ F, int ldf, int C,
+                                                    const float *__restrict__ xyz, int ldx, int N,
+                                                    const float *__restrict__ ctr, int ldc, int np,
+                                                    const int *__restrict__ idx, int K, const float *__restrict__ d2,
+                                                    float *__restrict__ out, int ldo, int inc_abs, int inc_ctr,
+                                                    long long rows, int W) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * W) return;
+  const long long row = e / W;
+  const int c = (int)(e - row * W);
+  const long long pi = row / K;  // (sample, point)
+  const int s = (int)(pi / np);
+  const int j = __ldg(idx + row);
+  float v;
+  if (c < C) {
+    v = __ldg(F + ((size_t)s * N + j) * ldf + c);
+  } else {
+    const int t = c - C;
+    const float *xj = xyz + ((size_t)s * N + j) * ldx;
+    const float *ci = ctr + (size_t)pi * ldc;
+    if (mode == 0) {
+      // [x_j - c_i | x_j | c_i]  (the abs / centre blocks are optional)
+      const int blk = t / 3, d = t - 3 * blk;
+      const int what = blk == 0 ? 0 : (blk == 1 && inc_abs ? 1 : 2);
+      const float a = __ldg(xj + d), cc = __ldg(ci + d);
+      v = what == 0 ? __fsub_rn(a, cc) : (what == 1 ? a : cc);
+    } else {
+      // [d2 | w | x_j | x_j - c_i | c_i],  w = (1/(d2+1e-8)) / sum_k (1/(d2+1e-8))  (sum in ascending k like torch.sum)
+      if (t == 0) {
+        v = __ldg(d2 + row);
+      } else if (t == 1) {
+        const float *dr = d2 + pi * K;
+        float sum = 0.f;
+        for (int k = 0; k < K; ++k) sum = __fadd_rn(sum, __fdiv_rn(1.0f, __fadd_rn(__ldg(dr + k), 1e-8f)));
+        v = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(__ldg(d2 + row), 1e-8f)), sum);
+      } else {
+        const int blk = (t - 2) / 3, d = (t - 2) - 3 * blk;
+        const float a = __ldg(xj + d), cc = __ldg(ci + d);
+        v = blk == 0 ? a : (blk == 1 ? __fsub_rn(a, cc) : cc);
+      }
+    }
+  }
+  out[row * ldo + c] = v;
 }
 
 // =====================================================================================================
@@ -627,14 +677,23 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
     }
     case SLIDE_OP_GROUP: {
       const long long rows = (long long)q[GRP_B] * q[GRP_NP] * q[GRP_K];
-      unsigned g = grid_for(rows * 32, 256);
-      if (g > 148 * 16) g = 148 * 16;
-      group_kernel<<<g, 256, 0, st>>>((int)q[GRP_MODE], AP<float>(p, q[GRP_F]), (int)q[GRP_LDF], (int)q[GRP_C],
-                                      AP<float>(p, q[GRP_XYZ]), (int)q[GRP_LDX], (int)q[GRP_N],
-                                      AP<float>(p, q[GRP_CTR]), (int)q[GRP_LDCTR], (int)q[GRP_NP],
-                                      AP<int>(p, q[GRP_IDX]), (int)q[GRP_K], AP<float>(p, q[GRP_D2]),
-                                      AP<float>(p, q[GRP_OUT]), (int)q[GRP_LDO], (int)q[GRP_ABS],
-                                      (int)q[GRP_CENTER], rows);
+      const int mode = (int)q[GRP_MODE];
+      const int W = (int)q[GRP_C] + (mode == 0 ? 3 + (q[GRP_ABS] ? 3 : 0) + (q[GRP_CENTER] ? 3 : 0) : 11);
+      if (W <= 16) {
+        group_elem_kernel<<<grid_for(rows * W, 256), 256, 0, st>>>(
+            mode, AP<float>(p, q[GRP_F]), (int)q[GRP_LDF], (int)q[GRP_C], AP<float>(p, q[GRP_XYZ]), (int)q[GRP_LDX],
+            (int)q[GRP_N], AP<float>(p, q[GRP_CTR]), (int)q[GRP_LDCTR], (int)q[GRP_NP], AP<int>(p, q[GRP_IDX]),
+            (int)q[GRP_K], AP<float>(p, q[GRP_D2]), AP<float>(p, q[GRP_OUT]), (int)q[GRP_LDO], (int)q[GRP_ABS],
+            (int)q[GRP_CENTER], rows, W);
+      } else {
+        unsigned g = grid_for(rows * 32, 256);
+        if (g > 148 * 16) g = 148 * 16;
+        group_rows_kernel<<<g, 256, 0, st>>>(
+            mode, AP<float>(p, q[GRP_F]), (int)q[GRP_LDF], (int)q[GRP_C], AP<float>(p, q[GRP_XYZ]), (int)q[GRP_LDX],
+            (int)q[GRP_N], AP<float>(p, q[GRP_CTR]), (int)q[GRP_LDCTR], (int)q[GRP_NP], AP<int>(p, q[GRP_IDX]),
+            (int)q[GRP_K], AP<float>(p, q[GRP_D2]), AP<float>(p, q[GRP_OUT]), (int)q[GRP_LDO], (int)q[GRP_ABS],
+            (int)q[GRP_CENTER], rows);
+      }
       return after_launch();
     }
     case SLIDE_OP_GEMM: {

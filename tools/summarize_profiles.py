@@ -71,7 +71,9 @@ def main():
     launches(tag)
     ncu_full(tag)
     for src, dst in (("prof_lat_auto.txt", "%s_records_latent_step.txt"), ("prof_pos_auto.txt", "%s_records_position_step.txt"),
-                     ("bench_r1.log", "%s_bench.json"), ("bench_r1_reference.log", "%s_bench_reference.json")):
+                     ("timeline_lat.txt", "%s_gemm_timeline_latent.txt"), ("timeline_pos.txt", "%s_gemm_timeline_position.txt"),
+                     ("bench_r1.log", "%s_bench.json"), ("bench_r1_reference.log", "%s_bench_reference.json"),
+                     ("bench_2gpu.log", "%s_bench_2gpu.json")):
         s = os.path.join(G, src)
         if os.path.exists(s):
             if src.endswith(".log"):
