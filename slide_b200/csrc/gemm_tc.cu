@@ -111,6 +111,12 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   return mbar_wait_slow(bar, parity);
 }
 
+// x / d for x >= 0, d > 0.  The divisors on the epilogue's per-chunk path (neighbours per point, rows per sample,
+// channels per GroupNorm group) are powers of two in every shipped configuration: a shift instead of the ~20-instruction
+// division sequence whose I2F / MUFU.RCP / F2I go through the quarter-rate XU pipe (ncu: XU pipe 60 % busy in the
+// epilogue-bound kernels).  d is warp-uniform, so the branch does not diverge.
+__device__ __forceinline__ int idiv(int x, int d) { return (d & (d - 1)) == 0 ? x >> (31 - __clz(d)) : x / d; }
+
 __device__ __forceinline__ uint32_t to_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -472,7 +478,7 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
     bias_nx = (on_ && a.bias) ? __ldg(a.bias + n_) : 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      ev_nx[q] = (!SMK && on_ && a.ev && mw_ + 32 <= a.M) ? __ldg(a.ev + (size_t)((mw_ + 8 * q) / a.evdiv) * a.evld + n_)
+      ev_nx[q] = (!SMK && on_ && a.ev && mw_ + 32 <= a.M) ? __ldg(a.ev + (size_t)idiv(mw_ + 8 * q, a.evdiv) * a.evld + n_)
                                                          : 0.f;
   };
   prefetch_vec(32 * (warp >> 2));
@@ -485,7 +491,7 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
   float *tbuf = reinterpret_cast<float *>(smem) + (warp < TC_PWARPS ? warp : 0) * (32 * 33);
   float4 *tabR = reinterpret_cast<float4 *>(smem + TC_PWARPS * 32 * 33 * 4);
   const bool has_xfr = a.res && (a.xfr.stats != nullptr || a.xfr.addvec != nullptr || a.xfr.relu != 0);
-  const int sR0 = m0 / a.xfr.R;
+  const int sR0 = idiv(m0, a.xfr.R);
   __syncthreads();
   if (has_xfr) {
     const int ncols = min(BN, a.N - n0);
@@ -515,9 +521,9 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int mb = mw + 8 * q;
-      ev_off[q] = a.ev ? (mb / a.evdiv) * a.evld : 0;
-      xr_off[q] = has_xfr ? (mb / a.xfr.R - sR0) * BN : 0;
-      st_off[q] = a.st_stats ? (mb / a.st_R - sS0) * XF_MAXG * 2 : 0;
+      ev_off[q] = a.ev ? idiv(mb, a.evdiv) * a.evld : 0;
+      xr_off[q] = has_xfr ? (idiv(mb, a.xfr.R) - sR0) * BN : 0;
+      st_off[q] = a.st_stats ? (idiv(mb, a.st_R) - sS0) * XF_MAXG * 2 : 0;
     }
     for (int c0 = 32 * cpar; c0 < BN; c0 += 64) {
       if (n0 + c0 >= a.N || (dbg & 4)) break;
@@ -551,7 +557,7 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
       const bool ncol = n < a.N;
       const int stch = a.st_choff + n;
       const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
-      const int stg = dost ? stch / a.st_cg : 0;
+      const int stg = dost ? idiv(stch, a.st_cg) : 0;
       if (SMK) {
         // fused AttentionModule tail: soft-max down each group of smk rows (the neighbours of one point), applied
         // to the transformed value rows; one output row per group.  (bias is constant down a column: it cancels.)
@@ -560,7 +566,7 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
         if (ncol && smk_fast) {
           float x[32];
           load_rows32(x, a.res + (size_t)mw * a.ldr + n, a.ldr, true);
-          float *op = a.C + (size_t)(mw / K) * a.ldc + n;
+          float *op = a.C + (size_t)idiv(mw, K) * a.ldc + n;
           if (K == 16) smk_chunk<16>(tbuf, lane, x, has_xfr, xr_relu, tabR, xr_off, c0 + lane, op, a.ldc);
           else if (K == 8) smk_chunk<8>(tbuf, lane, x, has_xfr, xr_relu, tabR, xr_off, c0 + lane, op, a.ldc);
           else if (K == 32) smk_chunk<32>(tbuf, lane, x, has_xfr, xr_relu, tabR, xr_off, c0 + lane, op, a.ldc);
@@ -1026,7 +1032,7 @@ __global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
         const int n_ = n0 + c0_ + lane;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          ev_nx[q] = (!SMK && a.ev && c0_ < BN && n_ < a.N) ? __ldg(a.ev + (size_t)((mw + 8 * q) / a.evdiv) * a.evld + n_) : 0.f;
+          ev_nx[q] = (!SMK && a.ev && c0_ < BN && n_ < a.N) ? __ldg(a.ev + (size_t)idiv(mw + 8 * q, a.evdiv) * a.evld + n_) : 0.f;
       };
       prefetch_ev(32 * cpar);
       epi_bar_sync();
@@ -1073,12 +1079,12 @@ __global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
         const float bias = c.w;
         const int stch = a.st_choff + n;
         const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
-        const int stg = dost ? stch / a.st_cg : 0;
+        const int stg = dost ? idiv(stch, a.st_cg) : 0;
         if (SMK) {
           // fused AttentionModule tail (see smk_chunk); the whole tile is one sample: a single resid-table row
           if (ncol) {
             const int zoff[4] = {0, 0, 0, 0};
-            float *op = a.C + (size_t)(mw / a.smk) * a.ldc + n;
+            float *op = a.C + (size_t)idiv(mw, a.smk) * a.ldc + n;
             if (a.smk == 16) smk_chunk<16>(tbuf, lane, xres, has_xfr, xr_relu, tabR, zoff, c0 + lane, op, a.ldc);
             else if (a.smk == 8) smk_chunk<8>(tbuf, lane, xres, has_xfr, xr_relu, tabR, zoff, c0 + lane, op, a.ldc);
             else if (a.smk == 32) smk_chunk<32>(tbuf, lane, xres, has_xfr, xr_relu, tabR, zoff, c0 + lane, op, a.ldc);
@@ -1337,6 +1343,80 @@ static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t
     return launch_tc_impl<BN, STAGES, false, true>(a, Wp, wp_na, st, tm);
   }
   return launch_tc_impl<BN, STAGES, false, false>(a, Wp, wp_na, st, tm);
+}
+
+// =====================================================================================================
+// Transform pre-pass for row tiles that span several samples.  With 16 rows per sample a 128-row tile needs 8 table
+// rows and the in-loop transform reads one table entry per ELEMENT (measured: M=4096 K=256 N=256 53 us with the
+// fused transform vs 16 us TMA-fed); the tensors are tiny (M x K x 4 B <= a few MB, L2-resident), so normalising
+// them once (~4 us) and feeding the GEMM by TMA is the faster order.  Same (scale, shift, add) arithmetic as the
+// fused path; the copy engine rounds to TF32.
+// =====================================================================================================
+constexpr int PP_COLS = 64;
+
+__global__ void __launch_bounds__(256) xf_prepass_kernel(GemmArgs a, float *__restrict__ out, int ldo) {
+  __shared__ float4 tab[XF_MAXS * PP_COLS];
+  __shared__ float2 mr[XF_MAXS * XF_MAXG];
+  const int m0 = blockIdx.y * TBM, k0 = blockIdx.x * PP_COLS;
+  const int mlast = min(m0 + TBM, a.M) - 1;
+  const int s0 = m0 / a.xfa.R, ns = mlast / a.xfa.R - s0 + 1;
+  const int ncols = min(PP_COLS, a.K - k0);
+  const int step = a.step ? *a.step : 0;
+  fill_xf_table(a.xfa, tab, mr, s0, ns, ncols, k0, PP_COLS, step, threadIdx.x, 256);
+  __syncthreads();
+  const bool relu = a.xfa.relu != 0;
+  for (int e = threadIdx.x; e < TBM * (PP_COLS / 4); e += 256) {
+    const int r = e / (PP_COLS / 4), c4 = (e - r * (PP_COLS / 4)) * 4;
+    const int m = m0 + r, k = k0 + c4;
+    if (m >= a.M || c4 >= ncols) continue;
+    const float4 x = *reinterpret_cast<const float4 *>(a.A + (size_t)m * a.lda + k);
+    const float4 *t = tab + (m / a.xfa.R - s0) * PP_COLS + c4;
+    float v[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (c4 + u < ncols) {
+        const float4 c = t[u];
+        float y = fmaf(v[u], c.x, c.y);
+        if (relu) y = fmaxf(y, 0.f);
+        v[u] = y + c.z;
+      } else {
+        v[u] = 0.f;
+      }
+    }
+    *reinterpret_cast<float4 *>(out + (size_t)m * ldo + k) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+static GemmArgs prepass_args(const GemmArgs &a, float *scratch) {
+  GemmArgs b = a;
+  b.A = scratch;
+  b.lda = (a.K + 3) & ~3;
+  b.xfa.stats = nullptr;
+  b.xfa.addvec = nullptr;
+  b.xfa.relu = 0;
+  return b;
+}
+
+bool gemm_tc_prepass_applicable(const GemmArgs &a) {
+  if (env_int("SLIDE_TC_PREPASS", 1) == 0) return false;
+  // A/B on B200 (M = 4096): K = 256 55 -> 25 us; K <= 128 18 -> 22 us (the extra launch costs more than it saves)
+  if (a.K <= 128) return false;
+  if (!has_xf(a.xfa) || a.xfa.R % TBM == 0 || TBM % a.xfa.R != 0 || TBM / a.xfa.R > XF_MAXS) return false;
+  if (a.xfa.stats && a.xfa.nnorm / a.xfa.cg > XF_MAXG) return false;
+  if (((uintptr_t)a.A & 15) || (a.lda & 3)) return false;
+  return true;
+}
+
+size_t gemm_tc_prepass_bytes(int M, int K) { return (size_t)M * ((K + 3) & ~3) * 4; }
+
+int launch_gemm_tc_prepass(const GemmArgs &a, const float *Wp, int wp_na, float *scratch, cudaStream_t st) {
+  const GemmArgs b = prepass_args(a, scratch);
+  if (!gemm_tc_eligible(b, Wp)) return TCP_NOT_APPLICABLE;
+  dim3 grid(ceil_div(a.K, PP_COLS), ceil_div(a.M, TBM));
+  xf_prepass_kernel<<<grid, 256, 0, st>>>(a, scratch, b.lda);
+  const int rc = after_launch();
+  if (rc != SLIDE_OK) return rc;
+  return launch_gemm_tc(b, Wp, wp_na, st);
 }
 
 int launch_gemm_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {

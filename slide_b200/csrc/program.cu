@@ -608,6 +608,9 @@ struct slide_program {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int use_side = 1;  // SLIDE_SIDE_BRANCH=0 runs everything on one stream
+  // scratch of the GEMM transform pre-pass (gemm_tc.cu), one buffer per stream so that the two branches never share
+  float *prepass[2] = {nullptr, nullptr};
+  size_t prepass_bytes = 0;
 };
 
 namespace {
@@ -726,6 +729,11 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       a.smk = (int)q[GEMM_SMK];
       if (a.smk > 0 && (!a.res || a.ev || a.st_stats || a.act || a.M % a.smk)) return SLIDE_ERR_INVALID;
       const float *wp = WP<float>(p, q[GEMM_WP_W]);
+      if (p->gemm_backend == 0 && wp && gemm_tc_prepass_applicable(a) &&
+          gemm_tc_prepass_bytes(a.M, a.K) <= p->prepass_bytes) {
+        const int rc = launch_gemm_tc_prepass(a, wp, (int)q[GEMM_WP_NA], p->prepass[st == p->side ? 1 : 0], st);
+        if (rc <= 0) return rc;  // > 0: not applicable after all -> the fused-transform paths below
+      }
       if (p->gemm_backend == 0 && gemm_tc_eligible(a, wp)) return launch_gemm_tc(a, wp, (int)q[GEMM_WP_NA], st);
       return launch_gemm_simt(a, st);
     }
@@ -907,6 +915,18 @@ int slide_program_create(const struct slide_op *ops, int n_ops, size_t arena_byt
   if (rc == SLIDE_OK) rc = cuda_rc(cudaMalloc((void **)&p->weights, weights_bytes > 0 ? weights_bytes : 256));
   if (rc == SLIDE_OK && weights && weights_bytes)
     rc = cuda_rc(cudaMemcpy(p->weights, weights, weights_bytes, cudaMemcpyHostToDevice));
+  // scratch for the GEMM transform pre-pass: the largest point-level A operand that qualifies (cheap: <= a few MB)
+  for (const slide_op &op : p->ops) {
+    if (op.kind != SLIDE_OP_GEMM || op.p[GEMM_WP_W] < 0) continue;
+    const int64_t *xf = op.p + GEMM_XFA;
+    const bool has = xf[XF_STATS] >= 0 || xf[XF_ADDVEC] >= 0 || xf[XF_RELU] != 0;
+    const int R = (int)xf[XF_R];
+    if (!has || R <= 0 || R % 128 == 0 || 128 % R != 0) continue;
+    const size_t need = gemm_tc_prepass_bytes((int)op.p[GEMM_M], (int)op.p[GEMM_K]);
+    if (need > p->prepass_bytes && need <= ((size_t)256 << 20)) p->prepass_bytes = need;
+  }
+  for (int i = 0; i < 2 && rc == SLIDE_OK && p->prepass_bytes; ++i)
+    rc = cuda_rc(cudaMalloc((void **)&p->prepass[i], p->prepass_bytes));
   if (rc == SLIDE_OK) rc = cuda_rc(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
   if (rc == SLIDE_OK) rc = cuda_rc(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
   if (rc == SLIDE_OK) rc = cuda_rc(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
@@ -927,6 +947,8 @@ void slide_program_destroy(slide_program *p) {
   if (p->side) cudaStreamDestroy(p->side);
   if (p->arena) cudaFree(p->arena);
   if (p->weights) cudaFree(p->weights);
+  for (int i = 0; i < 2; ++i)
+    if (p->prepass[i]) cudaFree(p->prepass[i]);
   delete p;
 }
 

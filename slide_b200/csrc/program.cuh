@@ -85,6 +85,11 @@ __device__ __forceinline__ float act_apply(int act, float v) {
 int launch_gemm_simt(const GemmArgs &a, cudaStream_t st);
 bool gemm_tc_eligible(const GemmArgs &a, const float *Wp);
 int launch_gemm_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st);
+// Row tiles of 128 that span several samples (point-level tensors: 16 rows per sample): apply the A transform in a
+// small elementwise pre-pass into `scratch` (rows of round4(K) floats) so that the GEMM takes the TMA-fed path.
+bool gemm_tc_prepass_applicable(const GemmArgs &a);
+size_t gemm_tc_prepass_bytes(int M, int K);
+int launch_gemm_tc_prepass(const GemmArgs &a, const float *Wp, int wp_na, float *scratch, cudaStream_t st);
 int tc_error_flag();
 int program_fps(int mode, const float *xyz, int ldx, int B, int N, int m, const int *start, int *out, cudaStream_t st);
 
