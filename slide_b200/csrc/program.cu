@@ -821,9 +821,12 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       if (!a.U || !a.out || !a.idx || a.K <= 0 || B <= 0 || B > 65535) return SLIDE_ERR_INVALID;
       if (a.d2 && (!a.wd || !a.ww)) return SLIDE_ERR_INVALID;
       if (a.res && a.xfr.stats && a.xfr.R != a.np * a.K) return SLIDE_ERR_UNSUPPORTED;
-      // points per CTA: aim for >= ~4 CTAs per SM overall, at least 64 rows per CTA
+      // points per CTA: aim for >= 16 CTAs per SM overall, at least 32 rows per CTA
       int pb = a.np;
-      while (pb > 1 && (long long)B * ceil_div(a.np, pb) < 592 && pb * a.K > 64) pb = (pb + 1) / 2;
+      static const char *e_ctas = getenv("SLIDE_PAIR_MIN_CTAS"), *e_rows = getenv("SLIDE_PAIR_MIN_ROWS");
+      // A/B on B200 (feature-DDPM step): (592 CTAs, 64 rows) 1764 us, (2368, 32) 1750 us, (4736, 16) 1784 us
+      const int min_ctas = e_ctas ? atoi(e_ctas) : 2368, min_rows = e_rows ? atoi(e_rows) : 32;
+      while (pb > 1 && (long long)B * ceil_div(a.np, pb) < min_ctas && pb * a.K > min_rows) pb = (pb + 1) / 2;
       a.pb = pb;
       if (((uintptr_t)a.U & 15) || (a.ldu & 3) || ((uintptr_t)a.out & 15) || (a.ldo & 3) ||
           (a.res && (((uintptr_t)a.res & 15) || (a.ldr & 3))))
