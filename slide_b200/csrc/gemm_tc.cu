@@ -1199,8 +1199,7 @@ static bool has_xf(const XFd &x) { return x.stats || x.addvec || x.relu; }
 
 bool gemm_tc_eligible(const GemmArgs &a, const float *Wp) {
   if (!Wp) return false;
-  // (the lowering gives tensor-core weight copies only to contractions with K, N >= 32 unless told otherwise)
-  if (a.M < TBM || a.K < 4 || a.N < 1) return false;
+  if (a.M < TBM || a.K < 32 || a.N < 32) return false;
   if ((long long)a.M * a.N * a.K < TC_MIN_MACS) return false;
   if (((uintptr_t)a.A & 15) || (a.lda & 3) || ((uintptr_t)Wp & 15)) return false;
   if (has_xf(a.xfa)) {

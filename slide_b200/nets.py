@@ -29,7 +29,7 @@ from .program import XF, NO_XF, Builder  # noqa: F401
 FACTOR_MIN_WORK = 250000  # see _Grouped.plan
 
 # contractions at least this large get a tensor-core weight copy (the kernel applies further shape tests)
-TC_MIN_K, TC_MIN_N = int(os.environ.get("SLIDE_TC_MIN_K", "32")), int(os.environ.get("SLIDE_TC_MIN_N", "32"))
+TC_MIN_K, TC_MIN_N = 32, 32
 
 
 def _np(x):
