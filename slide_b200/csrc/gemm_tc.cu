@@ -743,8 +743,8 @@ constexpr int TCP_THREADS = 32 * (2 + TCP_EPI_WARPS);
 constexpr int TCP_XFA_THREADS = TCP_THREADS + TC_PRODUCERS;
 
 __host__ __device__ constexpr int tcp_smem_bytes(int BN, int STAGES) {
-  // operand ring | per-warp transpose tiles | resid table x2 | barriers | statistics x2
-  return STAGES * tc_stage_bytes(BN) + TCP_EPI_WARPS * 32 * 33 * 4 + 2 * BN * 16 + 512 + 2 * XF_MAXG * 2 * 4;
+  // operand ring | per-warp transpose tiles | resid table x2 | barriers | per-lane-window column sums [4][BN] float2
+  return STAGES * tc_stage_bytes(BN) + TCP_EPI_WARPS * 32 * 33 * 4 + 2 * BN * 16 + 512 + 4 * BN * 8;
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TCP_EPI_WARPS * 32) : "memory"); }
@@ -769,9 +769,9 @@ __global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
   uint64_t *tfull_bar = raw_bar + STAGES;
   uint64_t *tempty_bar = tfull_bar + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
-  float *stacc_all = reinterpret_cast<float *>(ctrl + 512);
-  float2 *mrA = reinterpret_cast<float2 *>(ctrl + 512 + 2 * XF_MAXG * 2 * 4);  // XFA: (mean, rstd) per group
-  float4 *tabA = reinterpret_cast<float4 *>(ctrl + 512 + 2 * XF_MAXG * 2 * 4 + XF_MAXG * 8);  // XFA: per K column
+  float2 *spart = reinterpret_cast<float2 *>(ctrl + 512);  // (sum, sum of squares) per (lane window, tile column)
+  float2 *mrA = reinterpret_cast<float2 *>(ctrl + 512 + 4 * BN * 8);  // XFA: (mean, rstd) per group
+  float4 *tabA = reinterpret_cast<float4 *>(ctrl + 512 + 4 * BN * 8 + XF_MAXG * 8);  // XFA: per K column
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int step = a.step ? *a.step : 0;
@@ -993,10 +993,8 @@ __global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
       const int m0 = (t / tiles_n) * TBM, n0 = (t % tiles_n) * BN;
       const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
       float4 *tabR = tabR_all + buf * BN;
-      float *stacc = stacc_all + buf * (XF_MAXG * 2);
       // per-tile set-up (runs while the tile's MMAs are still in flight): statistics accumulators, and one
       // (scale, shift, add, bias) entry per column: the resid transform of this (sample, column range) + the bias
-      if (a.st_stats && etid < XF_MAXG * 2) stacc[etid] = 0.f;
       if (etid < BN) {
         const int n = n0 + etid;
         float scale = 1.f, shift = 0.f, add = 0.f, bias = 0.f;
@@ -1079,7 +1077,6 @@ __global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
         const float bias = c.w;
         const int stch = a.st_choff + n;
         const bool dost = a.st_stats && ncol && stch < a.st_nnorm;
-        const int stg = dost ? idiv(stch, a.st_cg) : 0;
         if (SMK) {
           // fused AttentionModule tail (see smk_chunk); the whole tile is one sample: a single resid-table row
           if (ncol) {
@@ -1140,21 +1137,9 @@ __global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
             }
           }
         }
-        if (a.st_stats) {  // warp-uniform; the whole tile belongs to one sample
-          float rs = ssum, rq = ssq;
-          bool leader = dost;
-          if (st_pow2) {
-            for (int d = 1; d < st_seg; d <<= 1) {
-              rs += __shfl_xor_sync(0xffffffffu, rs, d);
-              rq += __shfl_xor_sync(0xffffffffu, rq, d);
-            }
-            leader = dost && (lane & (st_seg - 1)) == 0;
-          }
-          if (leader) {
-            atomicAdd(stacc + stg * 2, rs);
-            atomicAdd(stacc + stg * 2 + 1, rq);
-          }
-        }
+        // column sums of this warp's 32 rows: parked per (lane window, column); reduced once per tile below (the
+        // per-chunk shuffle tree + shared-memory float atomics -- CAS loops -- cost 17 % of the epilogue's samples)
+        if (a.st_stats) spart[lq * BN + c0 + lane] = make_float2(dost ? ssum : 0.f, dost ? ssq : 0.f);
         __syncwarp();
         TLP_END(3);
       }
@@ -1163,13 +1148,37 @@ __global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(tempty_bar + buf));
       if (a.st_stats) {
-        epi_bar_sync();
+        epi_bar_sync();  // every warp has parked its column sums
+        // thread = tile column: add the four lane windows, reduce the columns of a GroupNorm group with a segmented
+        // butterfly, one fp64 atomic pair per (segment, moment)
         const int G = a.st_nnorm / a.st_cg;
-        if (etid < G * 2) {
-          const float v = stacc[etid];
-          if (v != 0.f)
-            atomicAdd(a.st_stats + ((size_t)(m0 / a.st_R) * G) * 2 + etid, (double)v * (double)a.st_weight);
+        const int ncols = min(BN, a.N - n0);
+        float rs = 0.f, rq = 0.f;
+        const int stch = a.st_choff + n0 + etid;
+        const bool on = etid < ncols && stch < a.st_nnorm;
+        if (on) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float2 v = spart[w * BN + etid];
+            rs += v.x;
+            rq += v.y;
+          }
         }
+        bool leader = on;
+        if (st_pow2) {
+          for (int d = 1; d < st_seg; d <<= 1) {
+            rs += __shfl_xor_sync(0xffffffffu, rs, d);
+            rq += __shfl_xor_sync(0xffffffffu, rq, d);
+          }
+          leader = on && (lane & (st_seg - 1)) == 0;
+        }
+        if (leader && etid < BN) {
+          double *slot = a.st_stats + ((size_t)(m0 / a.st_R) * G + idiv(stch, a.st_cg)) * 2;
+          atomicAdd(slot, (double)rs * (double)a.st_weight);
+          atomicAdd(slot + 1, (double)rq * (double)a.st_weight);
+        }
+        // (the parking area is rewritten only after the next tile's set-up barrier, which every warp reaches after
+        // these reads)
       }
     }
   }
