@@ -1327,7 +1327,7 @@ static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t
   // persistent kernel: 0 = never, 1 = TMA-fed operands only, 2 = also with transform producers / fused soft-max
   const int persist = env_int("SLIDE_TC_PERSIST", 2);  // read per launch: tests flip these
   const int persist_min_tiles = env_int("SLIDE_TC_PERSIST_MIN_TILES", 148);
-  const int persist_min_k = env_int("SLIDE_TC_PERSIST_MIN_K", 256);
+  const int persist_min_k = env_int("SLIDE_TC_PERSIST_MIN_K", 32);
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   // every row tile inside one sample, whole row tiles, 8-row blocks inside one ev row
@@ -1343,9 +1343,11 @@ static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t
   if (a.smk > 0) return launch_tc_impl<BN, STAGES, true, false>(a, Wp, wp_na, st, tm);
   // A needs no transform and its rows are 16-byte aligned with a 16-byte pitch: let TMA fetch it
   if (use_tma && !xfa && make_a_map(a, &tm)) {
-    // short K loops are epilogue-bound: two resident CTAs drain faster than one persistent CTA (measured on B200:
-    // K=60 N=256 60 -> 85 us persistent, K=512 N=512 109 -> 90 us)
-    if (persist >= 1 && one_sample && tiles >= persist_min_tiles && BN >= 128 && a.K >= persist_min_k) {
+    // A/B on B200 after the per-tile statistics reduction (feature / position DDPM step, us): min K 256: 1702 / 861,
+    // 64: 1703 / 835, 32: 1677 / 836; narrower tiles (BN < 128) gain nothing.  (Before that change short K loops were
+    // epilogue-bound and the persistent kernel lost: K=60 N=256 60 -> 85 us.)
+    if (persist >= 1 && one_sample && tiles >= persist_min_tiles && BN >= env_int("SLIDE_TC_PERSIST_MIN_BN", 128) &&
+        a.K >= persist_min_k) {
       const int rc = launch_tcp<BN, false, false>(a, Wp, wp_na, st, tm);
       if (rc != TCP_NOT_APPLICABLE) return rc;
     }
