@@ -118,3 +118,45 @@ def test_keypoint_file_and_result_formats(tmp_path):
     assert np.array_equal(data["points"], clouds[:, :, :3]) and np.array_equal(data["normals"], clouds[:, :, 3:])
     assert np.array_equal(data["keypoint"], whole["points"].numpy())
     assert list(data["category_name"]) == ["airplane"] * B
+
+
+class _FakePipe(object):
+    """Stands in for SlidePipeline (no GPU): clouds = keypoints tiled, features = batch index, so that the driver's
+    batching / tail padding / trimming can be checked on CPU."""
+    world, rank = 1, 0
+
+    class _Dec(object):
+        out_points = 2048
+
+    def __init__(self, Bl):
+        self.Bl, self.dec, self.device, self.calls = Bl, self._Dec(), torch.device("cpu"), []
+
+    def draw_host_inputs(self, labels):
+        assert labels.shape == (self.Bl,)
+        self._labels = labels
+
+    def stage_inputs(self):
+        pass
+
+    def sample_resident(self, keypoints=None, complete_x0=None, keypoint_mask=None):
+        assert keypoints.shape == (self.Bl, 16, 3)
+        self.calls.append((complete_x0 is not None, keypoint_mask is not None))
+        self.keypoint_feature = keypoints.sum(dim=2, keepdim=True).expand(self.Bl, 16, 48).contiguous()
+        return torch.cat([keypoints.repeat(1, 128, 1), torch.ones(self.Bl, 2048, 3)], dim=2)
+
+
+def test_generation_driver_batches_pads_and_trims(tmp_path):
+    n, Bl = 7, 3
+    kp = torch.arange(n * 16 * 3, dtype=torch.float32).reshape(n, 16, 3)
+    label = torch.arange(n) % 13
+    pipe = _FakePipe(Bl)
+    res = generation.generate_per_rank(pipe, kp, label, category=["c"] * n, category_name=["n"] * n,
+                                       save_dir=str(tmp_path), save_keypoint_feature=True,
+                                       complete_x0=torch.zeros(n, 16, 51), keypoint_mask=torch.ones(n, 16))
+    assert len(pipe.calls) == 3 and all(c == (True, True) for c in pipe.calls)  # 3 + 3 + (1 padded to 3)
+    assert res["points"].shape == (n, 2048, 3) and res["normals"].shape == (n, 2048, 3)
+    assert np.array_equal(res["points"][:, :16], kp.numpy())  # sample i of the output belongs to keypoint set i
+    assert np.array_equal(res["keypoint_feature"][:, :, 0], kp.sum(dim=2).numpy())
+    assert np.array_equal(res["label"], label.numpy()) and len(res["timing"]) == n
+    data = np.load(os.path.join(str(tmp_path), "shapenet_psr_generated_data_2048_pts.npz"))
+    assert np.array_equal(data["keypoint"], kp.numpy())
