@@ -1,26 +1,31 @@
 // tcgen05 GEMM for sm_100a: C = act( xfA(A) W^T + bias + ev + xfR(resid) ) with TF32 operands, fp32 accumulation
 // in tensor memory, and the fused GroupNorm prologue / statistics epilogue of SLIDE_OP_GEMM.
 //
+// Two kernels share the operand formats and the epilogue arithmetic:
+//   gemm_tcp_kernel  persistent and warp-specialised (copy warp, MMA warp, 8 epilogue warps, optionally 8 transform
+//                    warps), double-buffered TMEM accumulator; taken when a launch has >= 148 tiles that each lie
+//                    inside one sample (the pair-level layers of the DDPMs at batch 256, most decode / encode layers);
+//   gemm_tc_kernel   one tile per CTA, two CTAs per SM; takes everything else (point-level rows, ragged tiles).
+//
 // Operand paths
 //   W (weights)  : a TF32-rounded copy tiled on the host exactly as the B operand sits in shared memory
 //                  (slide_program.h, GEMM_WP_W), so one cp.async.bulk per (N tile, K block) lands a whole
 //                  SWIZZLE_128B tile and signals the stage's mbarrier with its byte count -- no thread touches it.
 //   A (activations): NOT stored in the form the tensor core consumes: the producing layer's GroupNorm + ReLU +
 //                  timestep/condition vector are applied WHILE loading (this is what removes the separate
-//                  normalisation pass over HBM).  Four producer warps move A global -> registers (transform,
-//                  round-to-nearest TF32) -> shared memory in the K-major SWIZZLE_128B layout, with the next
-//                  K block's global loads already in flight while the current one is transformed and stored.
-//                  When A needs no transform (the grouped inputs and residual-summed tensors: q/k/v projections,
-//                  first convs, residual branches) the tile is fetched by TMA instead: one
-//                  cp.async.bulk.tensor.2d per stage (TFLOAT32 tensor map: the copy engine rounds fp32 to TF32 and
-//                  writes the SWIZZLE_128B layout), and the producer warps sleep until the epilogue.
+//                  normalisation pass over HBM).
+//                  - no transform needed (grouped inputs, residual-summed tensors: q/k/v projections, first convs,
+//                    residual branches): one cp.async.bulk.tensor.2d per stage (TFLOAT32 tensor map: the copy engine
+//                    rounds fp32 to TF32 and writes the SWIZZLE_128B layout);
+//                  - persistent kernel, transform needed: the same tensor copy with a plain fp32 map, then the
+//                    transform warps rewrite the tile in place (shared -> registers -> shared, cvt.rna.tf32);
+//                  - one-tile kernel, transform needed: eight producer warps move A global -> registers (transform)
+//                    -> shared memory in the K-major SWIZZLE_128B layout, two K blocks of loads in flight;
+//                  - point-level operands with K > 128 (a 128-row tile spans 8 samples): normalised once by
+//                    xf_prepass_kernel into scratch, then TMA-fed.
 //   D            : one elected thread issues tcgen05.mma (M=128, N=BN, K=8 per instruction); the accumulator lives
-//                  in TMEM and is drained by the four producer warps with tcgen05.ld, transposed through shared
+//                  in TMEM and is drained with tcgen05.ld (32 lanes x 32 columns per warp), transposed through shared
 //                  memory so that every global store / residual load is a coalesced 128-byte row segment.
-//
-// CTA = 160 threads: warps 0-3 produce A, then run the epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4
-// allocates TMEM and issues the MMAs.  Shared memory is sized so that two CTAs share an SM: one CTA's epilogue
-// overlaps the other's main loop.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
