@@ -141,6 +141,8 @@ enum slide_copy_field { CP_SRC = 0, CP_LDS, CP_DST, CP_LDD, CP_ROWS, CP_NCOLS };
  * MODE 1 (diffusion_utils/diffusion.py:68-92): x0 = c1*x - c2*eps ; [clamp] ;
  *         [local resampling, :76-79: x0 = x0 * mask + X0C * (1 - mask)] ; mean = pm1*x0 + pm2*x ;
  *         x = mean + (t != 0) * sig * noise
+ * MODE 2 (pointnet2/util_fastdpmv2.py:436-443, FastDPM VAR / STEP samplers): x = x * a + (c * eps + sigma * noise)
+ *         with TABLE_W row = [a, c, sigma] (row index = step counter, see engine.fast_position_schedule)
  * Only columns [COL0, NCOLS) of x are written (keypoint-conditional sampling keeps the xyz columns).
  * TABLE_W: f32 [T, 8] per-timestep coefficients; NOISE: f32 [T, ROWS, NCOLS] (row stride NCOLS).
  * X0C (-1 = no local resampling): f32 [ROWS, NCOLS] (row stride LDX0C), the complete x0 whose features are kept where

@@ -223,6 +223,9 @@ class Machine(object):
             new = (x - k1 * eps) / sa
             if t > 0:
                 new = new + sig * noise
+        elif g("DD_MODE") == 2:
+            a_, c_, sig = f32(tab[0]), f32(tab[1]), f32(tab[2])
+            new = x * a_ + (c_ * eps + sig * noise)
         else:
             c1, c2, pm1, pm2, sig = [f32(v) for v in tab[:5]]
             x0 = c1 * x - c2 * eps

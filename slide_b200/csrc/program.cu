@@ -281,6 +281,9 @@ __global__ void ddpm_update_kernel(int mode, float *__restrict__ x, int ldx, con
     // x = (x - k1*eps) / sqrt_alpha ; if t > 0: x += sigma * z          (pointnet2/util.py:247-253)
     res = __fdiv_rn(__fsub_rn(xv, __fmul_rn(tab[0], ev)), tab[1]);
     if (t > 0) res = __fadd_rn(res, __fmul_rn(tab[2], nz));
+  } else if (mode == 2) {
+    // x *= a ; x += c*eps + sigma*z                                       (util_fastdpmv2.py:440-443)
+    res = __fadd_rn(__fmul_rn(xv, tab[0]), __fadd_rn(__fmul_rn(tab[1], ev), __fmul_rn(tab[2], nz)));
   } else {
     // x0 = c1*x - c2*eps ; clamp ; mean = pm1*x0 + pm2*x ; x = mean + (t != 0) * sig * z   (diffusion.py:71-92)
     float x0 = __fsub_rn(__fmul_rn(tab[0], xv), __fmul_rn(tab[1], ev));

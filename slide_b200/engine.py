@@ -60,14 +60,66 @@ def latent_table(dcfg):
     return tab.numpy()
 
 
+def _alpha_bar_fp32(T, beta_0, beta_T):
+    import torch
+    Beta = torch.linspace(beta_0, beta_T, T)
+    ab = 1 - Beta
+    for t in range(1, T):
+        ab[t] *= ab[t - 1]
+    return Beta, ab
+
+
+def fast_position_schedule(method, length, schedule, kappa, dcfg):
+    """FastDPM STEP sampler of the position DDPM (util_fastdpmv2.py: STEP_sampling :384-452, get_STEP_step :239-258,
+    entry fast_sampling_function_v2 :455-478) as data for a `mode 2` program:
+    returns (ts, table) with `length` rows in STEP-COUNTER order (row s is used when the program's step counter is s;
+    the sampler's i-th iteration is s = length-1-i): ts[s] = the (possibly fractional) diffusion step the denoiser is
+    evaluated at, table[s] = [a, c, sigma] of the update x = x*a + (c*eps + sigma*z).  All coefficient arithmetic is
+    fp32 torch in the reference's operation order."""
+    import torch
+    T, b0, bT = dcfg["T"], dcfg["beta_0"], dcfg["beta_T"]
+    Beta, ab = _alpha_bar_fp32(T, b0, bT)
+    if method == "step":
+        if schedule == "linear":
+            taus = [int(np.floor(i * ((T - 1.0) / (length - 1.0)))) for i in range(length)]
+        elif schedule == "quadratic":
+            taus = [int(v) for v in np.linspace(0, np.sqrt(T * 0.8), length) ** 2]
+        else:
+            raise NotImplementedError(schedule)
+        taus = sorted(taus, reverse=True)
+        ts = [float(t) for t in taus]
+        cur = [ab[t] for t in taus]
+    elif method == "var":
+        # VAR_sampling (util_fastdpmv2.py:307-381) cannot run as shipped: its last continuous step comes out as 0.497
+        # for every length / schedule of the (T=1000, 1e-4..0.02) configs and trips its own `assert abs(tau) < 0.1`
+        raise NotImplementedError("the reference's VAR sampler asserts on its own schedule; use method='step'")
+    else:
+        raise NotImplementedError(method)
+    tab = torch.zeros(length, 8)
+    for i in range(length):
+        if i == length - 1:
+            nxt, sigma = torch.tensor(1.0), torch.tensor(0.0)
+        else:
+            nxt = cur[i + 1]
+            sigma = kappa * torch.sqrt((1 - nxt) / (1 - cur[i]) * (1 - cur[i] / nxt))
+        a = torch.sqrt(nxt / cur[i])
+        c = torch.sqrt(1 - nxt - sigma ** 2) - torch.sqrt(1 - cur[i]) * torch.sqrt(nxt / cur[i])
+        s = length - 1 - i
+        tab[s, 0], tab[s, 1], tab[s, 2] = a, c, sigma
+    ts_by_counter = np.asarray(ts[::-1], dtype=np.float32)  # torch.ones(n) * tau in the reference: fp32
+    return ts_by_counter, tab.numpy()
+
+
 # ---------------------------------------------------------------------------------------------------
 # builders
 # ---------------------------------------------------------------------------------------------------
 def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0, with_noise=True,
-               local_resampling=False):
+               local_resampling=False, ts_values=None):
     """One program = setup segment + step segment (+ forward-only segment) for a DDPM denoiser.
 
-    mode 0: position sampler (util.sampling), mode 1: latent sampler (denoising_step).
+    mode 0: position sampler (util.sampling), mode 1: latent sampler (denoising_step), mode 2: FastDPM sampler
+    (util_fastdpmv2.VAR_sampling / STEP_sampling; T = number of reverse steps, ts_values / table from
+    fast_position_schedule).
     keep_cols: leading columns of x the update must not touch (3 for keypoint-conditional sampling).
     local_resampling (latent sampler only, diffusion.py:76-79): adds the handles x0c [B*n, C] (complete x0) and
     mask [B*n, 1] (1 = re-sample this point's features); with an all-ones mask the update equals the plain one.
@@ -98,6 +150,9 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
     h = dict(x=X, eps=net["out"], labels=labels, noise=noise, T=T, C=C, n_points=n_points)
     if local_resampling:
         h.update(x0c=x0c, mask=mask)
+    if ts_values is not None:
+        assert len(ts_values) == T
+        h["ts_values"] = np.asarray(ts_values, dtype=np.float32)
     h.update(net["inputs"])
     return b, h
 
@@ -146,7 +201,7 @@ def init_constants(machine, h):
     """Upload the constants a freshly created program needs before its setup segment runs: the timestep list
     0..T-1 and the class-embedding table(s).  `machine` is a Program or the CPU interpreter (same interface)."""
     if "ts_table" in h:
-        machine.upload(h["ts_table"], np.arange(h["T"], dtype=np.float32))
+        machine.upload(h["ts_table"], h["ts_values"] if "ts_values" in h else np.arange(h["T"], dtype=np.float32))
     if "class_emb" in h:
         t, w = h["class_emb"]
         machine.upload(t, w)

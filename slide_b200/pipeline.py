@@ -24,10 +24,10 @@ class DDPMSampler(object):
     """One denoiser + its ancestral sampling loop, resident on one GPU."""
 
     def __init__(self, pointnet_cfg, sd, B, table, mode, keep_cols, T, device, graph_steps=20, backend="auto",
-                 local_resampling=False, clamp=-1.0):
+                 local_resampling=False, clamp=-1.0, ts_values=None):
         self.B, self.T, self.mode = B, T, mode
         self.builder, self.h = engine.build_ddpm(pointnet_cfg, sd, B, T, table, mode, keep_cols=keep_cols, clamp=clamp,
-                                                 local_resampling=local_resampling)
+                                                 local_resampling=local_resampling, ts_values=ts_values)
         self.local_resampling = local_resampling
         self.prog = Program(self.builder, device)
         self.prog.set_gemm_backend(backend)
@@ -157,7 +157,9 @@ class SlidePipeline(object):
     """position DDPM -> latent DDPM -> decode for `local_batch` shapes on this GPU (rank `rank` of `world`)."""
 
     def __init__(self, cfg, global_batch, rank=0, world=1, device=None, state_dicts=None, decode_chunk=128,
-                 ddpm_steps=None, backend="auto", local_resampling=False):
+                 ddpm_steps=None, backend="auto", local_resampling=False, position_sampler=None):
+        """position_sampler: None = the 1000-step ancestral sampler (util.sampling), or the FastDPM STEP sampler
+        dict(method="step", length=L, schedule="linear"|"quadratic", kappa=k) (util_fastdpmv2.fast_sampling_function_v2)."""
         assert global_batch % world == 0
         self.cfg, self.B, self.rank, self.world = cfg, global_batch, rank, world
         self.Bl = global_batch // world
@@ -165,11 +167,19 @@ class SlidePipeline(object):
         sds = default_state_dicts() if state_dicts is None else state_dicts
         pos, lat = cfg["position_ddpm"], cfg["latent_ddpm"]
         d = pos["diffusion_config"]
-        self.T_pos = d["T"]
         self.T_lat = lat["standard_diffusion_config"]["num_diffusion_timesteps"]
-        self.pos = DDPMSampler(pos["pointnet_config"], sds["position"], self.Bl,
-                               engine.position_table(d["T"], d["beta_0"], d["beta_T"]), 0, 0, self.T_pos, self.device,
-                               backend=backend)
+        self.position_sampler = position_sampler
+        if position_sampler is None:
+            self.T_pos = d["T"]
+            self.pos = DDPMSampler(pos["pointnet_config"], sds["position"], self.Bl,
+                                   engine.position_table(d["T"], d["beta_0"], d["beta_T"]), 0, 0, self.T_pos, self.device,
+                                   backend=backend)
+        else:
+            ps = position_sampler
+            ts, table = engine.fast_position_schedule(ps["method"], ps["length"], ps["schedule"], ps["kappa"], d)
+            self.T_pos = ps["length"]
+            self.pos = DDPMSampler(pos["pointnet_config"], sds["position"], self.Bl, table, 2, 0, self.T_pos, self.device,
+                                   backend=backend, ts_values=ts)
         self.lat = DDPMSampler(lat["pointnet_config"], sds["latent"], self.Bl,
                                engine.latent_table(lat["standard_diffusion_config"]), 1, 3, self.T_lat, self.device,
                                backend=backend, local_resampling=local_resampling,
@@ -193,7 +203,8 @@ class SlidePipeline(object):
     def draw_host_inputs(self, labels):
         """labels: CPU int tensor (global_batch,).  Draws, on the CPU default generator and in the reference's
         order, everything the reference draws on the host; stores this rank's slices in pinned buffers."""
-        d = draw_host_inputs(self.cfg, self.B, self.rank, self.world, labels)
+        d = draw_host_inputs(self.cfg, self.B, self.rank, self.world, labels,
+                             fast_steps=None if self.position_sampler is None else self.T_pos)
         self._pos_noise_host.view(self.T_pos, self.Bl, 16, 3).copy_(d["pos_noise"])
         self._pos_xT_host.copy_(d["pos_xT"])
         self._lat_xT_host.copy_(d["lat_xT"])
@@ -282,14 +293,16 @@ class SlidePipeline(object):
                 (self.Bl // self.dec.chunk) * self.dec.launches_per_chunk())
 
 
-def draw_host_inputs(cfg, B, rank, world, labels):
+def draw_host_inputs(cfg, B, rank, world, labels, fast_steps=None):
     """Everything the reference draws on the CPU generator, for the FULL batch and in the reference's call order,
     sliced to rank `rank` of `world` (so results do not depend on the world size):
       pos_xT (Bl,16,3), pos_noise (T,Bl,16,3) with pos_noise[t] = the z added after step t (util.py:225,253),
-      lat_xT (Bl,16,3+F) (diffusion.py:373), starts (levels,Bl) pytorch3d FPS start indices, labels (Bl,)."""
+      lat_xT (Bl,16,3+F) (diffusion.py:373), starts (levels,Bl) pytorch3d FPS start indices, labels (Bl,).
+    fast_steps = L: the FastDPM samplers draw x_T and then one std_normal in EVERY one of their L iterations
+    (util_fastdpmv2.py:443): pos_noise (L,Bl,16,3) with row s = the draw of iteration L-1-s."""
     Bl = B // world
     lo, hi = rank * Bl, (rank + 1) * Bl
-    T = cfg["position_ddpm"]["diffusion_config"]["T"]
+    T = cfg["position_ddpm"]["diffusion_config"]["T"] if fast_steps is None else fast_steps + 1
     C_lat = 3 + cfg["latent_ddpm"]["pointnet_config"]["in_fea_dim"]
     size = (B, 16, 3)
     if (B * 48) % 16 == 0:
@@ -297,8 +310,11 @@ def draw_host_inputs(cfg, B, rank, world, labels):
     else:
         big = torch.stack([torch.normal(0, 1, size=size) for _ in range(T)])
     # big[0] = x_T; big[1+i] = z added after step t = T-1-i (i = 0..T-2)
-    pos_noise = torch.zeros(T, Bl, 16, 3)
-    pos_noise[1:] = torch.flip(big[1:, lo:hi], dims=[0])
+    if fast_steps is None:
+        pos_noise = torch.zeros(T, Bl, 16, 3)
+        pos_noise[1:] = torch.flip(big[1:, lo:hi], dims=[0])
+    else:
+        pos_noise = torch.flip(big[1:, lo:hi], dims=[0]).contiguous()
     lat_xT = torch.randn(B, 16, C_lat)[lo:hi].clone()
     decs = cfg["autoencoder"]["decoders"]
     starts = torch.zeros(len(decs), Bl, dtype=torch.int64)

@@ -81,3 +81,45 @@ def test_generation_driver_external_keypoints_and_local_resampling(pipeline_cfg,
     torch.cuda.manual_seed(6)
     res2 = generation.generate_per_rank(pipe, kp, label)
     assert res2["points"].shape == (n, 2048, 3) and np.isfinite(res2["points"]).all()
+
+
+@pytest.mark.parametrize("schedule,kappa", [("linear", 0.0), ("quadratic", 0.5), ("quadratic", 1.0)])
+def test_fast_sampler_update_kernel_matches_reference_golden(schedule, kappa, pipeline_cfg):
+    """the mode-2 update kernel + engine.fast_position_schedule, bit-exact against the reference's
+    STEP_sampling (golden_fast.npz, stand-in denoiser)."""
+    gf = dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_fast.npz")))
+    dcfg = {"T": 1000, "beta_0": 0.0001, "beta_T": 0.02}
+    draws = torch.from_numpy(gf["draws"])
+    L, B = int(gf["length"]), draws.shape[1]
+    ts, table = engine.fast_position_schedule("step", L, schedule, kappa, dcfg)
+    pos = pipeline_cfg["position_ddpm"]
+    b, h = engine.build_ddpm(pos["pointnet_config"], common.state_dict("pos"), B, L, table, 2, ts_values=ts)
+    upd = [i for i, op in enumerate(b.ops) if op[0] == KIND["SLIDE_OP_DDPM_UPDATE"]][0]
+    prog = Program(b)
+    prog.upload(h["x"], draws[0].reshape(B * 16, 3))
+    nz = prog.view(h["noise"]).view(L, B * 16, 3)
+    for i in range(L):
+        s = L - 1 - i
+        nz[s].copy_(draws[1 + i].reshape(B * 16, 3))
+        x = prog.download(h["x"]).cpu().reshape(B, 16, 3)
+        eps = 0.5 * torch.tanh(x) + 0.01 * (torch.ones(B) * float(ts[s]) / 1000).reshape(-1, 1, 1)
+        prog.upload(h["eps"], eps.reshape(B * 16, 3))
+        prog.set_step(s)
+        prog.run(upd, 1)
+    got = prog.download(h["x"]).cpu().reshape(B, 16, 3).numpy()
+    assert np.array_equal(got, gf["out_step_%s_%g" % (schedule, kappa)])
+
+
+def test_pipeline_with_fast_position_sampler(pipeline_cfg):
+    cfg = _tiny_cfg(pipeline_cfg)
+    cfg["position_ddpm"]["diffusion_config"]["T"] = 1000  # the STEP sampler picks its steps from the full schedule
+    B = 4
+    pipe = pipeline.SlidePipeline(cfg, B, decode_chunk=4,
+                                  position_sampler=dict(method="step", length=6, schedule="quadratic", kappa=0.5))
+    assert pipe.T_pos == 6 and pipe.pos.mode == 2
+    torch.manual_seed(1)
+    pipe.draw_host_inputs(torch.full((B,), cfg["label"], dtype=torch.long))
+    torch.cuda.manual_seed(2)
+    out = pipe.sample_to_host()
+    assert out.shape == (B, 2048, 6) and torch.isfinite(out).all()
+    assert lib.load().slide_tc_error() == 0
