@@ -1,5 +1,6 @@
-"""Golden vectors of the reference's feature-DDPM update, with and without local resampling, from the REAL
-pointnet2/diffusion_utils/diffusion.py (build container only: needs /root/reference).
+"""Golden vectors of the reference's samplers from the REAL reference (build container only: needs /root/reference):
+the feature-DDPM update, with and without local resampling (pointnet2/diffusion_utils/diffusion.py), and the position
+DDPM's full 1000-step chain (pointnet2/util.py::sampling).
 
     python tests/golden/make_golden_sampler.py      ->  tests/golden/golden_sampler.npz
 
@@ -67,6 +68,28 @@ def main():
                                             keypoint_mask=mask if local else None)
             assert torch.equal(x, mine), "oracle/ref_model.latent_denoise deviates from the reference (%s, local=%s)" % (tag, local)
             gold["out_%s_%s" % (tag, "local" if local else "plain")] = x.numpy()
+    # ---- position DDPM: the REAL util.sampling over its full 1000-step chain (stand-in denoiser, pinned draws: x_T,
+    # then one std_normal after every step t > 0, util.py:225,253)
+    import io
+    import contextlib
+    import util as ref_util
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    pcfg = weights.load_json("pipeline_airplane.json")["position_ddpm"]["diffusion_config"]
+    dh = ref_util.calc_diffusion_hyperparams(**pcfg)
+    Tp = pcfg["T"]
+    Bp = 2
+    pdraws = [torch.randn(Bp, N, 3, generator=g) for _ in range(Tp)]
+    it = iter(pdraws)
+    ref_util.std_normal = lambda size: next(it).clone()
+    pmodel = stand_in(Tp)
+    with contextlib.redirect_stdout(io.StringIO()):
+        xp = ref_util.sampling(pmodel, (Bp, N, 3), dh, label=None, verbose=False)
+    noises = {t: pdraws[Tp - t] for t in range(Tp - 1, 0, -1)}  # draw i+1 follows step t = T-1-i
+    mine = ref_model.position_sampling(lambda xx, tt: pmodel(xx, ts=tt), pdraws[0], noises,
+                                       ref_model.position_schedule(pcfg["T"], pcfg["beta_0"], pcfg["beta_T"]))
+    assert torch.equal(xp, mine), "oracle/ref_model.position_sampling deviates from the reference"
+    gold["pos_draws"] = torch.stack(pdraws).numpy()
+    gold["pos_out"] = xp.numpy()
     np.savez_compressed(os.path.join(OUT, "golden_sampler.npz"), **gold)
     print("wrote golden_sampler.npz:", sorted(gold))
 

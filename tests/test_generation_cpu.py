@@ -160,3 +160,31 @@ def test_generation_driver_batches_pads_and_trims(tmp_path):
     assert np.array_equal(res["label"], label.numpy()) and len(res["timing"]) == n
     data = np.load(os.path.join(str(tmp_path), "shapenet_psr_generated_data_2048_pts.npz"))
     assert np.array_equal(data["keypoint"], kp.numpy())
+
+
+def test_position_sampler_matches_reference_golden(gs, pipeline_cfg):
+    """The position DDPM's full 1000-step chain (pointnet2/util.py::sampling run by make_golden_sampler.py with a
+    stand-in denoiser): the oracle's loop and the mode-0 SLIDE_OP_DDPM_UPDATE record with engine.position_table are
+    both bit-exact, step after step."""
+    d = pipeline_cfg["position_ddpm"]["diffusion_config"]
+    T = d["T"]
+    draws = torch.from_numpy(gs["pos_draws"])
+    B = draws.shape[1]
+    model = _stand_in(T)
+    noises = {t: draws[T - t] for t in range(T - 1, 0, -1)}
+    got = ref_model.position_sampling(model, draws[0], noises, ref_model.position_schedule(T, d["beta_0"], d["beta_T"]))
+    assert np.array_equal(got.numpy(), gs["pos_out"])
+    b, h = engine.build_ddpm(pipeline_cfg["position_ddpm"]["pointnet_config"], common.state_dict("pos"), B, T,
+                             engine.position_table(T, d["beta_0"], d["beta_T"]), 0)
+    upd = [i for i, op in enumerate(b.ops) if op[0] == KIND["SLIDE_OP_DDPM_UPDATE"]][0]
+    m = ir_exec.Machine(b)
+    m.upload(h["x"], draws[0])
+    nz = m.view(h["noise"]).reshape(T, B * 16, 3)
+    for t in range(T - 1, -1, -1):
+        if t > 0:
+            nz[t] = noises[t].reshape(B * 16, 3).numpy()
+        x = m.download(h["x"]).reshape(B, 16, 3)
+        m.upload(h["eps"], model(x, torch.ones(B) * t))
+        m.set_step(t)
+        m.run(upd, 1)
+    assert np.array_equal(m.download(h["x"]).reshape(B, 16, 3).numpy(), gs["pos_out"])
