@@ -129,3 +129,18 @@ def test_against_reference_cuda_extension(ext):
         rd = ref.three_nn(q, x)
         gd = ext.three_nn(q, x)
         assert torch.equal(gd[0], rd[0]) and torch.equal(gd[1], rd[1])
+
+
+def test_sample_farthest_points_p3d_golden():
+    """slide_sample_farthest_points against the vendored pytorch3d reference implementation's golden vectors
+    (tests/golden/make_golden_fps.py): ragged lengths with per-cloud K, duplicated points, clouds shorter than K."""
+    import os
+    import numpy as np
+    slide_b200.install_dropin()
+    from pytorch3d.ops import sample_farthest_points
+    gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_fps.npz")))
+    for name in ("full", "ragged", "dup", "short", "decode"):
+        p = torch.from_numpy(gold[name + "_points"]).cuda()
+        lengths = torch.from_numpy(gold[name + "_lengths"]).cuda()
+        _, idx = sample_farthest_points(p, lengths, [int(k) for k in gold[name + "_K"]])
+        assert np.array_equal(idx.cpu().numpy(), gold[name + "_idx"]), name

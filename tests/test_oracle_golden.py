@@ -101,3 +101,21 @@ def test_schedules_match_reference_formulas(pipeline_cfg):
     assert tab[t, 0] == float(ref_model._extract(sch["sqrt_recip_alphas_cumprod"], tt, 1))
     assert tab[t, 3] == float(ref_model._extract(sch["posterior_mean_coef2"], tt, 1))
     assert tab[t, 4] == float(torch.exp(0.5 * ref_model._extract(sch["logvar"], tt, 1)))
+
+
+FPS_CASES = ["full", "ragged", "dup", "short", "decode"]
+
+
+def _fps_golden():
+    import os
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_fps.npz")))
+
+
+def test_p3d_fps_oracle_matches_vendored_pytorch3d_reference():
+    """golden_fps.npz = pointnet2/data_utils/points_sampling.py::sample_farthest_points_naive (the copy of pytorch3d's
+    reference implementation inside the SLIDE tree) on full / ragged / duplicated / short clouds."""
+    gold = _fps_golden()
+    for name in FPS_CASES:
+        p = torch.from_numpy(gold[name + "_points"])
+        _, idx = ops.sample_farthest_points(p, torch.from_numpy(gold[name + "_lengths"]), list(gold[name + "_K"]))
+        assert np.array_equal(idx.numpy(), gold[name + "_idx"]), name
