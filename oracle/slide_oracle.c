@@ -22,9 +22,11 @@
  * This file must be compiled with -ffp-contract=off so that only the explicit fmaf() calls fuse.
  *
  * Parity status: the _ext ops are pinned against the reference's own kernel source semantics and SASS
- * (and against the reference CUDA build on a GPU box when oracle/_ref exists).  so_knn / so_fps_p3d are
- * "parity unpinned": pytorch3d's source is absent; they restate its published algorithm (brute force,
- * squared L2 accumulated x,y,z with FMA, ascending sort; first-max FPS from a given start index).
+ * (and against the reference CUDA build on a GPU box when oracle/_ref exists).  so_fps_p3d is pinned against
+ * the copy of pytorch3d's reference implementation vendored in the reference tree
+ * (data_utils/points_sampling.py::sample_farthest_points_naive; tests/golden/make_golden_fps.py).  so_knn is
+ * "parity unpinned": pytorch3d's source is absent; it restates the published algorithm (brute force,
+ * squared L2 accumulated x,y,z with FMA, ascending sort).
  */
 #include <math.h>
 #include <stdint.h>
