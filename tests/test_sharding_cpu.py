@@ -57,3 +57,41 @@ def test_all_gather_two_ranks_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert out[0] and out[1]
+
+
+def _gen_worker(rank, world, port, kp_file, save_dir, out):
+    """Two ranks of the generation driver (fake pipelines: no GPU here): each takes its GeneralNpzDataset slice of the
+    keypoint file, writes its rank file, rank 0 merges after a barrier -- the reference's evaluate_per_rank +
+    gather_generated_results flow (mesh_evaluation.py:15-186)."""
+    from slide_b200 import generation
+    from tests.test_generation_cpu import _FakePipe
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kp = generation.load_keypoint_file(kp_file, rank=rank, world_size=world)
+    generation.generate_per_rank(_FakePipe(2), kp["points"], kp["label"], kp["category"], kp["category_name"],
+                                 save_dir=save_dir, rank=rank, world_size=world)
+    dist.barrier()
+    if rank == 0:
+        out["merged"] = generation.gather_generated_results(save_dir, world, num_points=2048)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_generation_driver_two_ranks_gloo(tmp_path):
+    import numpy as np
+    n = 5
+    g = np.random.RandomState(1)
+    kp_file = str(tmp_path / "kp.npz")
+    pts = g.rand(n, 16, 3).astype(np.float32)
+    np.savez(kp_file, points=pts, label=np.arange(n), category=np.array(["c%d" % i for i in range(n)]),
+             category_name=np.array(["n"] * n))
+    save_dir = str(tmp_path / "out")
+    os.makedirs(save_dir)
+    port = 29500 + ((os.getpid() + 7) % 500)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gen_worker, args=(2, port, kp_file, save_dir, out), nprocs=2, join=True)
+    data = np.load(out["merged"])
+    assert os.listdir(save_dir) == ["shapenet_psr_generated_data_2048_pts.npz"]
+    assert np.array_equal(data["keypoint"], pts) and list(data["category"]) == ["c%d" % i for i in range(n)]
+    assert np.array_equal(data["points"][:, :16], pts)  # cloud i was generated from keypoint set i, ranks in order
