@@ -50,6 +50,13 @@ void slide_reset_launch_count(void);
  * No scratch needed: the running distances live in registers. */
 int slide_furthest_point_sampling(const float *xyz, int B, int N, int m, int *idx, slide_stream_t stream);
 
+/* The same op for clouds of any size: N <= slide_fps_resident_max_points() (16384) runs the register-resident
+ * kernel above and ignores `temp`; larger clouds keep their running distances in `temp`, a caller-provided scratch
+ * f32[B,N] -- the reference's own `tmp` tensor (EXT/src/sampling.cpp:74-76; contents need not be initialised). */
+int slide_furthest_point_sampling_ws(const float *xyz, int B, int N, int m, int *idx, float *temp,
+                                     slide_stream_t stream);
+int slide_fps_resident_max_points(void);
+
 /* gather_points(points f32[B,C,N], idx i32[B,m]) -> f32[B,C,m]          EXT/src/sampling.cpp:15-39 */
 int slide_gather_points(const float *points, const int *idx, int B, int C, int N, int m, float *out,
                         slide_stream_t stream);
@@ -102,6 +109,11 @@ int slide_sample_farthest_points(const float *points, int B, int P, int D, const
                                  const int64_t *K, const int64_t *start_idx, int maxK, int64_t *idx,
                                  slide_stream_t stream);
 
+/* As above for P > slide_fps_resident_max_points(): `temp` is a caller-provided scratch f32[B,P]. */
+int slide_sample_farthest_points_ws(const float *points, int B, int P, int D, const int64_t *lengths,
+                                    const int64_t *K, const int64_t *start_idx, int maxK, int64_t *idx, float *temp,
+                                    slide_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused network programs: the denoiser forward (models/pointnet2_with_pcld_condition.py:286-489), the
  * DDPM steps (util.py:197-259, diffusion_utils/diffusion.py:58-95,346-404) and the autoencoder decode
@@ -132,6 +144,11 @@ int slide_program_replay(slide_program *p, int slot, int times, slide_stream_t s
 int slide_program_set_gemm_backend(slide_program *p, int backend);
 /* Non-zero if a tcgen05 pipeline wait ever timed out in this process (a bug guard; results are then invalid). */
 int slide_tc_error(void);
+/* Clear that flag (after the caller has discarded the affected results). */
+void slide_tc_reset_error(void);
+/* Kernel-selection knobs (SLIDE_TC_* / SLIDE_PAIR_* environment variables, for A/B runs and tests) are read once, on
+ * first use; this re-reads them. */
+void slide_tc_reload_tuning(void);
 /* Kernels launched by one pass over ops [first, first+count). */
 int slide_program_launches(slide_program *p, int first, int count);
 

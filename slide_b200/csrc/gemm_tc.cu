@@ -1264,47 +1264,74 @@ static bool make_a_map(const GemmArgs &a, CUtensorMap *m, bool raw = false) {
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Tuning knobs (A/B runs and the tests that force the persistent kernel onto small problems).  The environment is
+// read ONCE, on first use; slide_tc_reload_tuning() re-reads it (tests call it after changing a variable).
+struct TcTuning {
+  int use_tma, persist, persist_min_tiles, persist_min_k, persist_min_bn, persist_grid, prepass, debug;
+};
+static TcTuning g_tuning;
+static bool g_tuning_loaded = false;
+static void load_tuning() {
+  g_tuning.use_tma = env_int("SLIDE_TC_TMA", 1);
+  // persistent kernel: 0 = never, 1 = TMA-fed operands only, 2 = also with transform producers / fused soft-max
+  g_tuning.persist = env_int("SLIDE_TC_PERSIST", 2);
+  g_tuning.persist_min_tiles = env_int("SLIDE_TC_PERSIST_MIN_TILES", 148);
+  g_tuning.persist_min_k = env_int("SLIDE_TC_PERSIST_MIN_K", 32);
+  g_tuning.persist_min_bn = env_int("SLIDE_TC_PERSIST_MIN_BN", 128);
+  g_tuning.persist_grid = env_int("SLIDE_TC_PERSIST_GRID", 0);  // 0 = one CTA per SM of the current device
+  g_tuning.prepass = env_int("SLIDE_TC_PREPASS", 1);
+  g_tuning.debug = env_int("SLIDE_TC_DEBUG", 0);
+  g_tuning_loaded = true;
+}
+static inline const TcTuning &tuning() {
+  if (!g_tuning_loaded) load_tuning();
+  return g_tuning;
+}
+void tc_reload_tuning() { load_tuning(); }
+
+// Per-DEVICE caches (one process may drive several GPUs): SM count and "dynamic shared memory limit raised" flags.
+constexpr int MAX_DEVICES = 64;
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0;
+  return dev;
+}
+static int sm_count() {
+  static int n[MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
+
 template <int BN, int STAGES, bool SMK, bool TMA_A>
 static int launch_tc_impl(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st, const CUtensorMap &tm) {
   const int stride = tc_table_stride(a);
   const int rows = has_xf(a.xfa) ? tc_rows_per_tile(a.xfa.R) : 0;
   const int total = tc_stages_bytes(BN, STAGES) + rows * stride * 16 + TC_CTRL_BYTES + 1024 /* alignment slack */;
   if (total > TC_MAX_DYN_SMEM) return SLIDE_ERR_UNSUPPORTED;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[MAX_DEVICES] = {false};  // function attributes are per device
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, SMK, TMA_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TC_MAX_DYN_SMEM);
     if (e != cudaSuccess) return cuda_rc(e);
-    configured = true;
+    configured[dev] = true;
   }
   dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, TBM));
   if (grid.y > 65535) return SLIDE_ERR_UNSUPPORTED;
-  static int dbg = -1;
-  if (dbg < 0) {
-    const char *e = getenv("SLIDE_TC_DEBUG");
-    dbg = e ? atoi(e) : 0;
-  }
+  const int dbg = tuning().debug;
   gemm_tc_kernel<BN, STAGES, SMK, TMA_A><<<grid, TC_THREADS, total, st>>>(a, Wp, wp_na, stride, rows, dbg, tm);
   return after_launch();
 }
 
 constexpr int TCP_NOT_APPLICABLE = 1;  // internal: take the one-tile-per-CTA kernel instead
-
-static int env_int(const char *name, int dflt) {
-  const char *e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        n <= 0)
-      n = 148;
-  }
-  return n;
-}
 
 template <int BN, bool XFA, bool SMK>
 static int launch_tcp(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st, const CUtensorMap &tm) {
@@ -1312,15 +1339,16 @@ static int launch_tcp(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_
   const int stride = XFA ? tc_table_stride(a) : 0;
   const int total = tcp_smem_bytes(BN, PSTAGES) + (XFA ? XF_MAXG * 8 + stride * 16 : 0) + 1024 /* alignment slack */;
   if (total > TC_MAX_DYN_SMEM) return TCP_NOT_APPLICABLE;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[MAX_DEVICES] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<BN, PSTAGES, XFA, SMK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM);
     if (e != cudaSuccess) return cuda_rc(e);
-    configured = true;
+    configured[dev] = true;
   }
   const int tiles = (a.M / TBM) * ceil_div(a.N, BN);
-  const int max_grid = env_int("SLIDE_TC_PERSIST_GRID", sm_count());  // tests shrink it: many tiles per CTA
+  const int max_grid = tuning().persist_grid > 0 ? tuning().persist_grid : sm_count();  // tests shrink it: many tiles per CTA
   const int grid = tiles < max_grid ? tiles : max_grid;
   gemm_tcp_kernel<BN, PSTAGES, XFA, SMK><<<grid, XFA ? TCP_XFA_THREADS : TCP_THREADS, total, st>>>(a, Wp, wp_na, stride, tm);
   return after_launch();
@@ -1328,11 +1356,9 @@ static int launch_tcp(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_
 
 template <int BN, int STAGES>
 static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t st) {
-  static const int use_tma = env_int("SLIDE_TC_TMA", 1);
-  // persistent kernel: 0 = never, 1 = TMA-fed operands only, 2 = also with transform producers / fused soft-max
-  const int persist = env_int("SLIDE_TC_PERSIST", 2);  // read per launch: tests flip these
-  const int persist_min_tiles = env_int("SLIDE_TC_PERSIST_MIN_TILES", 148);
-  const int persist_min_k = env_int("SLIDE_TC_PERSIST_MIN_K", 32);
+  const TcTuning &tn = tuning();
+  const int use_tma = tn.use_tma, persist = tn.persist, persist_min_tiles = tn.persist_min_tiles,
+            persist_min_k = tn.persist_min_k;
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   // every row tile inside one sample, whole row tiles, 8-row blocks inside one ev row
@@ -1351,7 +1377,7 @@ static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t
     // A/B on B200 after the per-tile statistics reduction (feature / position DDPM step, us): min K 256: 1702 / 861,
     // 64: 1703 / 835, 32: 1677 / 836; narrower tiles (BN < 128) gain nothing.  (Before that change short K loops were
     // epilogue-bound and the persistent kernel lost: K=60 N=256 60 -> 85 us.)
-    if (persist >= 1 && one_sample && tiles >= persist_min_tiles && BN >= env_int("SLIDE_TC_PERSIST_MIN_BN", 128) &&
+    if (persist >= 1 && one_sample && tiles >= persist_min_tiles && BN >= tn.persist_min_bn &&
         a.K >= persist_min_k) {
       const int rc = launch_tcp<BN, false, false>(a, Wp, wp_na, st, tm);
       if (rc != TCP_NOT_APPLICABLE) return rc;
@@ -1414,7 +1440,7 @@ static GemmArgs prepass_args(const GemmArgs &a, float *scratch) {
 }
 
 bool gemm_tc_prepass_applicable(const GemmArgs &a) {
-  if (env_int("SLIDE_TC_PREPASS", 1) == 0) return false;
+  if (tuning().prepass == 0) return false;
   // A/B on B200 (M = 4096): K = 256 55 -> 25 us; K <= 128 18 -> 22 us (the extra launch costs more than it saves)
   if (a.K <= 128) return false;
   if (!has_xf(a.xfa) || a.xfa.R % TBM == 0 || TBM % a.xfa.R != 0 || TBM / a.xfa.R > XF_MAXS) return false;
@@ -1486,6 +1512,11 @@ int tc_error_flag() {
   int v = 0;
   cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int));
   return v;
+}
+
+void tc_error_reset() {
+  const int z = 0;
+  cudaMemcpyToSymbol(g_tc_error, &z, sizeof(int));
 }
 
 }  // namespace slide

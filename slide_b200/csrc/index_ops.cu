@@ -29,6 +29,8 @@ namespace slide {
 // MODE 1: pytorch3d semantics (start index given, init +inf, lowest index wins ties, i64 output, -1 pad).
 // MODE 2: MODE 1 with i32 start indices / output and no per-cloud lengths (used inside slide programs).
 // `ldx` is the row stride of xyz in floats (3 for a packed cloud).
+constexpr int FPS_MAX_RESIDENT_N = 16384;  // 1024 threads x 16 points in registers
+
 template <int PPT, int MODE>
 __global__ void __launch_bounds__(1024) fps_kernel(const float *__restrict__ xyz, int ldx, int N, int m, int s_log2,
                                                    int nb_log2, const int64_t *__restrict__ lengths,
@@ -136,6 +138,90 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float *__restrict__ xyz
   }
 }
 
+// Clouds too large for the register-resident kernel (N > 16384): same chain, same tie rule, with the running
+// distances in a caller-provided scratch `temp` f32[B,N] (the reference's own `tmp` tensor, sampling.cpp:74-76) and the
+// points re-read through L1/L2 every round.  Latency-bound like the reference's kernel, but with 1024 threads per cloud,
+// REDUX reductions and one barrier per round.
+template <int MODE>
+__global__ void __launch_bounds__(1024) fps_global_kernel(const float *__restrict__ xyz, int N, int m, int s_log2,
+                                                          int nb_log2, const int64_t *__restrict__ lengths,
+                                                          const int64_t *__restrict__ Ks,
+                                                          const int64_t *__restrict__ start_idx,
+                                                          float *__restrict__ temp, void *out_raw) {
+  __shared__ uint2 slots[2][32];
+  const int b = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const float *p = xyz + (size_t)b * N * 3;
+  float *md = temp + (size_t)b * N;
+  int len = N, kn = m;
+  if (MODE == 1) {
+    if (lengths) len = (int)lengths[b];
+    if (Ks) kn = (int)Ks[b];
+    if (kn > len) kn = len;
+    if (kn > m) kn = m;
+  }
+  for (int k = tid; k < len; k += T) md[k] = MODE == 0 ? 1e10f : INFINITY;
+  int old = 0;
+  if (MODE == 1 && start_idx) old = (int)start_idx[b];
+  int *out32 = (int *)out_raw + (size_t)b * m;
+  long long *out64 = (long long *)out_raw + (size_t)b * m;
+  if (tid == 0) {
+    if (MODE == 0) {
+      if (m > 0) out32[0] = 0;
+    } else {
+      for (int j = kn > 0 ? kn : 0; j < m; ++j) out64[j] = -1;
+      if (kn > 0) out64[0] = old;
+    }
+  }
+  for (int j = 1; j < kn; ++j) {
+    const float x1 = __ldg(p + (size_t)old * 3 + 0), y1 = __ldg(p + (size_t)old * 3 + 1), z1 = __ldg(p + (size_t)old * 3 + 2);
+    uint32_t bhi = 0, brk = 0xffffffffu;
+    for (int k = tid; k < len; k += T) {
+      const float x = __ldg(p + (size_t)k * 3 + 0), y = __ldg(p + (size_t)k * 3 + 1), z = __ldg(p + (size_t)k * 3 + 2);
+      float d;
+      uint32_t rk;
+      if (MODE == 0) {
+        if ((double)sumsq3_ref(x, y, z) <= 1e-3) continue;
+        d = sumsq3_ref(x - x1, y - y1, z - z1);
+        const uint32_t lo = (uint32_t)k & ((1u << s_log2) - 1u);
+        rk = ((s_log2 ? (__brev(lo) >> (32 - s_log2)) : 0u) << nb_log2) | ((uint32_t)k >> s_log2);
+      } else {
+        d = sumsq3_p3d(x1 - x, y1 - y, z1 - z);
+        rk = (uint32_t)k;
+      }
+      const float v = fminf(d, md[k]);
+      md[k] = v;
+      const uint32_t hi = __float_as_uint(v) + 1u;
+      if (hi > bhi || (hi == bhi && rk < brk)) {
+        bhi = hi;
+        brk = rk;
+      }
+    }
+    uint32_t mx = __reduce_max_sync(0xffffffffu, bhi);
+    uint32_t mr = __reduce_min_sync(0xffffffffu, bhi == mx ? brk : 0xffffffffu);
+    if (lane == 0) slots[j & 1][warp] = make_uint2(mx, mr);
+    __syncthreads();
+    uint2 sl = lane < nwarps ? slots[j & 1][lane] : make_uint2(0u, 0xffffffffu);
+    mx = __reduce_max_sync(0xffffffffu, sl.x);
+    mr = __reduce_min_sync(0xffffffffu, sl.x == mx ? sl.y : 0xffffffffu);
+    if (mx == 0u) {
+      old = 0;
+    } else if (MODE == 0) {
+      const uint32_t rev = mr >> nb_log2;
+      const uint32_t lo = s_log2 ? (__brev(rev) >> (32 - s_log2)) : 0u;
+      old = (int)((((mr & ((1u << nb_log2) - 1u))) << s_log2) | lo);
+    } else {
+      old = (int)mr;
+    }
+    if (tid == 0) {
+      if (MODE == 1)
+        out64[j] = old;
+      else
+        out32[j] = old;
+    }
+  }
+}
+
 static int host_opt_n_threads(int work_size) {
   // EXT/include/cuda_utils.h:15-19 (double-precision log, truncation) -- decides the reference's tie rule.
   const int pow_2 = (int)(log((double)work_size) / log(2.0));
@@ -155,7 +241,7 @@ template <int MODE>
 static int launch_fps(const float *xyz, int ldx, int B, int N, int m, const int64_t *lengths, const int64_t *Ks,
                       const void *start, void *out, cudaStream_t st) {
   if (B == 0 || m == 0) return SLIDE_OK;
-  if (N > 16384) return SLIDE_ERR_UNSUPPORTED;
+  if (N > FPS_MAX_RESIDENT_N) return SLIDE_ERR_UNSUPPORTED;  // use the *_ws entry points (scratch-backed kernel)
   int T = ((N + 31) / 32) * 32;
   if (T > 1024) T = 1024;
   const int ppt = ceil_div(N, T);
@@ -435,6 +521,19 @@ __global__ void __launch_bounds__(128) knn_kernel(const float *__restrict__ p1, 
 }
 
 // entry points for the program executor (program.cu)
+template <int MODE>
+static int launch_fps_global(const float *xyz, int B, int N, int m, const int64_t *lengths, const int64_t *Ks,
+                             const int64_t *start, float *temp, void *out, cudaStream_t st) {
+  if (B == 0 || m == 0) return SLIDE_OK;
+  if (!temp) return SLIDE_ERR_INVALID;
+  const int S = host_opt_n_threads(N);
+  const int s_log2 = ilog2_ceil(S);
+  const int nb_log2 = ilog2_ceil(ceil_div(N, S));
+  if (s_log2 + nb_log2 > 31) return SLIDE_ERR_UNSUPPORTED;
+  fps_global_kernel<MODE><<<B, 1024, 0, st>>>(xyz, N, m, s_log2, nb_log2, lengths, Ks, start, temp, out);
+  return after_launch();
+}
+
 int program_fps(int mode, const float *xyz, int ldx, int B, int N, int m, const int *start, int *out, cudaStream_t st) {
   if (mode == 0) return launch_fps<0>(xyz, ldx, B, N, m, nullptr, nullptr, nullptr, out, st);
   return launch_fps<2>(xyz, ldx, B, N, m, nullptr, nullptr, start, out, st);
@@ -467,6 +566,25 @@ int slide_sample_farthest_points(const float *points, int B, int P, int D, const
   if (D != 3) return SLIDE_ERR_UNSUPPORTED;
   return launch_fps<1>(points, 3, B, P, maxK, lengths, K, start_idx, idx, (cudaStream_t)stream);
 }
+
+int slide_furthest_point_sampling_ws(const float *xyz, int B, int N, int m, int *idx, float *temp,
+                                     slide_stream_t stream) {
+  if (!xyz || !idx || B < 0 || N <= 0 || m < 0) return SLIDE_ERR_INVALID;
+  if (N <= FPS_MAX_RESIDENT_N) return launch_fps<0>(xyz, 3, B, N, m, nullptr, nullptr, nullptr, idx, (cudaStream_t)stream);
+  return launch_fps_global<0>(xyz, B, N, m, nullptr, nullptr, nullptr, temp, idx, (cudaStream_t)stream);
+}
+
+int slide_sample_farthest_points_ws(const float *points, int B, int P, int D, const int64_t *lengths,
+                                    const int64_t *K, const int64_t *start_idx, int maxK, int64_t *idx, float *temp,
+                                    slide_stream_t stream) {
+  if (!points || !idx || B < 0 || P <= 0 || maxK < 0) return SLIDE_ERR_INVALID;
+  if (D != 3) return SLIDE_ERR_UNSUPPORTED;
+  if (P <= FPS_MAX_RESIDENT_N)
+    return launch_fps<1>(points, 3, B, P, maxK, lengths, K, start_idx, idx, (cudaStream_t)stream);
+  return launch_fps_global<1>(points, B, P, maxK, lengths, K, start_idx, temp, idx, (cudaStream_t)stream);
+}
+
+int slide_fps_resident_max_points(void) { return FPS_MAX_RESIDENT_N; }
 
 int slide_gather_points(const float *points, const int *idx, int B, int C, int N, int m, float *out,
                         slide_stream_t stream) {

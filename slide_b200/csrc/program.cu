@@ -618,6 +618,10 @@ struct slide_program {
 
 namespace {
 
+// PAIR launch-shape knobs: environment read once (slide_tc_reload_tuning() re-reads)
+bool g_pair_tuning_loaded = false;
+int g_pair_min_ctas = 2368, g_pair_min_rows = 32;
+
 template <typename T>
 inline T *AP(slide_program *p, int64_t off) {
   return off < 0 ? nullptr : reinterpret_cast<T *>(p->arena + off);
@@ -826,9 +830,14 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       if (a.res && a.xfr.stats && a.xfr.R != a.np * a.K) return SLIDE_ERR_UNSUPPORTED;
       // points per CTA: aim for >= 16 CTAs per SM overall, at least 32 rows per CTA
       int pb = a.np;
-      static const char *e_ctas = getenv("SLIDE_PAIR_MIN_CTAS"), *e_rows = getenv("SLIDE_PAIR_MIN_ROWS");
       // A/B on B200 (feature-DDPM step): (592 CTAs, 64 rows) 1764 us, (2368, 32) 1750 us, (4736, 16) 1784 us
-      const int min_ctas = e_ctas ? atoi(e_ctas) : 2368, min_rows = e_rows ? atoi(e_rows) : 32;
+      if (!g_pair_tuning_loaded) {
+        const char *e_ctas = getenv("SLIDE_PAIR_MIN_CTAS"), *e_rows = getenv("SLIDE_PAIR_MIN_ROWS");
+        g_pair_min_ctas = e_ctas ? atoi(e_ctas) : 2368;
+        g_pair_min_rows = e_rows ? atoi(e_rows) : 32;
+        g_pair_tuning_loaded = true;
+      }
+      const int min_ctas = g_pair_min_ctas, min_rows = g_pair_min_rows;
       while (pb > 1 && (long long)B * ceil_div(a.np, pb) < min_ctas && pb * a.K > min_rows) pb = (pb + 1) / 2;
       a.pb = pb;
       if (((uintptr_t)a.U & 15) || (a.ldu & 3) || ((uintptr_t)a.out & 15) || (a.ldo & 3) ||
@@ -1015,6 +1024,11 @@ int slide_program_replay(slide_program *p, int slot, int times, slide_stream_t s
 }
 
 int slide_tc_error(void) { return tc_error_flag(); }
+void slide_tc_reset_error(void) { tc_error_reset(); }
+void slide_tc_reload_tuning(void) {
+  tc_reload_tuning();
+  g_pair_tuning_loaded = false;
+}
 
 int slide_program_launches(slide_program *p, int first, int count) {
   if (!p || first < 0 || count < 0 || (size_t)(first + count) > p->ops.size()) return SLIDE_ERR_INVALID;

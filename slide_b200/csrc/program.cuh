@@ -91,6 +91,8 @@ bool gemm_tc_prepass_applicable(const GemmArgs &a);
 size_t gemm_tc_prepass_bytes(int M, int K);
 int launch_gemm_tc_prepass(const GemmArgs &a, const float *Wp, int wp_na, float *scratch, cudaStream_t st);
 int tc_error_flag();
+void tc_error_reset();
+void tc_reload_tuning();
 int program_fps(int mode, const float *xyz, int ldx, int B, int N, int m, const int *start, int *out, cudaStream_t st);
 
 }  // namespace slide

@@ -59,9 +59,13 @@ def furthest_point_sampling(points, nsamples):
     _contig(points, "points"); _float(points, "points"); _cuda(points)
     B, N, _ = points.shape
     out = torch.zeros(B, nsamples, device=points.device, dtype=torch.int32)
+    lib = _l.load()
+    # clouds beyond the register-resident kernel's capacity keep their running distances in a scratch tensor, like the
+    # reference's `tmp` (sampling.cpp:74-76)
+    tmp = torch.empty(B, N, device=points.device) if N > lib.slide_fps_resident_max_points() else None
     with torch.cuda.device(points.device):
-        _l.check(_l.load().slide_furthest_point_sampling(_l.ptr(points), B, N, int(nsamples), _l.ptr(out),
-                                                         _l.stream_of(points)), "furthest_point_sampling")
+        _l.check(lib.slide_furthest_point_sampling_ws(_l.ptr(points), B, N, int(nsamples), _l.ptr(out), _l.ptr(tmp),
+                                                      _l.stream_of(points)), "furthest_point_sampling")
     return out
 
 

@@ -31,7 +31,37 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, norm=2, K=1, version=-1, re
         _l.check(_l.load().slide_knn_points(_l.ptr(p1c), _l.ptr(p2c), B, P1, P2, D, _l.ptr(l1), _l.ptr(l2), int(K),
                                             _l.ptr(dists), _l.ptr(idx), _l.stream_of(p1c)), "knn_points")
     nn = knn_gather(p2, idx, lengths2) if return_nn else None
+    if torch.is_grad_enabled() and (p1.requires_grad or p2.requires_grad):
+        # pytorch3d's knn_points is differentiable w.r.t. p1 / p2 through dists (group_knn feeds d2 and 1/(d2+1e-8)
+        # into the features, pointnet2_utils.py:506-517).  The kernel's distances carry no graph, so the backward is
+        # attached here: grad_p1 = 2 (p1 - p2[idx]) g, grad_p2 = scatter of -2 (p1 - p2[idx]) g; forward values stay
+        # the kernel's (bit-exact with the no-grad path).
+        dists = _KnnDists.apply(p1, p2, idx, dists, l2)
     return _KNN(dists=dists, idx=idx, knn=nn)
+
+
+class _KnnDists(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p1, p2, idx, dists, lengths2):
+        ctx.save_for_backward(p1, p2, idx)
+        ctx.lengths2 = lengths2
+        return dists.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        p1, p2, idx = ctx.saved_tensors
+        N, P1, K = idx.shape
+        D = p1.shape[2]
+        if ctx.lengths2 is not None:  # padded neighbour slots (k >= lengths2) carry no gradient
+            g = g * (torch.arange(K, device=g.device)[None, None, :] < ctx.lengths2[:, None, None]).to(g.dtype)
+        nb = p2[:, :, None].expand(-1, -1, K, -1).gather(1, idx[:, :, :, None].expand(-1, -1, -1, D))
+        diff = 2.0 * (p1[:, :, None, :] - nb) * g[:, :, :, None]            # (N,P1,K,D)
+        g1 = diff.sum(2) if ctx.needs_input_grad[0] else None
+        g2 = None
+        if ctx.needs_input_grad[1]:
+            g2 = torch.zeros_like(p2).scatter_add_(1, idx.reshape(N, P1 * K, 1).expand(-1, -1, D),
+                                                   (-diff).reshape(N, P1 * K, D))
+        return g1, g2, None, None, None
 
 
 def knn_gather(x, idx, lengths=None):

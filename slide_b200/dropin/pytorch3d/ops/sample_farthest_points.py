@@ -36,8 +36,10 @@ def sample_farthest_points(points, lengths=None, K=50, random_start_point=False)
         start_dev = start.to(device)
     pts = points.contiguous().float()
     idx = torch.empty(N, maxK, device=device, dtype=torch.int64)
+    lib = _l.load()
+    tmp = torch.empty(N, P, device=device) if P > lib.slide_fps_resident_max_points() else None  # large clouds only
     with torch.cuda.device(device):
-        _l.check(_l.load().slide_sample_farthest_points(_l.ptr(pts), N, P, D, _l.ptr(lengths_dev), _l.ptr(K_dev),
-                                                        _l.ptr(start_dev), int(maxK), _l.ptr(idx),
-                                                        _l.stream_of(pts)), "sample_farthest_points")
+        _l.check(lib.slide_sample_farthest_points_ws(_l.ptr(pts), N, P, D, _l.ptr(lengths_dev), _l.ptr(K_dev),
+                                                     _l.ptr(start_dev), int(maxK), _l.ptr(idx), _l.ptr(tmp),
+                                                     _l.stream_of(pts)), "sample_farthest_points")
     return masked_gather(points, idx), idx

@@ -86,13 +86,14 @@ def generate_per_rank(pipe, keypoints, label, category=None, category_name=None,
             else t[b0:b0 + m]
         start = time.time()
         # the host draws of one batch, in the reference's order (x_T, then the decoder's FPS start indices); the
-        # position-DDPM draws are not consumed on this path
-        pipe.draw_host_inputs(pad(label))
+        # reference never draws position-DDPM noise on this path (diffusion.py:373 is its first draw), so neither do we
+        pipe.draw_host_inputs(pad(label), skip_position=True)
         pipe.stage_inputs()
         out = pipe.sample_resident(keypoints=pad(keypoints).to(pipe.device),
                                    complete_x0=None if complete_x0 is None else pad(complete_x0),
                                    keypoint_mask=None if keypoint_mask is None else pad(keypoint_mask))
         host = out[:m].cpu()
+        pipe.check_device_errors()
         timing.extend([(time.time() - start) / m] * m)
         clouds.append(host.numpy())
         feats.append(pipe.keypoint_feature[:m].cpu().numpy())

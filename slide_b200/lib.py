@@ -20,9 +20,10 @@ SYMBOLS = [
     "slide_furthest_point_sampling", "slide_gather_points", "slide_gather_points_grad", "slide_ball_query",
     "slide_group_points", "slide_group_points_grad", "slide_three_nn", "slide_three_interpolate",
     "slide_three_interpolate_grad", "slide_knn_points", "slide_sample_farthest_points",
+    "slide_furthest_point_sampling_ws", "slide_sample_farthest_points_ws", "slide_fps_resident_max_points",
     "slide_program_create", "slide_program_destroy", "slide_program_arena", "slide_program_weights",
     "slide_program_run", "slide_program_capture", "slide_program_replay", "slide_program_launches",
-    "slide_program_set_gemm_backend", "slide_tc_error",
+    "slide_program_set_gemm_backend", "slide_tc_error", "slide_tc_reset_error", "slide_tc_reload_tuning",
 ]
 
 

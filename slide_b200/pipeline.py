@@ -63,8 +63,11 @@ class DDPMSampler(object):
         first, count = self.builder.segments["step"]
         self.prog.set_step(self.T)
         if not self._captured:
-            # one eager step first: configures kernel attributes outside of stream capture
+            # one eager step first (configures kernel attributes outside of stream capture).  The step is NOT a no-op --
+            # it updates x in place and moves the step counter -- so the live state is snapshotted and restored.
+            x_live = self.prog.download(self.h["x"])
             self.prog.run(first, count)
+            self.prog.upload(self.h["x"], x_live)
             self.prog.set_step(self.T)
             self.prog.capture(0, first, count, repeat=self.graph_steps)
             self._captured = True
@@ -200,13 +203,19 @@ class SlidePipeline(object):
         self._out_host = torch.empty(self.Bl, self.dec.out_points, self.dec.out_dim).pin_memory()
 
     # ---- host-side RNG in the reference's call order (full batch, then this rank's slice) -------------------
-    def draw_host_inputs(self, labels):
+    def draw_host_inputs(self, labels, skip_position=False):
         """labels: CPU int tensor (global_batch,).  Draws, on the CPU default generator and in the reference's
-        order, everything the reference draws on the host; stores this rank's slices in pinned buffers."""
+        order, everything the reference draws on the host; stores this rank's slices in pinned buffers.
+        skip_position: external keypoints -- the reference's latent_ddpm_keypoint_conditional_generation never draws
+        position noise, so neither the position x_T nor its T noise tensors are drawn (the generator then advances
+        exactly as in the reference: x_T of the latent DDPM, then the decoder's FPS start indices)."""
         d = draw_host_inputs(self.cfg, self.B, self.rank, self.world, labels,
-                             fast_steps=None if self.position_sampler is None else self.T_pos)
-        self._pos_noise_host.view(self.T_pos, self.Bl, 16, 3).copy_(d["pos_noise"])
-        self._pos_xT_host.copy_(d["pos_xT"])
+                             fast_steps=None if self.position_sampler is None else self.T_pos,
+                             skip_position=skip_position)
+        self._skip_position = skip_position
+        if not skip_position:
+            self._pos_noise_host.view(self.T_pos, self.Bl, 16, 3).copy_(d["pos_noise"])
+            self._pos_xT_host.copy_(d["pos_xT"])
         self._lat_xT_host.copy_(d["lat_xT"])
         self._labels_host.copy_(d["labels"])
         self._starts_host.copy_(d["starts"])
@@ -220,8 +229,9 @@ class SlidePipeline(object):
             self.pos.set_labels(labels)
             self.lat.set_labels(labels)
             self._labels = labels
-        self.pos.noise_view().copy_(self._pos_noise_host, non_blocking=True)
-        self._pos_xT_dev = self._pos_xT_host.to(dev, non_blocking=True)
+        if not getattr(self, "_skip_position", False):
+            self.pos.noise_view().copy_(self._pos_noise_host, non_blocking=True)
+            self._pos_xT_dev = self._pos_xT_host.to(dev, non_blocking=True)
         self._lat_xT_dev = self._lat_xT_host.to(dev, non_blocking=True)
         self._starts_dev = self._starts_host.to(dev, non_blocking=True)
 
@@ -276,7 +286,14 @@ class SlidePipeline(object):
         out = self.sample()
         self._out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        self.check_device_errors()
         return self._out_host
+
+    def check_device_errors(self):
+        """Raise if a tcgen05 pipeline wait timed out (sticky device flag): the clouds would be garbage."""
+        from . import lib
+        if lib.load().slide_tc_error() != 0:
+            raise lib.SlideError("a tcgen05 GEMM pipeline timed out on the device (slide_tc_error != 0): results invalid")
 
     def h2d_bytes(self):
         return (self._pos_noise_host.numel() + self._pos_xT_host.numel() + self._lat_xT_host.numel()) * 4 + \
@@ -293,7 +310,7 @@ class SlidePipeline(object):
                 (self.Bl // self.dec.chunk) * self.dec.launches_per_chunk())
 
 
-def draw_host_inputs(cfg, B, rank, world, labels, fast_steps=None):
+def draw_host_inputs(cfg, B, rank, world, labels, fast_steps=None, skip_position=False):
     """Everything the reference draws on the CPU generator, for the FULL batch and in the reference's call order,
     sliced to rank `rank` of `world` (so results do not depend on the world size):
       pos_xT (Bl,16,3), pos_noise (T,Bl,16,3) with pos_noise[t] = the z added after step t (util.py:225,253),
@@ -305,16 +322,19 @@ def draw_host_inputs(cfg, B, rank, world, labels, fast_steps=None):
     T = cfg["position_ddpm"]["diffusion_config"]["T"] if fast_steps is None else fast_steps + 1
     C_lat = 3 + cfg["latent_ddpm"]["pointnet_config"]["in_fea_dim"]
     size = (B, 16, 3)
-    if (B * 48) % 16 == 0:
-        big = torch.normal(0, 1, size=(T,) + size)  # == T sequential torch.normal(0,1,size) calls (chunks of 16)
-    else:
-        big = torch.stack([torch.normal(0, 1, size=size) for _ in range(T)])
-    # big[0] = x_T; big[1+i] = z added after step t = T-1-i (i = 0..T-2)
-    if fast_steps is None:
-        pos_noise = torch.zeros(T, Bl, 16, 3)
-        pos_noise[1:] = torch.flip(big[1:, lo:hi], dims=[0])
-    else:
-        pos_noise = torch.flip(big[1:, lo:hi], dims=[0]).contiguous()
+    pos_xT = pos_noise = None
+    if not skip_position:
+        if (B * 48) % 16 == 0:
+            big = torch.normal(0, 1, size=(T,) + size)  # == T sequential torch.normal(0,1,size) calls (chunks of 16)
+        else:
+            big = torch.stack([torch.normal(0, 1, size=size) for _ in range(T)])
+        # big[0] = x_T; big[1+i] = z added after step t = T-1-i (i = 0..T-2)
+        if fast_steps is None:
+            pos_noise = torch.zeros(T, Bl, 16, 3)
+            pos_noise[1:] = torch.flip(big[1:, lo:hi], dims=[0])
+        else:
+            pos_noise = torch.flip(big[1:, lo:hi], dims=[0]).contiguous()
+        pos_xT = big[0, lo:hi].clone()
     lat_xT = torch.randn(B, 16, C_lat)[lo:hi].clone()
     decs = cfg["autoencoder"]["decoders"]
     starts = torch.zeros(len(decs), Bl, dtype=torch.int64)
@@ -327,7 +347,7 @@ def draw_host_inputs(cfg, B, rank, world, labels, fast_steps=None):
             draws = torch.tensor([int(torch.randint(high=P, size=(1,)).item()) for _ in range(B)])
             starts[lvl] = draws[lo:hi]
         n_in = up["num_output_points"]
-    return {"pos_xT": big[0, lo:hi].clone(), "pos_noise": pos_noise, "lat_xT": lat_xT, "starts": starts,
+    return {"pos_xT": pos_xT, "pos_noise": pos_noise, "lat_xT": lat_xT, "starts": starts,
             "labels": labels[lo:hi].clone()}
 
 

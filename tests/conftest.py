@@ -32,3 +32,18 @@ def golden():
 def pipeline_cfg():
     from slide_b200 import weights
     return weights.load_json("pipeline_airplane.json")
+
+
+@pytest.fixture(autouse=True)
+def _default_kernel_tuning(request):
+    """libslide_b200.so reads its SLIDE_TC_* / SLIDE_PAIR_* knobs once; GPU tests that override them (monkeypatch) call
+    slide_tc_reload_tuning() themselves -- this restores the default dispatch for whatever test runs next."""
+    yield
+    if "gpu" in request.keywords:
+        import torch
+        if torch.cuda.is_available():
+            from slide_b200 import lib
+            os.environ.pop("SLIDE_TC_PERSIST_MIN_TILES", None)
+            os.environ.pop("SLIDE_TC_PERSIST_MIN_K", None)
+            os.environ.pop("SLIDE_TC_PERSIST_GRID", None)
+            lib.load().slide_tc_reload_tuning()

@@ -56,6 +56,7 @@ def test_records_teacher_forced(which, backend, B, pipeline_cfg, monkeypatch):
         monkeypatch.setenv("SLIDE_TC_PERSIST_MIN_K", "32")
         monkeypatch.setenv("SLIDE_TC_PERSIST_GRID", "3")
         backend = "auto"
+    lib.load().slide_tc_reload_tuning()  # the library reads its knobs once; pick up (or drop) the overrides
     b, h, pc, sd = common.ddpm_program(pipeline_cfg, which, B, with_noise=True, T=4)
     m = ir_exec.Machine(b)
     labels = np.arange(B) % 13

@@ -95,3 +95,26 @@ def test_generation_driver_two_ranks_gloo(tmp_path):
     assert os.listdir(save_dir) == ["shapenet_psr_generated_data_2048_pts.npz"]
     assert np.array_equal(data["keypoint"], pts) and list(data["category"]) == ["c%d" % i for i in range(n)]
     assert np.array_equal(data["points"][:, :16], pts)  # cloud i was generated from keypoint set i, ranks in order
+
+
+def test_external_keypoint_draws_follow_reference_rng_order():
+    """latent_ddpm_keypoint_conditional_generation never draws position noise: its first CPU draw is the latent x_T
+    (diffusion_utils/diffusion.py:373), then the decoder's FPS start indices.  skip_position reproduces exactly that
+    generator sequence (the unused position draws used to advance the generator)."""
+    cfg = weights.load_json("pipeline_airplane.json")
+    B = 4
+    labels = torch.zeros(B, dtype=torch.long)
+    torch.manual_seed(123)
+    d = pipeline.draw_host_inputs(cfg, B, 0, 1, labels, skip_position=True)
+    torch.manual_seed(123)
+    want_xT = torch.randn(B, 16, 3 + cfg["latent_ddpm"]["pointnet_config"]["in_fea_dim"])
+    assert torch.equal(d["lat_xT"], want_xT)
+    assert d["pos_xT"] is None and d["pos_noise"] is None
+    n_in = 16
+    for lvl, dcfg in enumerate(cfg["autoencoder"]["decoders"]):
+        up = dcfg["upsampling_setting"]
+        P = n_in * up["point_upsample_factor"]
+        if P > up["num_output_points"]:
+            want = torch.tensor([int(torch.randint(high=P, size=(1,)).item()) for _ in range(B)])
+            assert torch.equal(d["starts"][lvl], want)
+        n_in = up["num_output_points"]
