@@ -149,6 +149,17 @@ void slide_tc_reset_error(void);
 /* Kernel-selection knobs (SLIDE_TC_* / SLIDE_PAIR_* environment variables, for A/B runs and tests) are read once, on
  * first use; this re-reads them. */
 void slide_tc_reload_tuning(void);
+/* Sample-resident execution of a record range (slide_resident.h): `plan` / `rops` are HOST arrays produced by the host
+ * side's compiler (slide_b200/resident.py) for ops [plan->first, plan->first + plan->count); they are copied.  From then
+ * on slide_program_run / _capture over exactly that range launch ONE kernel (one thread-block cluster per sample,
+ * activations resident in shared memory) instead of one kernel per record -- while the GEMM backend is 0 and resident
+ * execution is enabled (slide_program_use_resident, env SLIDE_RESIDENT=0 disables at creation).  The packed weight
+ * copies the plan refers to must already be part of the program's weight blob. */
+struct slide_resident_plan;
+struct slide_rop;
+int slide_program_set_resident(slide_program *p, const struct slide_resident_plan *plan, const struct slide_rop *rops,
+                               int n_rops);
+int slide_program_use_resident(slide_program *p, int enable);
 /* Kernels launched by one pass over ops [first, first+count). */
 int slide_program_launches(slide_program *p, int first, int count);
 

@@ -9,6 +9,7 @@
 
 #include <vector>
 
+#include "../../include/slide_resident.h"
 #include "common.cuh"
 #include "program.cuh"
 
@@ -614,6 +615,9 @@ struct slide_program {
   // scratch of the GEMM transform pre-pass (gemm_tc.cu), one buffer per stream so that the two branches never share
   float *prepass[2] = {nullptr, nullptr};
   size_t prepass_bytes = 0;
+  // sample-resident plans (resident.cu): a record range [first, first+count) that runs as ONE kernel
+  std::vector<ResidentPlan *> resident;
+  int use_resident = 1;  // SLIDE_RESIDENT=0 keeps the per-record executor
 };
 
 namespace {
@@ -877,8 +881,16 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
 // Main-stream records go to `st`; SIDE records go to p->side.  The side stream forks lazily (it waits for everything
 // enqueued on `st` before the region's first SIDE record) and is joined at a JOIN record or at the end of the range,
 // so any sub-range (the tests run single records) is self-contained.
+const ResidentPlan *resident_for(slide_program *p, int first, int count) {
+  if (!p->use_resident || p->gemm_backend != 0) return nullptr;
+  for (const ResidentPlan *r : p->resident)
+    if (resident_first(r) == first && resident_count(r) == count) return r;
+  return nullptr;
+}
+
 int run_range(slide_program *p, int first, int count, cudaStream_t st) {
   if (!p || first < 0 || count < 0 || (size_t)(first + count) > p->ops.size()) return SLIDE_ERR_INVALID;
+  if (const ResidentPlan *r = resident_for(p, first, count)) return resident_launch(r, p->arena, p->weights, st);
   bool side_live = false;
   auto join = [&]() -> int {
     if (!side_live) return SLIDE_OK;
@@ -925,6 +937,8 @@ int slide_program_create(const struct slide_op *ops, int n_ops, size_t arena_byt
   if (be && strcmp(be, "simt") == 0) p->gemm_backend = 1;
   const char *sb = getenv("SLIDE_SIDE_BRANCH");
   if (sb && atoi(sb) == 0) p->use_side = 0;
+  const char *rs = getenv("SLIDE_RESIDENT");
+  if (rs && atoi(rs) == 0) p->use_resident = 0;
   int rc = cuda_rc(cudaMalloc((void **)&p->arena, arena_bytes > 0 ? arena_bytes : 256));
   if (rc == SLIDE_OK) rc = cuda_rc(cudaMemset(p->arena, 0, arena_bytes));
   if (rc == SLIDE_OK) rc = cuda_rc(cudaMalloc((void **)&p->weights, weights_bytes > 0 ? weights_bytes : 256));
@@ -964,7 +978,31 @@ void slide_program_destroy(slide_program *p) {
   if (p->weights) cudaFree(p->weights);
   for (int i = 0; i < 2; ++i)
     if (p->prepass[i]) cudaFree(p->prepass[i]);
+  for (ResidentPlan *r : p->resident) resident_free(r);
   delete p;
+}
+
+int slide_program_set_resident(slide_program *p, const struct slide_resident_plan *plan, const struct slide_rop *rops,
+                               int n_rops) {
+  if (!p || !plan || !rops || n_rops <= 0) return SLIDE_ERR_INVALID;
+  if (plan->first < 0 || plan->count <= 0 || (size_t)(plan->first + plan->count) > p->ops.size()) return SLIDE_ERR_INVALID;
+  ResidentPlan *r = nullptr;
+  const int rc = resident_create(plan, rops, n_rops, &r);
+  if (rc != SLIDE_OK) return rc;
+  for (ResidentPlan *&old : p->resident)
+    if (resident_first(old) == plan->first && resident_count(old) == plan->count) {
+      resident_free(old);
+      old = r;
+      return SLIDE_OK;
+    }
+  p->resident.push_back(r);
+  return SLIDE_OK;
+}
+
+int slide_program_use_resident(slide_program *p, int enable) {
+  if (!p) return SLIDE_ERR_INVALID;
+  p->use_resident = enable ? 1 : 0;
+  return SLIDE_OK;
 }
 
 void *slide_program_arena(slide_program *p) { return p ? p->arena : nullptr; }
@@ -1032,6 +1070,7 @@ void slide_tc_reload_tuning(void) {
 
 int slide_program_launches(slide_program *p, int first, int count) {
   if (!p || first < 0 || count < 0 || (size_t)(first + count) > p->ops.size()) return SLIDE_ERR_INVALID;
+  if (resident_for(p, first, count)) return 1;
   int n = 0;
   for (int i = first; i < first + count; ++i)
     if (p->ops[i].kind != SLIDE_OP_NOP && p->ops[i].kind != SLIDE_OP_JOIN) ++n;

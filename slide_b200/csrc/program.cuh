@@ -93,6 +93,17 @@ int launch_gemm_tc_prepass(const GemmArgs &a, const float *Wp, int wp_na, float 
 int tc_error_flag();
 void tc_error_reset();
 void tc_reload_tuning();
+// sample-resident plans (resident.cu)
+struct ResidentPlan;
+}  // namespace slide
+struct slide_resident_plan;
+struct slide_rop;
+namespace slide {
+int resident_create(const slide_resident_plan *hdr, const slide_rop *rops, int n_rops, ResidentPlan **out);
+void resident_free(ResidentPlan *p);
+int resident_launch(const ResidentPlan *p, char *arena, const char *weights, cudaStream_t st);
+int resident_first(const ResidentPlan *p);
+int resident_count(const ResidentPlan *p);
 int program_fps(int mode, const float *xyz, int ldx, int B, int N, int m, const int *start, int *out, cudaStream_t st);
 
 }  // namespace slide

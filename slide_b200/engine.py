@@ -114,7 +114,7 @@ def fast_position_schedule(method, length, schedule, kappa, dcfg):
 # builders
 # ---------------------------------------------------------------------------------------------------
 def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0, with_noise=True,
-               local_resampling=False, ts_values=None):
+               local_resampling=False, ts_values=None, resident=None):
     """One program = setup segment + step segment (+ forward-only segment) for a DDPM denoiser.
 
     mode 0: position sampler (util.sampling), mode 1: latent sampler (denoising_step), mode 2: FastDPM sampler
@@ -124,6 +124,9 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
     local_resampling (latent sampler only, diffusion.py:76-79): adds the handles x0c [B*n, C] (complete x0) and
     mask [B*n, 1] (1 = re-sample this point's features); with an all-ones mask the update equals the plain one.
     Handles: x, eps, labels, noise [T*B*n, C], ts_table, class_emb.
+    resident: None, or dict(cluster=2|4, precise=bool): also compile the "step" and "forward" ranges into
+    sample-resident plans (slide_b200/resident.py; one kernel per step instead of one per record) -> h["resident_plans"]
+    (a list, empty when the network does not fit the resident kernel); Program.set_resident installs them.
     """
     b = Builder(B)
     C = 3 + cfg["in_fea_dim"]
@@ -137,7 +140,7 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
     P = nets.Params(sd)
     b.begin_segment("step")
     b.step_begin()
-    net = nets.lower_cloud_net(b, P, cfg, X, n_points, "net", T=T, labels=labels)
+    net = nets.lower_cloud_net(b, P, cfg, X, n_points, "net", T=T, labels=labels, factor_group=bool(resident))
     fwd_count = len(b.ops) - b._seg_open[1]
     b.ddpm_update(mode, X, net["out"], noise, table_off, col0=keep_cols, clamp=clamp, x0c=x0c, mask=mask,
                   note="ddpm_update")
@@ -154,6 +157,17 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
         assert len(ts_values) == T
         h["ts_values"] = np.asarray(ts_values, dtype=np.float32)
     h.update(net["inputs"])
+    if resident:
+        from . import resident as res
+        plans = []
+        try:
+            for seg in ("step", "forward"):
+                plans.append(res.plan_segment(b, seg, cluster=resident.get("cluster", 4),
+                                              precise=resident.get("precise", False), np_points=n_points))
+        except res.Unsupported as e:
+            plans = []
+            h["resident_unsupported"] = str(e)
+        h["resident_plans"] = plans
     return b, h
 
 

@@ -24,6 +24,7 @@ SYMBOLS = [
     "slide_program_create", "slide_program_destroy", "slide_program_arena", "slide_program_weights",
     "slide_program_run", "slide_program_capture", "slide_program_replay", "slide_program_launches",
     "slide_program_set_gemm_backend", "slide_tc_error", "slide_tc_reset_error", "slide_tc_reload_tuning",
+    "slide_program_set_resident", "slide_program_use_resident",
 ]
 
 
@@ -56,6 +57,8 @@ def load():
         lib.slide_program_replay.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         lib.slide_program_launches.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         lib.slide_program_set_gemm_backend.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.slide_program_set_resident.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.slide_program_use_resident.argtypes = [ctypes.c_void_p, ctypes.c_int]
         _lib = lib
     return _lib
 

@@ -149,6 +149,8 @@ class _Grouped(object):
         tcgen05 GEMMs over the grouped tensor are cheaper than the extra U GEMM + the gather-bound PAIR kernels."""
         ntot = sum(int(Pc["weight"].shape[0]) for Pc in convs)
         mode = os.environ.get("SLIDE_FACTOR_GROUP", "auto")
+        if getattr(self.ctx, "factor_group", None):  # resident plans need the factored form (no grouped tensor at all)
+            mode = "1"
         self.factored = (mode == "1") or (mode == "auto" and self.Ctot * ntot >= FACTOR_MIN_WORK)
         if not self.factored:
             self._materialise()
@@ -433,7 +435,7 @@ def t_embedding_source(b, P, cfg, T, name):
     return ts, h2, emit
 
 
-def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None):
+def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None, factor_group=None):
     """Lower PointNet2CloudCondition (no condition cloud).
 
     X: arena tensor [B*n_points, 3 + in_fea_dim] (xyz first).  T: number of timesteps (DDPM denoisers) or None.
@@ -472,6 +474,7 @@ def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None)
                     note=name + ".class_emb")
         setup_pre.append(emit_c)
     ctx = _Ctx(b, cfg, t_src, cond_src)
+    ctx.factor_group = factor_group
 
     Fin = X.C - 3
     assert X.R == n_points

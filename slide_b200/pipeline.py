@@ -24,13 +24,19 @@ class DDPMSampler(object):
     """One denoiser + its ancestral sampling loop, resident on one GPU."""
 
     def __init__(self, pointnet_cfg, sd, B, table, mode, keep_cols, T, device, graph_steps=20, backend="auto",
-                 local_resampling=False, clamp=-1.0, ts_values=None):
+                 local_resampling=False, clamp=-1.0, ts_values=None, resident=None):
+        """resident: None, or dict(cluster=2|4, precise=bool): run every step as ONE sample-resident kernel
+        (slide_b200/resident.py) when the network fits it; otherwise (and with backend "simt") one kernel per record."""
         self.B, self.T, self.mode = B, T, mode
         self.builder, self.h = engine.build_ddpm(pointnet_cfg, sd, B, T, table, mode, keep_cols=keep_cols, clamp=clamp,
-                                                 local_resampling=local_resampling, ts_values=ts_values)
+                                                 local_resampling=local_resampling, ts_values=ts_values,
+                                                 resident=resident if backend == "auto" else None)
         self.local_resampling = local_resampling
         self.prog = Program(self.builder, device)
         self.prog.set_gemm_backend(backend)
+        self.resident = bool(self.h.get("resident_plans"))
+        for plan in self.h.get("resident_plans", []):
+            self.prog.set_resident(plan)
         self.C = self.h["C"]
         self.graph_steps = graph_steps
         while T % self.graph_steps:

@@ -14,11 +14,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _HEADER = os.path.join(_HERE, "..", "include", "slide_program.h")
 
 
-def _parse_header():
+def _parse_header(path=None, const_pattern=r"SLIDE_OP_N\w+"):
     """Field indices and constants come from the C header: one source of truth for both sides."""
-    src = open(_HEADER).read()
+    src = open(_HEADER if path is None else path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(SLIDE_OP_N\w+)\s+(\d+)", src)}
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(%s)\s+(\d+)" % const_pattern, src)}
     enums = {}
     values = {}
     for m in re.finditer(r"enum\s+(\w+)\s*\{(.*?)\}", src, flags=re.S):
@@ -444,6 +444,19 @@ class Program(object):
         """'auto' (tcgen05 where eligible) or 'simt' (fp32 FFMA everywhere)."""
         self._l.check(self.lib.slide_program_set_gemm_backend(self.handle, {"auto": 0, "simt": 1}[name]),
                       "slide_program_set_gemm_backend")
+
+    def set_resident(self, plan):
+        """Install a sample-resident plan (slide_b200.resident.Planner, built BEFORE this Program was created so that
+        its packed weight copies are in the weight blob)."""
+        hdr, rec = plan.pack()
+        assert plan.b is self.builder
+        with self._torch.cuda.device(self.device):
+            self._l.check(self.lib.slide_program_set_resident(self.handle, hdr.ctypes.data_as(ctypes.c_void_p),
+                                                              rec.ctypes.data_as(ctypes.c_void_p), len(rec)),
+                          "slide_program_set_resident")
+
+    def use_resident(self, enable):
+        self._l.check(self.lib.slide_program_use_resident(self.handle, int(bool(enable))), "slide_program_use_resident")
 
     def upload(self, t, value):
         """Copy a (rows, C) torch/numpy array into arena tensor t (async on the current stream)."""
