@@ -28,26 +28,25 @@ class ResidentSim(object):
         self.npl = self.np // self.cl
 
     # ---- operands ----------------------------------------------------------------------------------------------------
-    def _mat(self, arena, sm, sample, q, rows, cols, row0=0):
-        """View (rows x cols) of operand block q = rec['i'][base:base+4]; returns a writable numpy view."""
-        space, off, ld, sstride = [int(v) for v in q]
-        if space == 0:
+    @staticmethod
+    def _sm(sm, off, ld, rows, cols, row0=0):
+        """(rows x cols) window of a shared-memory array at float offset `off` (None when off < 0)."""
+        if off < 0:
             return None
-        if space == 1:
-            idx = (np.arange(row0, row0 + rows)[:, None] * ld + np.arange(cols)[None, :])
-            return _View(sm, off + idx)
-        if space == 2:
-            base = off + sample * sstride
-        elif space == 3:
-            base = off
-        else:
-            raise AssertionError(space)
-        buf = np.frombuffer(arena, dtype=np.float32, count=(row0 + rows) * ld, offset=base)
         idx = (np.arange(row0, row0 + rows)[:, None] * ld + np.arange(cols)[None, :])
-        return _View(buf, idx)
+        return _View(sm, off + idx)
+
+    @staticmethod
+    def _ar(arena, off, ld, rows, cols, row0=0):
+        """(rows x cols) window of the arena at FLOAT index `off`."""
+        if off < 0:
+            return None
+        buf = np.frombuffer(arena, dtype=np.float32)
+        idx = (np.arange(row0, row0 + rows)[:, None] * ld + np.arange(cols)[None, :])
+        return _View(buf, off + idx)
 
     def _w(self, off, n):
-        return np.frombuffer(self.weights, dtype=np.float32, count=n, offset=int(off))
+        return np.frombuffer(self.weights, dtype=np.float32, count=n, offset=4 * int(off))
 
     # ---- execution ---------------------------------------------------------------------------------------------------
     def run(self, arena):
@@ -80,32 +79,35 @@ class ResidentSim(object):
 
     def _copy(self, r, arena, sms, s, t, rank, scratch):
         i = r["i"]
-        rows, cols = int(i[RV["RC_ROWS"]]), int(i[RV["RC_COLS"]])
-        r0 = 0
-        if int(i[RV["RC_OWNED"]]):
-            rpp = int(i[RV["RC_RPP"]])
-            r0, rows = rank * self.npl * rpp, self.npl * rpp
-        src = self._mat(arena, sms[rank], s, i[RV["RC_SRC"]:RV["RC_SRC"] + 4], rows, cols, r0)
-        dst = self._mat(arena, sms[rank], s, i[RV["RC_DST"]:RV["RC_DST"] + 4], rows, cols, r0)
+        g = lambda k: int(i[RV[k]])
+        rows, cols, r0 = g("RC_ROWS"), g("RC_COLS"), 0
+        if g("RC_OWNED"):
+            r0, rows = rank * self.npl, self.npl
+        sm = sms[rank]
+        src = self._ar(arena, g("RC_SRC") + s * g("RC_SSTRIDE"), g("RC_SLD"), rows, cols, r0) if g("RC_SRC_G") else \
+            self._sm(sm, g("RC_SRC"), g("RC_SLD"), rows, cols, r0)
+        dst = self._ar(arena, g("RC_DST") + s * g("RC_DSTRIDE"), g("RC_DLD"), rows, cols, r0) if g("RC_DST_G") else \
+            self._sm(sm, g("RC_DST"), g("RC_DLD"), rows, cols, r0)
         dst.set(src.get())
 
     def _knn(self, r, arena, sms, s, t, rank, scratch):
         i = r["i"]
-        P1, P2, K = int(i[RV["RK_P1"]]), int(i[RV["RK_P2"]]), int(i[RV["RK_K"]])
-        q = self._mat(arena, sms[rank], s, i[RV["RK_Q"]:RV["RK_Q"] + 4], P1, 3).get()
-        ref = self._mat(arena, sms[rank], s, i[RV["RK_REF"]:RV["RK_REF"] + 4], P2, 3).get()
+        g = lambda k: int(i[RV[k]])
+        P1, P2, K = g("RK_P1"), g("RK_P2"), g("RK_K")
+        sm = sms[rank]
+        q = self._sm(sm, g("RK_Q"), g("RK_QLD"), P1, 3).get()
+        ref = self._sm(sm, g("RK_REF"), g("RK_RLD"), P2, 3).get()
         assert np.isfinite(q).all() and np.isfinite(ref).all()
         res = ops.knn_points(torch.from_numpy(q)[None], torch.from_numpy(ref)[None], K=K)
-        sm = sms[rank]
-        io = int(i[RV["RK_IDX"]])
+        io = g("RK_IDX")
         sm[io:io + P1 * K] = res.idx.reshape(-1).numpy().astype(np.int32).view(np.float32)
-        do = int(i[RV["RK_D2"]])
+        do = g("RK_D2")
         if do >= 0:
             sm[do:do + P1 * K] = res.dists.reshape(-1).numpy()
 
     def _unpack_w(self, i, N, K):
         npad, nchunk = int(i[RV["RG_NPAD"]]), int(i[RV["RG_NCHUNK"]])
-        buf = self._w(i[RV["RG_WCH"]], nchunk * npad * R.WLD).reshape(nchunk, npad, R.WLD)
+        buf = self._w(int(i[RV["RG_WCH"]]), nchunk * npad * R.WLD).reshape(nchunk, npad, R.WLD)
         assert nchunk == (K + R.WCH - 1) // R.WCH and npad == (N + 7) // 8 * 8
         w = np.concatenate([buf[q, :, :R.WCH] for q in range(nchunk)], axis=1)
         assert not w[N:].any() and not w[:, K:].any(), "weight copy padding must be zero"
@@ -123,115 +125,115 @@ class ResidentSim(object):
 
     def _gemm(self, r, arena, sms, s, t, rank, scratch):
         i, f = r["i"], r["f"]
+        g = lambda k: int(i[RV[k]])
         sm = sms[rank]
-        M, K, N = int(i[RV["RG_M"]]), int(i[RV["RG_K"]]), int(i[RV["RG_N"]])
-        pair, rpp, smk = int(i[RV["RG_PAIRROWS"]]), int(i[RV["RG_RPP"]]), int(i[RV["RG_SMK"]])
+        M, K, N = g("RG_M"), g("RG_K"), g("RG_N")
+        pair, rshift, smk = g("RG_PAIRROWS"), g("RG_RPP_SHIFT"), g("RG_SMK")
         p0 = rank * self.npl
-        A = self._mat(arena, sm, s, i[RV["RG_A"]:RV["RG_A"] + 4], M, K).get()
+        A = self._sm(sm, g("RG_A"), g("RG_ALD"), M, K).get()
         assert np.isfinite(A).all(), "GEMM A operand holds uninitialised / clobbered values"
         W = self._unpack_w(i, N, K)
         if not int(self.h["precise"]):
             A = R.tf32_rna(A)
         c = (torch.from_numpy(np.ascontiguousarray(A)) @ torch.from_numpy(np.ascontiguousarray(W)).t()).numpy()
-        if int(i[RV["RG_BIAS"]]) >= 0:
-            c = c + self._w(i[RV["RG_BIAS"]], N)
-        point = (p0 + np.arange(M) // rpp) if pair else np.arange(M)
+        if g("RG_BIAS") >= 0:
+            c = c + self._w(g("RG_BIAS"), N)
+        point = (p0 + (np.arange(M) >> rshift)) if pair else np.arange(M)
         if smk > 0:
-            val = self._mat(arena, sm, s, i[RV["RG_RES"]:RV["RG_RES"] + 4], M, N).get()
+            assert (1 << rshift) == smk
+            val = self._sm(sm, g("RG_RES"), g("RG_RESLD"), M, N).get()
             assert np.isfinite(val).all()
             w = torch.softmax(torch.from_numpy(c.astype(np.float32).reshape(M // smk, smk, N)), dim=1).numpy()
             out = (val.reshape(M // smk, smk, N) * w).sum(axis=1, dtype=np.float32)
             rows = p0 + np.arange(M // smk)
             for rk in range(self.cl):  # published to every CTA of the cluster
-                dst = self._mat(arena, sms[rk], s, i[RV["RG_C"]:RV["RG_C"] + 4], self.np, N)
-                dst.set_rows(rows, out)
+                self._sm(sms[rk], g("RG_C"), g("RG_CLD"), self.np, N).set_rows(rows, out)
             return
-        ev = self._mat(arena, sm, s, i[RV["RG_EV"]:RV["RG_EV"] + 4], self.np, N)
+        ev = self._sm(sm, g("RG_EV"), g("RG_EVLD"), self.np, N)
         if ev is not None:
             e = ev.get()[point]
             assert np.isfinite(e).all()
             c = c + e
-        res = self._mat(arena, sm, s, i[RV["RG_RES"]:RV["RG_RES"] + 4], M, N)
+        res = self._sm(sm, g("RG_RES"), g("RG_RESLD"), M, N)
         if res is not None:
             rv = res.get()
             assert np.isfinite(rv).all()
             c = c + rv
-        if int(i[RV["RG_ACT"]]) == 1:
+        if g("RG_ACT") == 1:
             c = np.maximum(c, 0)
         c = c.astype(np.float32)
-        self._mat(arena, sm, s, i[RV["RG_C"]:RV["RG_C"] + 4], M, N).set(c)
-        st = int(i[RV["RG_ST"]])
+        self._sm(sm, g("RG_C"), g("RG_CLD"), M, N).set(c)
+        st = g("RG_ST")
         if st >= 0:
             vals = c
-            if int(i[RV["RG_ST_OWNED"]]):
+            if g("RG_ST_OWNED"):
                 vals = c[(point >= p0) & (point < p0 + self.npl)]
-            self._stats_add(sm, st, int(i[RV["RG_ST_CG"]]), int(i[RV["RG_ST_NNORM"]]), int(i[RV["RG_ST_CHOFF"]]), range(N), vals,
-                            f[0])
+            self._stats_add(sm, st, g("RG_ST_CG"), g("RG_ST_NNORM"), g("RG_ST_CHOFF"), range(N), vals, f[0])
 
     def _pair(self, r, arena, sms, s, t, rank, scratch):
         i = r["i"]
+        g = lambda k: int(i[RV[k]])
         sm = sms[rank]
-        K, N = int(i[RV["RP_K"]]), int(i[RV["RP_N"]])
+        K, N = g("RP_K"), g("RP_N")
         p0, npl, npts = rank * self.npl, self.npl, self.np
-        U = self._mat(arena, sm, s, i[RV["RP_U"]:RV["RP_U"] + 4], npts, N).get()
-        X = self._mat(arena, sm, s, i[RV["RP_XYZ"]:RV["RP_XYZ"] + 4], npts, 3).get()
-        CT = self._mat(arena, sm, s, i[RV["RP_CTR"]:RV["RP_CTR"] + 4], npts, 3).get()
-        io = int(i[RV["RP_IDX"]])
+        U = self._sm(sm, g("RP_U"), g("RP_ULD"), npts, N).get()
+        X = self._sm(sm, g("RP_XYZ"), g("RP_XLD"), npts, 3).get()
+        CT = self._sm(sm, g("RP_CTR"), g("RP_CLD"), npts, 3).get()
+        io = g("RP_IDX")
         idx = sm[io:io + npts * K].view(np.int32).reshape(npts, K)[p0:p0 + npl]
         assert np.isfinite(U).all() and np.isfinite(X).all() and (idx >= 0).all() and (idx < npts).all()
-        wx, wc = self._w(i[RV["RP_WX"]], N * 3).reshape(N, 3), self._w(i[RV["RP_WC"]], N * 3).reshape(N, 3)
+        wx, wc = self._w(g("RP_WX"), N * 3).reshape(N, 3), self._w(g("RP_WC"), N * 3).reshape(N, 3)
         out = U[idx] + X[idx] @ wx.T + (CT[p0:p0 + npl] @ wc.T)[:, None, :]
-        if int(i[RV["RP_BIAS"]]) >= 0:
-            out = out + self._w(i[RV["RP_BIAS"]], N)
-        do = int(i[RV["RP_D2"]])
+        if g("RP_BIAS") >= 0:
+            out = out + self._w(g("RP_BIAS"), N)
+        do = g("RP_D2")
         if do >= 0:
             d2 = sm[do:do + npts * K].reshape(npts, K)[p0:p0 + npl][:, :, None]
             inv = (np.float32(1.0) / (d2 + np.float32(1e-8))).astype(np.float32)
             w = inv / inv.sum(axis=1, keepdims=True, dtype=np.float32)
-            out = out + d2 * self._w(i[RV["RP_WD"]], N) + w * self._w(i[RV["RP_WW"]], N)
+            out = out + d2 * self._w(g("RP_WD"), N) + w * self._w(g("RP_WW"), N)
         c = out.reshape(npl * K, N).astype(np.float32)
-        res = self._mat(arena, sm, s, i[RV["RP_RES"]:RV["RP_RES"] + 4], npl * K, N)
+        res = self._sm(sm, g("RP_RES"), g("RP_RLD"), npl * K, N)
         if res is not None:
             rv = res.get()
             assert np.isfinite(rv).all()
             c = c + rv
-        if int(i[RV["RP_ACT"]]) == 1:
+        if g("RP_ACT") == 1:
             c = np.maximum(c, 0)
         c = c.astype(np.float32)
-        self._mat(arena, sm, s, i[RV["RP_OUT"]:RV["RP_OUT"] + 4], npl * K, N).set(c)
-        st = int(i[RV["RP_ST"]])
+        self._sm(sm, g("RP_OUT"), g("RP_OLD"), npl * K, N).set(c)
+        st = g("RP_ST")
         if st >= 0:
-            self._stats_add(sm, st, int(i[RV["RP_ST_CG"]]), int(i[RV["RP_ST_NNORM"]]), int(i[RV["RP_ST_CHOFF"]]), range(N), c, 1.0)
+            self._stats_add(sm, st, g("RP_ST_CG"), g("RP_ST_NNORM"), g("RP_ST_CHOFF"), range(N), c, 1.0)
 
     def _xform(self, r, arena, sms, s, t, rank, scratch):
         i, f = r["i"], r["f"]
+        g = lambda k: int(i[RV[k]])
         sm = sms[rank]
-        rows, C = int(i[RV["RX_ROWS"]]), int(i[RV["RX_C"]])
-        X = self._mat(arena, sm, s, i[RV["RX_X"]:RV["RX_X"] + 4], rows, C)
+        rows, C = g("RX_ROWS"), g("RX_C")
+        X = self._sm(sm, g("RX_X"), g("RX_XLD"), rows, C)
         x = X.get()
         assert np.isfinite(x).all(), "XFORM input holds uninitialised / clobbered values"
-        st, cg, nnorm, choff = int(i[RV["RX_ST"]]), int(i[RV["RX_CG"]]), int(i[RV["RX_NNORM"]]), int(i[RV["RX_CHOFF"]])
+        st, cg, nnorm, choff = g("RX_ST"), g("RX_CG"), g("RX_NNORM"), g("RX_CHOFF")
         y = x.copy()
         if st >= 0:
-            gam, bet = self._w(i[RV["RX_GAMMA"]], nnorm), self._w(i[RV["RX_BETA"]], nnorm)
+            gam, bet = self._w(g("RX_GAMMA"), nnorm), self._w(g("RX_BETA"), nnorm)
             for n in range(C):
                 ch = choff + n
                 if ch < nnorm:
-                    g = ch // cg
-                    mean = sm[st + 2 * g] * f[0]
-                    var = max(sm[st + 2 * g + 1] * f[0] - mean * mean, np.float32(0))
+                    gi = ch // cg
+                    mean = sm[st + 2 * gi] * f[0]
+                    var = max(sm[st + 2 * gi + 1] * f[0] - mean * mean, np.float32(0))
                     rstd = np.float32(1.0) / np.sqrt(np.float32(var + np.float32(EPS)))
                     a = rstd * gam[ch]
                     b = bet[ch] - mean * a
                     y[:, n] = x[:, n] * a + b
-        if int(i[RV["RX_RELU"]]):
+        if g("RX_RELU"):
             y = np.maximum(y, 0)
-        q = i[RV["RX_ADD"]:RV["RX_ADD"] + 4]
-        if int(q[0]) != 0:
-            mode = int(i[RV["RX_ADDMODE"]])
+        if g("RX_ADD") >= 0:
+            mode = g("RX_ADDMODE")
             arow = s if mode == 0 else (t if mode == 1 else 0)
-            ld = int(q[2])
-            add = np.frombuffer(arena, dtype=np.float32, count=C, offset=int(q[1]) + 4 * ld * arow)
+            add = np.frombuffer(arena, dtype=np.float32, count=C, offset=4 * (g("RX_ADD") + g("RX_ADDLD") * arow))
             y = y + add
         X.set(y.astype(np.float32))
 
@@ -246,15 +248,16 @@ class ResidentSim(object):
 
     def _ddpm(self, r, arena, sms, s, t, rank, scratch):
         i, f = r["i"], r["f"]
+        g = lambda k: int(i[RV[k]])
         sm = sms[rank]
-        mode, nc, c0 = int(i[RV["RD_MODE"]]), int(i[RV["RD_NCOLS"]]), int(i[RV["RD_COL0"]])
+        mode, nc, c0 = g("RD_MODE"), g("RD_NCOLS"), g("RD_COL0")
         p0, npl = rank * self.npl, self.npl
-        brows = int(i[RV["RD_BROWS"]])
-        x = self._mat(arena, sm, s, i[RV["RD_X"]:RV["RD_X"] + 4], npl, nc, p0).get()
-        eps = self._mat(arena, sm, s, i[RV["RD_EPS"]:RV["RD_EPS"] + 4], npl, nc, p0).get()
+        brows = g("RD_BROWS")
+        x = self._sm(sm, g("RD_X"), g("RD_XLD"), npl, nc, p0).get()
+        eps = self._sm(sm, g("RD_EPS"), g("RD_ELD"), npl, nc, p0).get()
         assert np.isfinite(x).all() and np.isfinite(eps).all()
-        tab = self._w(int(i[RV["RD_TABLE"]]) + 32 * t, 8)
-        noise = np.frombuffer(arena, dtype=np.float32, count=brows * nc, offset=int(i[RV["RD_NOISE"]]) + 4 * brows * nc * t)
+        tab = self._w(g("RD_TABLE") + 8 * t, 8)
+        noise = np.frombuffer(arena, dtype=np.float32, count=brows * nc, offset=4 * (g("RD_NOISE") + brows * nc * t))
         noise = noise.reshape(brows, nc)[s * self.np + p0:s * self.np + p0 + npl]
         f32 = np.float32
         if mode == 0:
@@ -268,26 +271,26 @@ class ResidentSim(object):
             x0 = c1 * x - c2 * eps
             if f[0] > 0:
                 x0 = np.clip(x0, -f[0], f[0])
-            x0c = self._mat(arena, sm, s, i[RV["RD_X0C"]:RV["RD_X0C"] + 4], npl, nc, p0)
-            if x0c is not None:
-                m = self._mat(arena, sm, s, i[RV["RD_MASK"]:RV["RD_MASK"] + 4], npl, 1, p0).get()
-                x0 = x0 * m + x0c.get() * (f32(1.0) - m)
+            if g("RD_X0C") >= 0:
+                x0c = self._ar(arena, g("RD_X0C") + s * g("RD_X0CSTRIDE"), g("RD_X0CLD"), npl, nc, p0).get()
+                m = self._ar(arena, g("RD_MASK") + s * g("RD_MASKSTRIDE"), 1, npl, 1, p0).get()
+                x0 = x0 * m + x0c * (f32(1.0) - m)
             new = pm1 * x0 + pm2 * x
             new = new + (f32(0.0 if t == 0 else 1.0) * sig) * noise
-        xg = self._mat(arena, sm, s, i[RV["RD_XG"]:RV["RD_XG"] + 4], npl, nc, p0)
+        xg = self._ar(arena, g("RD_XG") + s * g("RD_XGSTRIDE"), g("RD_XGLD"), npl, nc, p0)
         cur = xg.get()
         cur[:, c0:] = new.astype(np.float32)[:, c0:]
         xg.set(cur)
 
     def _spill(self, r, arena, sms, s, t, rank, scratch):
         i = r["i"]
-        o, n, so = int(i[RV["RL_SMEM"]]), int(i[RV["RL_NFLOATS"]]), int(i[RV["RL_SCRATCH"]]) // 4
+        o, n, so = int(i[RV["RL_SMEM"]]), int(i[RV["RL_NFLOATS"]]), int(i[RV["RL_SCRATCH"]])
         scratch[so:so + n] = sms[rank][o:o + n]
         sms[rank][o:o + n] = np.nan  # the region is reused by other tensors
 
     def _fill(self, r, arena, sms, s, t, rank, scratch):
         i = r["i"]
-        o, n, so = int(i[RV["RL_SMEM"]]), int(i[RV["RL_NFLOATS"]]), int(i[RV["RL_SCRATCH"]]) // 4
+        o, n, so = int(i[RV["RL_SMEM"]]), int(i[RV["RL_NFLOATS"]]), int(i[RV["RL_SCRATCH"]])
         sms[rank][o:o + n] = scratch[so:so + n]
 
 

@@ -5,11 +5,14 @@
 // already in flight while the current layer's epilogue runs).
 //
 // Arithmetic: the contractions here are small (K, N <= 139 for the position DDPM) and every operand is on chip, so the
-// work is issue/latency bound, not tensor-pipe bound; the dense products run on the warp-level tensor path (mma.sync
-// m16n8k8, TF32 operands rounded to nearest, fp32 accumulate -- the numerics class of the reference's cuDNN convs) fed by
-// ldmatrix from padded shared-memory rows (row stride = 4 mod 8 floats: conflict-free).  PRECISE plans split both
-// operands (3xTF32) and match the fp32 oracle to ~1e-6.  Everything else (grouping, GroupNorm, soft-max, update) is
-// fp32 on the CUDA cores.  Replaces 65 launches per position-DDPM step of the per-record executor (program.cu).
+// kernel is bound by INSTRUCTION ISSUE, not by the tensor pipe or memory (ncu: tensor pipe < 5 %, issue slots ~ 50 %
+// busy with 4 warps per scheduler).  Hence: the dense products run on the warp-level tensor path (mma.sync m16n8k8, TF32
+// operands rounded to nearest, fp32 accumulate -- the numerics class of the reference's cuDNN convs) fed by ldmatrix from
+// padded shared-memory rows (row stride = 4 mod 8 floats: conflict-free); tile counts are compile-time so the inner loop
+// is ldmatrix + cvt + mma only; records are fully resolved on the host (32-bit offsets, shifts instead of divisions);
+// element-wise passes use 16-byte accesses; statistics go through per-warp column partials instead of shared-memory
+// float atomics (CAS loops on this architecture).  PRECISE plans split both operands (3xTF32) and match the fp32 oracle
+// to ~1e-6.  Replaces 62 launches per position-DDPM step of the per-record executor (program.cu).
 #include <math.h>
 #include <string.h>
 
@@ -26,15 +29,15 @@ constexpr int NW = RT / 32;
 constexpr int WCH = SLIDE_RES_WCHUNK;        // K columns per staged weight chunk
 constexpr int WLD = WCH + SLIDE_RES_WPAD;    // staged row stride in floats (4 mod 8)
 constexpr int WSTAGES = SLIDE_RES_WSTAGES;
-constexpr int NTMAX = 5;                     // n-tiles per warp
+constexpr int NBLK_PAD = SLIDE_RES_NBLK + 8;  // column slots of the statistics scratch (and rows of a ring stage)
 
 struct ResArgs {
   const slide_rop *rops;
   int n_rops;
-  char *arena;
-  const char *weights;
-  char *scratch;  // [grid][scratch_bytes]
-  int *done;      // CTAs finished (for the step-counter update)
+  float *arena;
+  const float *weights;
+  float *scratch;  // [grid][scratch_floats]
+  int *done;       // CTAs finished (for the step-counter update)
   slide_resident_plan plan;
 };
 
@@ -89,125 +92,103 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// ---- operands ------------------------------------------------------------------------------------------------------
 struct Ctx {
-  float *sm;            // dynamic shared memory
-  char *arena;
-  const char *weights;
+  float *arena;
+  const float *weights;
   int sample, rank, cl, np, npl, p0, t;
 };
 
-struct Opnd {
-  float *ptr;  // resolved base pointer (shared or global), nullptr = absent
-  int ld;
-  bool shared;
-};
-
-__device__ __forceinline__ Opnd resolve(const Ctx &c, const int64_t *f) {
-  Opnd o;
-  o.ld = (int)f[RO_LD];
-  o.shared = false;
-  switch ((int)f[RO_SPACE]) {
-    case 1:
-      o.ptr = c.sm + f[RO_OFF];
-      o.shared = true;
-      break;
-    case 2:
-      o.ptr = reinterpret_cast<float *>(c.arena + f[RO_OFF] + (int64_t)c.sample * f[RO_SSTRIDE]);
-      break;
-    case 3:
-      o.ptr = reinterpret_cast<float *>(c.arena + f[RO_OFF]);
-      break;
-    case 4:
-      o.ptr = reinterpret_cast<float *>(const_cast<char *>(c.weights) + f[RO_OFF]);
-      break;
-    default:
-      o.ptr = nullptr;
-  }
-  return o;
-}
-__device__ __forceinline__ const float *wptr(const Ctx &c, int64_t off) {
-  return off < 0 ? nullptr : reinterpret_cast<const float *>(c.weights + off);
-}
-
 // ---- weight-chunk ring ---------------------------------------------------------------------------------------------
-// Chunk q of a GEMM's packed weight copy ([nchunk][npad][WLD] floats) -> stage (issue index % WSTAGES).  Every thread
-// commits exactly one group per issued chunk, so cp.async.wait_group counts are uniform across the CTA.
-__device__ __forceinline__ void issue_chunk(const Ctx &c, float *wst, int stage_floats, int slot, int64_t wch, int npad, int q,
-                                            int tid) {
-  const float4 *src = reinterpret_cast<const float4 *>(c.weights + wch) + (size_t)q * npad * (WLD / 4);
-  const uint32_t dst = smem_u32(wst + (size_t)slot * stage_floats);
-  const int n16 = npad * (WLD / 4);
-  for (int i = tid; i < n16; i += RT) cp_async16(dst + i * 16, src + i);
+// Chunk q of a GEMM's packed weight copy ([nchunk][npad][WLD] floats) -> stage q % WSTAGES.  Every thread commits exactly
+// one group per issued chunk, so cp.async.wait_group counts are uniform across the CTA.
+__device__ __forceinline__ void issue_chunk(const float *wsrc, uint32_t wst_u, int stage_bytes, int n16, int q, int tid) {
+  const float4 *src = reinterpret_cast<const float4 *>(wsrc) + q * n16;
+  const uint32_t dst = wst_u + (uint32_t)((q % WSTAGES) * stage_bytes);
+  if (tid < n16) cp_async16(dst + tid * 16, src + tid);
+  if (tid + RT < n16) cp_async16(dst + (tid + RT) * 16, src + tid + RT);
   cp_commit();
+}
+
+// ---- column statistics ---------------------------------------------------------------------------------------------
+// Per-(slot, column) partial sums {sum, sum of squares} parked in `scr` ([nslots][NBLK_PAD][2] floats; a free stage of the
+// weight ring) are folded into the statistics buffer by ONE thread per group.  Group gi covers channels
+// [gi*cg, (gi+1)*cg) = local columns [gi*cg - choff, ...) clipped to [0, lim): the first and last group of the range may
+// be shared with another producer (q | k concatenations, column blocks), which ran in an earlier rop.
+__device__ __forceinline__ void fold_colsum(float *st, const float *scr, int nslots, int ncols, int cg, int nnorm, int choff,
+                                            float weight, int tid) {
+  const int lim = min(ncols, nnorm - choff);
+  if (tid >= 64 || lim <= 0) return;  // <= 32 groups per tensor (+ a shared edge group)
+  const int g_first = choff / cg, g_last = (choff + lim - 1) / cg;
+  if (tid <= g_last - g_first) {
+    const int gi = g_first + tid;
+    const int c0 = max(0, gi * cg - choff), c1 = min(lim, (gi + 1) * cg - choff);
+    float s = 0.f, q = 0.f;
+    for (int slot = 0; slot < nslots; ++slot)
+      for (int col = c0; col < c1; ++col) {
+        const float2 v = *reinterpret_cast<const float2 *>(scr + (slot * NBLK_PAD + col) * 2);
+        s += v.x;
+        q += v.y;
+      }
+    st[2 * gi] += weight * s;
+    st[2 * gi + 1] += weight * q;
+  }
 }
 
 // ---- RS_GEMM -------------------------------------------------------------------------------------------------------
 // Warp grid over (row tiles of 16, column tiles of 8): 8 row tiles -> 4 x 4 warps with 2 row tiles each, 4 -> 4 x 4,
 // 2 -> 2 x 8, 1 -> 1 x 16.  More than 128 rows: passes of 128 rows (the weight chunks are streamed again).
-template <bool PRECISE>
-__device__ void rs_gemm(const Ctx &c, const slide_rop &r, float *wst, int stage_floats, int &ring, int tid) {
-  const int64_t *f = r.i;
-  const Opnd A = resolve(c, f + RG_A), C = resolve(c, f + RG_C), EV = resolve(c, f + RG_EV), RES = resolve(c, f + RG_RES);
-  const int M = (int)f[RG_M], K = (int)f[RG_K], N = (int)f[RG_N];
-  const int pairrows = (int)f[RG_PAIRROWS], rpp = (int)f[RG_RPP];
-  const int nchunk = (int)f[RG_NCHUNK], npad = (int)f[RG_NPAD];
-  const int64_t wch = f[RG_WCH];
-  const float *bias = wptr(c, f[RG_BIAS]);
-  const int act = (int)f[RG_ACT], smk = (int)f[RG_SMK];
-  const int st_off = (int)f[RG_ST], st_cg = (int)f[RG_ST_CG], st_nnorm = (int)f[RG_ST_NNORM], st_choff = (int)f[RG_ST_CHOFF];
-  const int st_owned = (int)f[RG_ST_OWNED];
-  const float st_w = r.f[0];
+// MT / NT (row / column tiles per warp) are compile-time: the inner loop is branch-free (ldmatrix + cvt + mma only).
+template <int MT, int NT, bool PRECISE>
+__device__ __forceinline__ void gemm_pass(const Ctx &c, const int *f, float stw, float *sm, float *wst, int stage_floats,
+                                          int &ring, int tid, int m_pass, int wgm, bool last_pass) {
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int K = f[RG_K], N = f[RG_N], nchunk = f[RG_NCHUNK];
   const int n_tiles = (N + 7) >> 3;
+  const int wm = warp % wgm, wn = warp / wgm;
+  const int tile0 = wn * NT;
+  const int row0 = m_pass + wm * MT * 16;
+  const bool active = tile0 < n_tiles;
+  const int lda = f[RG_ALD];
 
-  for (int m_pass = 0; m_pass < M; m_pass += 128) {
-    const int m_rows = min(128, M - m_pass);
-    const int m_tiles = m_rows >> 4;
-    int wgm, mt_n;
-    if (m_tiles >= 8) { wgm = 4; mt_n = 2; }
-    else if (m_tiles >= 4) { wgm = 4; mt_n = 1; }
-    else if (m_tiles >= 2) { wgm = 2; mt_n = 1; }
-    else { wgm = 1; mt_n = 1; }
-    const int wgn = NW / wgm;
-    const int wm = warp % wgm, wn = warp / wgm;
-    const int nt_n = (n_tiles + wgn - 1) / wgn;  // <= NTMAX by construction (N <= 128 -> 16 tiles / >= 4 column warps)
-    const int tile0 = wn * nt_n;                  // this warp's first column tile
-    const int row0 = m_pass + wm * mt_n * 16;     // this warp's first row
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int a = 0; a < MT; ++a)
+#pragma unroll
+    for (int b = 0; b < NT; ++b)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
 
-    float acc[2][NTMAX][4];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < NTMAX; ++b)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
-
-    // chunks already in flight for this GEMM (issued by the previous GEMM rop's tail): only on the first row pass
-    int issued = (m_pass == 0) ? min(ring, nchunk) : 0;
-    if (m_pass == 0) ring = 0;
-    // ldmatrix lane addressing
-    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = ((lane >> 4) & 1) * 4;
-    const int b_row = (lane & 7) + ((lane >> 4) & 1) * 8, b_col = ((lane >> 3) & 1) * 4;
-    for (int q = 0; q < nchunk; ++q) {
-      // keep two chunks in flight
-      while (issued < nchunk && issued < q + 2) {
-        issue_chunk(c, wst, stage_floats, issued % WSTAGES, wch, npad, issued, tid);
-        ++issued;
-      }
-      if (issued - q >= 2) cp_wait<1>(); else cp_wait<0>();
-      __syncthreads();  // chunk q visible to all warps; everyone is done with chunk q-1 (its stage may be refilled)
-      const float *ws = wst + (size_t)(q % WSTAGES) * stage_floats;
+  const float *wsrc = c.weights + f[RG_WCH];
+  const int n16 = f[RG_NPAD] * (WLD / 4);
+  const uint32_t wst_u = smem_u32(wst);
+  const int stage_bytes = stage_floats * 4;
+  int issued = (m_pass == 0) ? min(ring, nchunk) : 0;
+  if (m_pass == 0) ring = 0;
+  while (issued < nchunk && issued < 2) {  // chunks 0 and 1 (unless the previous GEMM's tail already sent them)
+    issue_chunk(wsrc, wst_u, stage_bytes, n16, issued, tid);
+    ++issued;
+  }
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = ((lane >> 4) & 1) * 4;
+  const int b_row = (lane & 7) + ((lane >> 4) & 1) * 8, b_col = ((lane >> 3) & 1) * 4;
+  uint32_t a_addr = smem_u32(sm + f[RG_A] + (row0 + a_row) * lda + a_col);
+  const uint32_t a_mt = (uint32_t)(16 * lda * 4);
+  const uint32_t b_off = (uint32_t)(((tile0 * 8 + b_row) * WLD + b_col) * 4);
+  for (int q = 0; q < nchunk; ++q) {
+    // pending groups here: chunk q, and chunk q+1 if it exists (issued one iteration ago / by the prologue)
+    if (q + 1 < nchunk) cp_wait<1>(); else cp_wait<0>();
+    __syncthreads();  // chunk q visible to all warps; everyone is done with chunk q-1, whose stage takes chunk q+2
+    if (q + 2 < nchunk && q + 2 >= issued) issue_chunk(wsrc, wst_u, stage_bytes, n16, q + 2, tid);
+    if (active) {
+      const uint32_t ws = wst_u + (uint32_t)((q % WSTAGES) * stage_bytes) + b_off;
 #pragma unroll
       for (int ks = 0; ks < WCH / 8; ++ks) {
         const int k0 = q * WCH + ks * 8;
-        if (k0 >= K) break;
-        uint32_t ah[2][4], al[2][4];
+        if (k0 < K) {
+          uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          if (mt < mt_n) {
+          for (int mt = 0; mt < MT; ++mt) {
             uint32_t r0, r1, r2, r3;
-            ldsm4(smem_u32(A.ptr + (size_t)(row0 + mt * 16 + a_row) * A.ld + k0 + a_col), r0, r1, r2, r3);
+            ldsm4(a_addr + mt * a_mt + ks * 32, r0, r1, r2, r3);
             float v[4] = {__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)};
             if (k0 + 8 > K) {  // K tail: columns >= K of A are not part of the operand (and may hold anything)
               if (k0 + tq >= K) v[0] = v[1] = 0.f;
@@ -219,17 +200,14 @@ __device__ void rs_gemm(const Ctx &c, const slide_rop &r, float *wst, int stage_
               if (PRECISE) al[mt][e] = tf32_rna(v[e] - __uint_as_float(ah[mt][e]));
             }
           }
-        }
 #pragma unroll
-        for (int jp = 0; jp < (NTMAX + 1) / 2; ++jp) {
-          const int j0 = jp * 2;
-          if (j0 < nt_n && tile0 + j0 < n_tiles) {
+          for (int jp = 0; jp < (NT + 1) / 2; ++jp) {
             uint32_t b[4];
-            ldsm4(smem_u32(ws + (size_t)((tile0 + j0) * 8 + b_row) * WLD + ks * 8 + b_col), b[0], b[1], b[2], b[3]);
+            ldsm4(ws + (uint32_t)((jp * 16 * WLD + ks * 8) * 4), b[0], b[1], b[2], b[3]);
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
-              const int j = j0 + jj;
-              if (j < NTMAX && j < nt_n && tile0 + j < n_tiles) {
+              const int j = jp * 2 + jj;
+              if (j < NT) {
                 uint32_t bh0 = b[jj * 2], bh1 = b[jj * 2 + 1];
                 if (PRECISE) {
                   const float f0 = __uint_as_float(bh0), f1 = __uint_as_float(bh1);
@@ -237,51 +215,63 @@ __device__ void rs_gemm(const Ctx &c, const slide_rop &r, float *wst, int stage_
                   bh1 = tf32_rna(f1);
                   const uint32_t bl0 = tf32_rna(f0 - __uint_as_float(bh0)), bl1 = tf32_rna(f1 - __uint_as_float(bh1));
 #pragma unroll
-                  for (int mt = 0; mt < 2; ++mt)
-                    if (mt < mt_n) {
-                      mma_tf32(acc[mt][j], al[mt][0], al[mt][1], al[mt][2], al[mt][3], bh0, bh1);
-                      mma_tf32(acc[mt][j], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bl0, bl1);
-                    }
+                  for (int mt = 0; mt < MT; ++mt) {
+                    mma_tf32(acc[mt][j], al[mt][0], al[mt][1], al[mt][2], al[mt][3], bh0, bh1);
+                    mma_tf32(acc[mt][j], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bl0, bl1);
+                  }
                 }
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-                  if (mt < mt_n) mma_tf32(acc[mt][j], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bh0, bh1);
+                for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][j], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bh0, bh1);
               }
             }
           }
         }
       }
+      a_addr += WCH * 4;
     }
-    __syncthreads();  // every warp is done with the last chunk: the ring may be refilled
-    // the next GEMM's first two chunks go in flight under this epilogue (and any rops in between)
-    if (m_pass + 128 >= M && f[RG_NEXT_WCH] >= 0) {
-      const int nn = (int)f[RG_NEXT_NPAD];
-      const int nc = (int)f[RG_NEXT_NCHUNK];
-      ring = min(2, nc);
-      for (int q = 0; q < ring; ++q) issue_chunk(c, wst, stage_floats, q % WSTAGES, f[RG_NEXT_WCH], nn, q, tid);
-    }
+  }
+  __syncthreads();  // every warp is done with the last chunk: the ring may be refilled
+  // the next GEMM's first chunks go in flight under this epilogue (and any rops in between)
+  if (last_pass && f[RG_NEXT_WCH] >= 0) {
+    ring = min(f[RG_NEXT_PF], f[RG_NEXT_NCHUNK]);
+    const float *nsrc = c.weights + f[RG_NEXT_WCH];
+    const int nn16 = f[RG_NEXT_NPAD] * (WLD / 4);
+    for (int q = 0; q < ring; ++q) issue_chunk(nsrc, wst_u, stage_bytes, nn16, q, tid);
+  }
 
-    // ---- epilogue ----
-    float *st = st_off >= 0 ? c.sm + st_off : nullptr;
+  // ---- epilogue ----
+  float *scr = wst + 2 * stage_floats;  // stage 2 is free between the main loop and the next GEMM's third chunk
+  const int st_off = f[RG_ST];
+  const bool stats = st_off >= 0;
+  if (active) {
+    const float *bias = f[RG_BIAS] >= 0 ? c.weights + f[RG_BIAS] : nullptr;
+    const int smk = f[RG_SMK];
+    float *Cp = sm + f[RG_C];
+    const int ldc = f[RG_CLD];
+    const float *Rp = f[RG_RES] >= 0 ? sm + f[RG_RES] : nullptr;
+    const int ldr = f[RG_RESLD];
+    const float *Ep = f[RG_EV] >= 0 ? sm + f[RG_EV] : nullptr;
+    const int lde = f[RG_EVLD];
+    const int pairrows = f[RG_PAIRROWS], rshift = f[RG_RPP_SHIFT], act = f[RG_ACT], st_owned = f[RG_ST_OWNED];
 #pragma unroll
-    for (int j = 0; j < NTMAX; ++j) {
+    for (int j = 0; j < NT; ++j) {
       const int tile = tile0 + j;
-      if (j >= nt_n || tile >= n_tiles) continue;
+      if (tile >= n_tiles) continue;
       const int n0 = tile * 8 + tq * 2;
       const bool v0 = n0 < N, v1 = n0 + 1 < N;
       const float b0 = (bias && v0) ? __ldg(bias + n0) : 0.f, b1 = (bias && v1) ? __ldg(bias + n0 + 1) : 0.f;
       if (smk > 0) {
         // fused soft-max over the smk (8 or 16) rows of each point, applied to the value rows RES
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          if (mt >= mt_n) continue;
+        for (int mt = 0; mt < MT; ++mt) {
           const int rbase = row0 + mt * 16;
           float s[4] = {acc[mt][j][0] + b0, acc[mt][j][1] + b1, acc[mt][j][2] + b0, acc[mt][j][3] + b1};
           float val[4];
-          val[0] = v0 ? RES.ptr[(size_t)(rbase + g) * RES.ld + n0] : 0.f;
-          val[1] = v1 ? RES.ptr[(size_t)(rbase + g) * RES.ld + n0 + 1] : 0.f;
-          val[2] = v0 ? RES.ptr[(size_t)(rbase + g + 8) * RES.ld + n0] : 0.f;
-          val[3] = v1 ? RES.ptr[(size_t)(rbase + g + 8) * RES.ld + n0 + 1] : 0.f;
+          const float *vr = Rp + (rbase + g) * ldr + n0;
+          val[0] = v0 ? vr[0] : 0.f;
+          val[1] = v1 ? vr[1] : 0.f;
+          val[2] = v0 ? vr[8 * ldr] : 0.f;
+          val[3] = v1 ? vr[8 * ldr + 1] : 0.f;
           float mx[4] = {s[0], s[1], s[2], s[3]};
           if (smk == 16) {
             mx[0] = mx[2] = fmaxf(s[0], s[2]);
@@ -291,12 +281,11 @@ __device__ void rs_gemm(const Ctx &c, const slide_rop &r, float *wst, int stage_
           for (int o = 4; o < 32; o <<= 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e) mx[e] = fmaxf(mx[e], __shfl_xor_sync(0xffffffffu, mx[e], o));
-          float ex[4], num[4], den[4];
+          float num[4], den[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            ex[e] = expf(s[e] - mx[e]);
-            num[e] = ex[e] * val[e];
-            den[e] = ex[e];
+            den[e] = expf(s[e] - mx[e]);
+            num[e] = den[e] * val[e];
           }
           if (smk == 16) {
             num[0] += num[2]; num[1] += num[3]; den[0] += den[2]; den[1] += den[3];
@@ -311,8 +300,8 @@ __device__ void rs_gemm(const Ctx &c, const slide_rop &r, float *wst, int stage_
           if (g == 0) {
             const int npts = smk == 16 ? 1 : 2;
             for (int h = 0; h < npts; ++h) {
-              const int prow = c.p0 + (rbase + h * 8) / smk;
-              float *dst = C.ptr + (size_t)prow * C.ld + n0;
+              const int prow = c.p0 + ((rbase + h * 8) >> rshift);
+              float *dst = Cp + prow * ldc + n0;
               const float o0 = num[h * 2] / den[h * 2], o1 = num[h * 2 + 1] / den[h * 2 + 1];
               if (v0) dst[0] = o0;
               if (v1) dst[1] = o1;
@@ -332,35 +321,37 @@ __device__ void rs_gemm(const Ctx &c, const slide_rop &r, float *wst, int stage_
       }
       float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        if (mt >= mt_n) continue;
+      for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int row = row0 + mt * 16 + g + h * 8;
           float x0 = acc[mt][j][h * 2] + b0, x1 = acc[mt][j][h * 2 + 1] + b1;
-          const int point = pairrows ? c.p0 + row / rpp : row;
-          if (EV.ptr) {
-            if (v0) x0 += EV.ptr[(size_t)point * EV.ld + n0];
-            if (v1) x1 += EV.ptr[(size_t)point * EV.ld + n0 + 1];
+          const int point = pairrows ? c.p0 + (row >> rshift) : row;
+          if (Ep) {
+            const float *e = Ep + point * lde + n0;
+            if (v0) x0 += e[0];
+            if (v1) x1 += e[1];
           }
-          if (RES.ptr) {
-            if (v0) x0 += RES.ptr[(size_t)row * RES.ld + n0];
-            if (v1) x1 += RES.ptr[(size_t)row * RES.ld + n0 + 1];
+          if (Rp) {
+            const float *e = Rp + row * ldr + n0;
+            if (v0) x0 += e[0];
+            if (v1) x1 += e[1];
           }
           if (act == 1) {
             x0 = fmaxf(x0, 0.f);
             x1 = fmaxf(x1, 0.f);
           }
-          if (v0) C.ptr[(size_t)row * C.ld + n0] = x0;
-          if (v1) C.ptr[(size_t)row * C.ld + n0 + 1] = x1;
+          float *d = Cp + row * ldc + n0;
+          if (v1) *reinterpret_cast<float2 *>(d) = make_float2(x0, x1);  // n0 even, ld even, base 16-byte aligned
+          else if (v0) d[0] = x0;
           const bool counted = !st_owned || (point >= c.p0 && point < c.p0 + c.npl);
-          if (st && counted) {
+          if (stats && counted) {
             if (v0) { s0 += x0; q0 += x0 * x0; }
             if (v1) { s1 += x1; q1 += x1 * x1; }
           }
         }
       }
-      if (st) {
+      if (stats) {
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) {
           s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -368,217 +359,299 @@ __device__ void rs_gemm(const Ctx &c, const slide_rop &r, float *wst, int stage_
           q0 += __shfl_xor_sync(0xffffffffu, q0, o);
           q1 += __shfl_xor_sync(0xffffffffu, q1, o);
         }
-        if (g == 0) {
-          const int ch0 = st_choff + n0;
-          if (v0 && ch0 < st_nnorm) {
-            atomicAdd(st + 2 * (ch0 / st_cg), st_w * s0);
-            atomicAdd(st + 2 * (ch0 / st_cg) + 1, st_w * q0);
-          }
-          if (v1 && ch0 + 1 < st_nnorm) {
-            atomicAdd(st + 2 * ((ch0 + 1) / st_cg), st_w * s1);
-            atomicAdd(st + 2 * ((ch0 + 1) / st_cg) + 1, st_w * q1);
-          }
-        }
+        if (g == 0) *reinterpret_cast<float4 *>(scr + (wm * NBLK_PAD + n0) * 2) = make_float4(s0, q0, s1, q1);
       }
     }
+  }
+  if (stats) {
+    __syncthreads();
+    fold_colsum(sm + st_off, scr, wgm, N, f[RG_ST_CG], f[RG_ST_NNORM], f[RG_ST_CHOFF], stw, tid);
+  }
+}
+
+template <bool PRECISE>
+__device__ void rs_gemm(const Ctx &c, const slide_rop &r, float *sm, float *wst, int stage_floats, int &ring, int tid) {
+  const int *f = r.i;
+  const int M = f[RG_M];
+  const int n_tiles = (f[RG_N] + 7) >> 3;
+  for (int m_pass = 0; m_pass < M; m_pass += 128) {
+    const int m_tiles = min(128, M - m_pass) >> 4;
+    const bool last = m_pass + 128 >= M;
+#define GP(MT_, NT_, WGM_) gemm_pass<MT_, NT_, PRECISE>(c, f, r.f[0], sm, wst, stage_floats, ring, tid, m_pass, WGM_, last)
+    if (m_tiles >= 8) {         // 4 x 4 warps, 2 row tiles each
+      const int nt = (n_tiles + 3) >> 2;
+      if (nt <= 1) GP(2, 1, 4); else if (nt == 2) GP(2, 2, 4); else if (nt == 3) GP(2, 3, 4); else GP(2, 4, 4);
+    } else if (m_tiles >= 4) {  // 4 x 4 warps
+      const int nt = (n_tiles + 3) >> 2;
+      if (nt <= 1) GP(1, 1, 4); else if (nt == 2) GP(1, 2, 4); else if (nt == 3) GP(1, 3, 4); else GP(1, 4, 4);
+    } else if (m_tiles >= 2) {  // 2 x 8 warps
+      if (n_tiles <= 8) GP(1, 1, 2); else GP(1, 2, 2);
+    } else {                    // 1 x 16 warps
+      GP(1, 1, 1);
+    }
+#undef GP
   }
   __syncthreads();
 }
 
 // ---- RS_PAIR -------------------------------------------------------------------------------------------------------
-__device__ void rs_pair(const Ctx &c, const slide_rop &r, int tid) {
-  const int64_t *f = r.i;
-  const Opnd U = resolve(c, f + RP_U), X = resolve(c, f + RP_XYZ), CT = resolve(c, f + RP_CTR), O = resolve(c, f + RP_OUT),
-             RES = resolve(c, f + RP_RES);
-  const int K = (int)f[RP_K], N = (int)f[RP_N], act = (int)f[RP_ACT];
-  const int *idx = reinterpret_cast<const int *>(c.sm + f[RP_IDX]);
-  const float *d2 = f[RP_D2] >= 0 ? c.sm + f[RP_D2] : nullptr;
-  const float *wx = wptr(c, f[RP_WX]), *wc = wptr(c, f[RP_WC]), *wd = wptr(c, f[RP_WD]), *ww = wptr(c, f[RP_WW]),
-              *bias = wptr(c, f[RP_BIAS]);
-  const int st_off = (int)f[RP_ST], st_cg = (int)f[RP_ST_CG], st_nnorm = (int)f[RP_ST_NNORM], st_choff = (int)f[RP_ST_CHOFF];
-  float *st = st_off >= 0 ? c.sm + st_off : nullptr;
+// Lanes own 4 consecutive output columns (16-byte accesses), warps own row slices; per-row scalars (neighbour index,
+// coordinates, d2, interpolation weight) are computed once into the scratch stage.
+__device__ void rs_pair(const Ctx &c, const slide_rop &r, float *sm, float *scr, int tid) {
+  const int *f = r.i;
+  const float *Up = sm + f[RP_U], *Xp = sm + f[RP_XYZ], *Ctp = sm + f[RP_CTR];
+  float *Op = sm + f[RP_OUT];
+  const float *Rp = f[RP_RES] >= 0 ? sm + f[RP_RES] : nullptr;
+  const int ldu = f[RP_ULD], ldx = f[RP_XLD], ldct = f[RP_CLD], ldo = f[RP_OLD], ldr = f[RP_RLD];
+  const int K = f[RP_K], N = f[RP_N], act = f[RP_ACT];
+  const int *idx = reinterpret_cast<const int *>(sm + f[RP_IDX]);
+  const float *d2 = f[RP_D2] >= 0 ? sm + f[RP_D2] : nullptr;
+  const float *wx = c.weights + f[RP_WX], *wc = c.weights + f[RP_WC];
+  const float *wd = f[RP_WD] >= 0 ? c.weights + f[RP_WD] : nullptr, *ww = f[RP_WW] >= 0 ? c.weights + f[RP_WW] : nullptr;
+  const float *bias = f[RP_BIAS] >= 0 ? c.weights + f[RP_BIAS] : nullptr;
+  const int st_off = f[RP_ST];
   const int warp = tid >> 5, lane = tid & 31;
-  const int rows = c.npl * K;
-  for (int n0 = 0; n0 < N; n0 += 32) {
-    const int n = n0 + lane;
-    const bool v = n < N;
-    float wxx = 0.f, wxy = 0.f, wxz = 0.f, wcx = 0.f, wcy = 0.f, wcz = 0.f, bb = 0.f, wdd = 0.f, www = 0.f;
-    if (v) {
-      wxx = __ldg(wx + n * 3); wxy = __ldg(wx + n * 3 + 1); wxz = __ldg(wx + n * 3 + 2);
-      wcx = __ldg(wc + n * 3); wcy = __ldg(wc + n * 3 + 1); wcz = __ldg(wc + n * 3 + 2);
-      if (bias) bb = __ldg(bias + n);
-      if (d2) { wdd = __ldg(wd + n); www = __ldg(ww + n); }
+  const int rows = c.npl * K;  // <= 128
+  // row table: [rows][12] = {j, xj(3), ci(3), d2, w, -, -, -}
+  float *rowtab = scr;               // 128 * 12 = 1536 floats
+  float *colsum = scr + 128 * 12;    // [8][NBLK_PAD][2] = 2176 floats
+  if (tid < rows) {
+    const int il = tid / K, k = tid - il * K;
+    const int pi = c.p0 + il;
+    const int j = idx[pi * K + k];
+    float *t = rowtab + tid * 12;
+    t[0] = __int_as_float(j);
+    t[1] = Xp[j * ldx];
+    t[2] = Xp[j * ldx + 1];
+    t[3] = Xp[j * ldx + 2];
+    t[4] = Ctp[pi * ldct];
+    t[5] = Ctp[pi * ldct + 1];
+    t[6] = Ctp[pi * ldct + 2];
+    float dd = 0.f, w = 0.f;
+    if (d2) {
+      float sum = 0.f;
+      for (int kk = 0; kk < K; ++kk) sum += 1.0f / (d2[pi * K + kk] + 1e-8f);
+      dd = d2[pi * K + k];
+      w = (1.0f / (dd + 1e-8f)) / sum;
     }
-    float s = 0.f, q = 0.f;
-    for (int lr = warp; lr < rows; lr += NW) {
-      const int il = lr / K, k = lr - il * K;
-      const int pi = c.p0 + il;
-      const int j = idx[pi * K + k];
-      const float xj0 = X.ptr[(size_t)j * X.ld], xj1 = X.ptr[(size_t)j * X.ld + 1], xj2 = X.ptr[(size_t)j * X.ld + 2];
-      const float c0 = CT.ptr[(size_t)pi * CT.ld], c1 = CT.ptr[(size_t)pi * CT.ld + 1], c2 = CT.ptr[(size_t)pi * CT.ld + 2];
-      float val = 0.f;
-      if (v) {
-        val = U.ptr[(size_t)j * U.ld + n];
-        val += xj0 * wxx + xj1 * wxy + xj2 * wxz;
-        val += c0 * wcx + c1 * wcy + c2 * wcz;
-        val += bb;
-      }
-      if (d2) {
-        float sum = 0.f;
-        for (int kk = 0; kk < K; ++kk) sum += 1.0f / (d2[pi * K + kk] + 1e-8f);
-        const float dd = d2[pi * K + k];
-        const float w = (1.0f / (dd + 1e-8f)) / sum;
-        val += dd * wdd + w * www;
-      }
-      if (v) {
-        if (RES.ptr) val += RES.ptr[(size_t)lr * RES.ld + n];
-        if (act == 1) val = fmaxf(val, 0.f);
-        O.ptr[(size_t)lr * O.ld + n] = val;
-        s += val;
-        q += val * val;
+    t[7] = dd;
+    t[8] = w;
+  }
+  __syncthreads();
+  const bool stats = st_off >= 0;
+  for (int n0 = 0; n0 < N; n0 += 128) {
+    const int n = n0 + lane * 4;
+    float wxx[4], wxy[4], wxz[4], wcx[4], wcy[4], wcz[4], bb[4], wdd[4], www[4];
+    bool v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[e] = n + e < N;
+      const int ne = v[e] ? n + e : 0;
+      wxx[e] = __ldg(wx + ne * 3); wxy[e] = __ldg(wx + ne * 3 + 1); wxz[e] = __ldg(wx + ne * 3 + 2);
+      wcx[e] = __ldg(wc + ne * 3); wcy[e] = __ldg(wc + ne * 3 + 1); wcz[e] = __ldg(wc + ne * 3 + 2);
+      bb[e] = bias ? __ldg(bias + ne) : 0.f;
+      wdd[e] = d2 ? __ldg(wd + ne) : 0.f;
+      www[e] = d2 ? __ldg(ww + ne) : 0.f;
+    }
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    if (v[0]) {
+      for (int lr = warp; lr < rows; lr += NW) {
+        const float4 t0 = *reinterpret_cast<const float4 *>(rowtab + lr * 12);
+        const float4 t1 = *reinterpret_cast<const float4 *>(rowtab + lr * 12 + 4);
+        const float t8 = rowtab[lr * 12 + 8];
+        const int j = __float_as_int(t0.x);
+        const float4 u = *reinterpret_cast<const float4 *>(Up + j * ldu + n);
+        float val[4] = {u.x, u.y, u.z, u.w};
+        float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (Rp) rs = *reinterpret_cast<const float4 *>(Rp + lr * ldr + n);
+        const float rr[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float a = val[e];
+          a += t0.y * wxx[e] + t0.z * wxy[e] + t0.w * wxz[e];
+          a += t1.x * wcx[e] + t1.y * wcy[e] + t1.z * wcz[e];
+          a += bb[e];
+          a += t1.w * wdd[e] + t8 * www[e];
+          a += rr[e];
+          if (act == 1) a = fmaxf(a, 0.f);
+          val[e] = a;
+          if (v[e]) {
+            s[e] += a;
+            q[e] += a * a;
+          }
+        }
+        float *o = Op + lr * ldo + n;
+        if (v[3]) {
+          *reinterpret_cast<float4 *>(o) = make_float4(val[0], val[1], val[2], val[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 3; ++e)
+            if (v[e]) o[e] = val[e];
+        }
       }
     }
-    if (st) {
-      const int ch = st_choff + n;
-      const bool in = v && ch < st_nnorm;
-      if (!in) s = q = 0.f;
-      // lanes of one group are adjacent when the group size is a power of two that divides the chunk start
-      if ((st_cg & (st_cg - 1)) == 0 && st_cg <= 32 && ((st_choff + n0) % st_cg) == 0) {
-        for (int o = 1; o < st_cg; o <<= 1) {
-          s += __shfl_xor_sync(0xffffffffu, s, o);
-          q += __shfl_xor_sync(0xffffffffu, q, o);
-        }
-        if (in && (lane % st_cg) == 0) {
-          atomicAdd(st + 2 * (ch / st_cg), s);
-          atomicAdd(st + 2 * (ch / st_cg) + 1, q);
-        }
-      } else if (in) {
-        atomicAdd(st + 2 * (ch / st_cg), s);
-        atomicAdd(st + 2 * (ch / st_cg) + 1, q);
+    if (stats) {
+      // 16 row slices -> 8 (warps 8..15 hand their partials to warps 0..7) -> one thread per group
+      const int nl = n - n0;  // local column 0..127
+      if (warp >= 8 && v[0]) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          *reinterpret_cast<float2 *>(colsum + ((warp - 8) * NBLK_PAD + nl + e) * 2) = make_float2(s[e], q[e]);
       }
+      __syncthreads();
+      if (warp < 8 && v[0]) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 *slot = reinterpret_cast<float2 *>(colsum + (warp * NBLK_PAD + nl + e) * 2);
+          const float2 o = *slot;
+          *slot = make_float2(o.x + s[e], o.y + q[e]);
+        }
+      }
+      __syncthreads();
+      fold_colsum(sm + st_off, colsum, 8, min(128, N - n0), f[RP_ST_CG], f[RP_ST_NNORM], f[RP_ST_CHOFF] + n0, 1.0f, tid);
+      __syncthreads();
     }
   }
   __syncthreads();
 }
 
 // ---- RS_XFORM ------------------------------------------------------------------------------------------------------
-__device__ void rs_xform(const Ctx &c, const slide_rop &r, int tid) {
-  const int64_t *f = r.i;
-  const Opnd X = resolve(c, f + RX_X);
-  const int rows = (int)f[RX_ROWS], C = (int)f[RX_C];
-  const int st_off = (int)f[RX_ST], cg = (int)f[RX_CG], nnorm = (int)f[RX_NNORM], choff = (int)f[RX_CHOFF];
-  const float *gamma = wptr(c, f[RX_GAMMA]), *beta = wptr(c, f[RX_BETA]);
-  const int relu = (int)f[RX_RELU], addmode = (int)f[RX_ADDMODE];
-  const float inv_count = r.f[0];
-  const float *st = st_off >= 0 ? c.sm + st_off : nullptr;
-  const float *add = nullptr;
-  if ((int)f[RX_ADD + RO_SPACE] != 0) {
-    const float *base = reinterpret_cast<const float *>(c.arena + f[RX_ADD + RO_OFF]);
-    const int64_t arow = addmode == 0 ? c.sample : (addmode == 1 ? c.t : 0);
-    add = base + arow * f[RX_ADD + RO_LD];
-  }
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int n0 = 0; n0 < C; n0 += 32) {
-    const int n = n0 + lane;
-    if (n >= C) continue;
-    float a = 1.f, b = 0.f;
-    const int ch = choff + n;
-    if (st && ch < nnorm) {
-      const float sum = st[2 * (ch / cg)], sq = st[2 * (ch / cg) + 1];
-      const float mean = sum * inv_count;
-      float var = sq * inv_count - mean * mean;
+// Per-column constants (scale, shift, additive vector) are computed ONCE by the first C threads into the scratch stage;
+// then lanes own 4 consecutive columns, warps own row slices.
+__device__ void rs_xform(const Ctx &c, const slide_rop &r, float *sm, float *scr, int tid) {
+  const int *f = r.i;
+  float *Xp = sm + f[RX_X];
+  const int ldx = f[RX_XLD], rows = f[RX_ROWS], C = f[RX_C];
+  float *ca = scr, *cb = scr + 640, *cadd = scr + 1280;  // C <= 640 columns
+  for (int n = tid; n < C; n += RT) {
+    float a = 1.f, b = 0.f, av = 0.f;
+    const int st_off = f[RX_ST];
+    const int ch = f[RX_CHOFF] + n;
+    if (st_off >= 0 && ch < f[RX_NNORM]) {
+      const float inv_count = r.f[0];
+      const float2 sq = *reinterpret_cast<const float2 *>(sm + st_off + 2 * (ch / f[RX_CG]));
+      const float mean = sq.x * inv_count;
+      float var = sq.y * inv_count - mean * mean;
       var = var < 0.f ? 0.f : var;
       const float rstd = 1.0f / sqrtf(var + SLIDE_GN_EPS);
-      a = rstd * __ldg(gamma + ch);
-      b = __ldg(beta + ch) - mean * a;
+      a = rstd * __ldg(c.weights + f[RX_GAMMA] + ch);
+      b = __ldg(c.weights + f[RX_BETA] + ch) - mean * a;
     }
-    const float av = add ? __ldg(add + n) : 0.f;
+    if (f[RX_ADD] >= 0) {
+      const int mode = f[RX_ADDMODE];
+      const long long arow = mode == 0 ? c.sample : (mode == 1 ? c.t : 0);
+      av = __ldg(c.arena + f[RX_ADD] + arow * f[RX_ADDLD] + n);
+    }
+    ca[n] = a;
+    cb[n] = b;
+    cadd[n] = av;
+  }
+  __syncthreads();
+  const int relu = f[RX_RELU];
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int n0 = 0; n0 < C; n0 += 128) {
+    const int n = n0 + lane * 4;
+    if (n >= C) continue;
+    const float4 a4 = *reinterpret_cast<const float4 *>(ca + n), b4 = *reinterpret_cast<const float4 *>(cb + n),
+                 d4 = *reinterpret_cast<const float4 *>(cadd + n);
+    const bool full = n + 3 < C;
     for (int row = warp; row < rows; row += NW) {
-      float v = X.ptr[(size_t)row * X.ld + n];
-      v = v * a + b;
-      if (relu) v = fmaxf(v, 0.f);
-      X.ptr[(size_t)row * X.ld + n] = v + av;
+      float *px = Xp + row * ldx + n;
+      float4 x = *reinterpret_cast<const float4 *>(px);
+      x.x = x.x * a4.x + b4.x;
+      x.y = x.y * a4.y + b4.y;
+      x.z = x.z * a4.z + b4.z;
+      x.w = x.w * a4.w + b4.w;
+      if (relu) {
+        x.x = fmaxf(x.x, 0.f);
+        x.y = fmaxf(x.y, 0.f);
+        x.z = fmaxf(x.z, 0.f);
+        x.w = fmaxf(x.w, 0.f);
+      }
+      x.x += d4.x;
+      x.y += d4.y;
+      x.z += d4.z;
+      x.w += d4.w;
+      if (full) {
+        *reinterpret_cast<float4 *>(px) = x;
+      } else {
+        px[0] = x.x;
+        if (n + 1 < C) px[1] = x.y;
+        if (n + 2 < C) px[2] = x.z;
+      }
     }
   }
   __syncthreads();
 }
 
 // ---- RS_KNN --------------------------------------------------------------------------------------------------------
-__device__ void rs_knn(const Ctx &c, const slide_rop &r, int tid) {
-  const int64_t *f = r.i;
-  const Opnd Q = resolve(c, f + RK_Q), R = resolve(c, f + RK_REF);
-  const int P1 = (int)f[RK_P1], P2 = (int)f[RK_P2], K = (int)f[RK_K];
-  int *idx = reinterpret_cast<int *>(c.sm + f[RK_IDX]);
-  float *d2 = f[RK_D2] >= 0 ? c.sm + f[RK_D2] : nullptr;
-  if (tid < P1) {
-    const float qx = Q.ptr[(size_t)tid * Q.ld], qy = Q.ptr[(size_t)tid * Q.ld + 1], qz = Q.ptr[(size_t)tid * Q.ld + 2];
-    float bd[16];
-    int bi[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      bd[k] = INFINITY;
-      bi[k] = 0;
+// One thread per (query, reference) pair: its rank among the query's distances (strict <, ties by ascending index -- the
+// order pytorch3d's sorted insertion produces) is the slot it is written to.
+__device__ void rs_knn(const Ctx &c, const slide_rop &r, float *sm, float *scr, int tid) {
+  const int *f = r.i;
+  const float *Q = sm + f[RK_Q], *R = sm + f[RK_REF];
+  const int ldq = f[RK_QLD], ldr = f[RK_RLD];
+  const int P1 = f[RK_P1], P2 = f[RK_P2], K = f[RK_K];
+  int *idx = reinterpret_cast<int *>(sm + f[RK_IDX]);
+  float *d2 = f[RK_D2] >= 0 ? sm + f[RK_D2] : nullptr;
+  float *dist = scr;  // [P1][P2] <= 16 x 32
+  const int q = tid / P2, p = tid - q * P2;
+  float d = 0.f;
+  if (tid < P1 * P2) {
+    d = sumsq3_p3d(Q[q * ldq] - R[p * ldr], Q[q * ldq + 1] - R[p * ldr + 1], Q[q * ldq + 2] - R[p * ldr + 2]);
+    dist[tid] = d;
+  }
+  __syncthreads();
+  if (tid < P1 * P2) {
+    int rank = 0;
+    for (int o = 0; o < P2; ++o) {
+      const float od = dist[q * P2 + o];
+      rank += (od < d || (od == d && o < p)) ? 1 : 0;
     }
-    for (int p = 0; p < P2; ++p) {
-      const float d = sumsq3_p3d(qx - R.ptr[(size_t)p * R.ld], qy - R.ptr[(size_t)p * R.ld + 1], qz - R.ptr[(size_t)p * R.ld + 2]);
-      float cd = d;
-      int ci = p;
-#pragma unroll
-      for (int s = 0; s < 16; ++s) {
-        const bool sw = cd < bd[s];
-        const float td = bd[s];
-        const int ti = bi[s];
-        bd[s] = sw ? cd : td;
-        bi[s] = sw ? ci : ti;
-        cd = sw ? td : cd;
-        ci = sw ? ti : ci;
-      }
+    if (rank < K) {
+      idx[q * K + rank] = p;
+      if (d2) d2[q * K + rank] = d;
     }
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-      if (k < K) {
-        idx[tid * K + k] = bi[k];
-        if (d2) d2[tid * K + k] = bd[k];
-      }
   }
   __syncthreads();
 }
 
 // ---- RS_COPY -------------------------------------------------------------------------------------------------------
-__device__ void rs_copy(const Ctx &c, const slide_rop &r, int tid) {
-  const int64_t *f = r.i;
-  const Opnd S = resolve(c, f + RC_SRC), D = resolve(c, f + RC_DST);
-  int rows = (int)f[RC_ROWS];
-  const int cols = (int)f[RC_COLS];
-  int r0 = 0;
+__device__ void rs_copy(const Ctx &c, const slide_rop &r, float *sm, int tid) {
+  const int *f = r.i;
+  const float *S = f[RC_SRC_G] ? c.arena + f[RC_SRC] + (long long)c.sample * f[RC_SSTRIDE] : sm + f[RC_SRC];
+  float *D = f[RC_DST_G] ? c.arena + f[RC_DST] + (long long)c.sample * f[RC_DSTRIDE] : sm + f[RC_DST];
+  const int lds = f[RC_SLD], ldd = f[RC_DLD], cols = f[RC_COLS];
+  int rows = f[RC_ROWS], r0 = 0;
   if (f[RC_OWNED]) {
-    r0 = c.p0 * (int)f[RC_RPP];
-    rows = c.npl * (int)f[RC_RPP];
+    r0 = c.p0;
+    rows = c.npl;
   }
   for (int e = tid; e < rows * cols; e += RT) {
     const int row = r0 + e / cols, col = e % cols;
-    D.ptr[(size_t)row * D.ld + col] = S.ptr[(size_t)row * S.ld + col];
+    D[row * ldd + col] = S[row * lds + col];
   }
   __syncthreads();
 }
 
 // ---- RS_DDPM -------------------------------------------------------------------------------------------------------
-__device__ void rs_ddpm(const Ctx &c, const slide_rop &r, int tid) {
-  const int64_t *f = r.i;
-  const Opnd X = resolve(c, f + RD_X), XG = resolve(c, f + RD_XG), E = resolve(c, f + RD_EPS), X0C = resolve(c, f + RD_X0C),
-             MK = resolve(c, f + RD_MASK);
-  const int mode = (int)f[RD_MODE], ncols = (int)f[RD_NCOLS], col0 = (int)f[RD_COL0];
-  const int64_t brows = f[RD_BROWS];  // rows of the whole batch (B * NP)
-  const float *tab = wptr(c, f[RD_TABLE]) + (size_t)c.t * 8;
-  const float *noise = reinterpret_cast<const float *>(c.arena + f[RD_NOISE]);
-  const float clamp = r.f[0];
+__device__ void rs_ddpm(const Ctx &c, const slide_rop &r, float *sm, int tid) {
+  const int *f = r.i;
+  const float *X = sm + f[RD_X], *E = sm + f[RD_EPS];
+  float *XG = c.arena + f[RD_XG] + (long long)c.sample * f[RD_XGSTRIDE];
+  const float *X0C = f[RD_X0C] >= 0 ? c.arena + f[RD_X0C] + (long long)c.sample * f[RD_X0CSTRIDE] : nullptr;
+  const float *MK = f[RD_MASK] >= 0 ? c.arena + f[RD_MASK] + (long long)c.sample * f[RD_MASKSTRIDE] : nullptr;
+  const int mode = f[RD_MODE], ncols = f[RD_NCOLS], col0 = f[RD_COL0];
+  const long long brows = f[RD_BROWS];  // rows of the whole batch (B * NP)
   const int t = c.t;
+  const float *tab = c.weights + f[RD_TABLE] + t * 8;
+  const float *noise = c.arena + f[RD_NOISE] + ((long long)t * brows + (long long)c.sample * c.np) * ncols;
+  const float clamp = r.f[0];
   for (int e = tid; e < c.npl * ncols; e += RT) {
     const int row = c.p0 + e / ncols, col = e % ncols;
     if (col < col0) continue;
-    const int64_t grow = (int64_t)c.sample * c.np + row;
-    const float xv = X.ptr[(size_t)row * X.ld + col], ev = E.ptr[(size_t)row * E.ld + col];
-    const float nz = noise[((size_t)t * brows + grow) * ncols + col];
+    const float xv = X[row * f[RD_XLD] + col], ev = E[row * f[RD_ELD] + col];
+    const float nz = noise[row * ncols + col];
     float res;
     if (mode == 0) {
       res = __fdiv_rn(__fsub_rn(xv, __fmul_rn(tab[0], ev)), tab[1]);
@@ -588,15 +661,15 @@ __device__ void rs_ddpm(const Ctx &c, const slide_rop &r, int tid) {
     } else {
       float x0 = __fsub_rn(__fmul_rn(tab[0], xv), __fmul_rn(tab[1], ev));
       if (clamp > 0.f) x0 = fminf(fmaxf(x0, -clamp), clamp);
-      if (X0C.ptr) {
-        const float m = MK.ptr[row];
-        x0 = __fadd_rn(__fmul_rn(x0, m), __fmul_rn(X0C.ptr[(size_t)row * X0C.ld + col], __fsub_rn(1.0f, m)));
+      if (X0C) {
+        const float m = MK[row];
+        x0 = __fadd_rn(__fmul_rn(x0, m), __fmul_rn(X0C[row * f[RD_X0CLD] + col], __fsub_rn(1.0f, m)));
       }
       const float mean = __fadd_rn(__fmul_rn(tab[2], x0), __fmul_rn(tab[3], xv));
       const float m = t == 0 ? 0.f : 1.f;
       res = __fadd_rn(mean, __fmul_rn(__fmul_rn(m, tab[4]), nz));
     }
-    XG.ptr[(size_t)row * XG.ld + col] = res;
+    XG[row * f[RD_XGLD] + col] = res;
   }
   __syncthreads();
 }
@@ -608,7 +681,6 @@ __global__ void __launch_bounds__(RT, 1) resident_kernel(const ResArgs a) {
   __shared__ slide_rop rop_s[2];
   const int tid = threadIdx.x;
   Ctx c;
-  c.sm = sm;
   c.arena = a.arena;
   c.weights = a.weights;
   c.cl = CL;
@@ -617,7 +689,8 @@ __global__ void __launch_bounds__(RT, 1) resident_kernel(const ResArgs a) {
   c.np = a.plan.np;
   c.npl = a.plan.np / CL;
   c.p0 = c.rank * c.npl;
-  c.t = *reinterpret_cast<const volatile int *>(a.arena + a.plan.step_off) - 1;
+  int *step_ptr = reinterpret_cast<int *>(reinterpret_cast<char *>(a.arena) + a.plan.step_off);
+  c.t = *reinterpret_cast<const volatile int *>(step_ptr) - 1;
   float *wst = sm + a.plan.wstage_off;
   const int stage_floats = a.plan.wstage_floats;
   int ring = 0;  // chunks of the next GEMM already in flight
@@ -629,20 +702,21 @@ __global__ void __launch_bounds__(RT, 1) resident_kernel(const ResArgs a) {
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // every CTA of the cluster is resident before any remote access
 
-  for (int ri = 0; ri < a.n_rops; ++ri) {
+  const int n_rops = a.n_rops;
+  for (int ri = 0; ri < n_rops; ++ri) {
     const slide_rop &r = rop_s[ri & 1];
-    if (ri + 1 < a.n_rops && tid < ROP_WORDS)  // next record (visible after this rop's trailing barrier)
+    if (ri + 1 < n_rops && tid < ROP_WORDS)  // next record (visible after this rop's trailing barrier)
       reinterpret_cast<uint32_t *>(&rop_s[(ri + 1) & 1])[tid] =
           reinterpret_cast<const uint32_t *>(a.rops + ri + 1)[tid];
     switch (r.kind) {
-      case RS_COPY: rs_copy(c, r, tid); break;
-      case RS_KNN: rs_knn(c, r, tid); break;
-      case RS_GEMM: rs_gemm<PRECISE>(c, r, wst, stage_floats, ring, tid); break;
-      case RS_PAIR: rs_pair(c, r, tid); break;
-      case RS_XFORM: rs_xform(c, r, tid); break;
+      case RS_GEMM: rs_gemm<PRECISE>(c, r, sm, wst, stage_floats, ring, tid); break;
+      case RS_XFORM: rs_xform(c, r, sm, wst + 2 * stage_floats, tid); break;
+      case RS_PAIR: rs_pair(c, r, sm, wst + stage_floats, tid); break;  // stages 1 + 2
+      case RS_COPY: rs_copy(c, r, sm, tid); break;
+      case RS_KNN: rs_knn(c, r, sm, wst + 2 * stage_floats, tid); break;
       case RS_STATSX: {
         // partial sums of every CTA are final -> totals (separate buffer: partials are never rewritten)
-        const int src = (int)r.i[RT_ST], dst = (int)r.i[RT_DST], n = (int)r.i[RT_NFLOATS];
+        const int src = r.i[RT_ST], dst = r.i[RT_DST], n = r.i[RT_NFLOATS];
         if (CL > 1) cluster_sync_all(); else __syncthreads();
         if (tid < n) {
           float v = sm[src + tid];
@@ -659,12 +733,12 @@ __global__ void __launch_bounds__(RT, 1) resident_kernel(const ResArgs a) {
       case RS_CSYNC:
         if (CL > 1) cluster_sync_all(); else __syncthreads();
         break;
-      case RS_DDPM: rs_ddpm(c, r, tid); break;
+      case RS_DDPM: rs_ddpm(c, r, sm, tid); break;
       case RS_SPILL:
       case RS_FILL: {
         float4 *s4 = reinterpret_cast<float4 *>(sm + r.i[RL_SMEM]);
-        float4 *g4 = reinterpret_cast<float4 *>(a.scratch + (size_t)blockIdx.x * a.plan.scratch_bytes + r.i[RL_SCRATCH]);
-        const int n4 = (int)(r.i[RL_NFLOATS] / 4);
+        float4 *g4 = reinterpret_cast<float4 *>(a.scratch + (size_t)blockIdx.x * (a.plan.scratch_bytes / 4) + r.i[RL_SCRATCH]);
+        const int n4 = r.i[RL_NFLOATS] / 4;
         if (r.kind == RS_SPILL)
           for (int i = tid; i < n4; i += RT) g4[i] = s4[i];
         else
@@ -684,7 +758,7 @@ __global__ void __launch_bounds__(RT, 1) resident_kernel(const ResArgs a) {
     __threadfence();
     const int prev = atomicAdd(a.done, 1);
     if (prev == (int)gridDim.x - 1) {
-      *reinterpret_cast<volatile int *>(a.arena + a.plan.step_off) = c.t;
+      *reinterpret_cast<volatile int *>(step_ptr) = c.t;
       *a.done = 0;
       __threadfence();
     }
@@ -698,7 +772,7 @@ struct ResidentPlan {
   slide_resident_plan hdr;
   slide_rop *rops = nullptr;  // device
   int n_rops = 0;
-  char *scratch = nullptr;
+  float *scratch = nullptr;
   int *done = nullptr;
   size_t smem_bytes = 0;
 };
@@ -711,15 +785,17 @@ void resident_free(ResidentPlan *p) {
   delete p;
 }
 
+constexpr int RES_MAX_DYN_SMEM = 227 * 1024 - (int)sizeof(slide_rop) * 2 - 64;
+
 int resident_create(const slide_resident_plan *hdr, const slide_rop *rops, int n_rops, ResidentPlan **out) {
   if (!hdr || !rops || n_rops <= 0 || !out) return SLIDE_ERR_INVALID;
-  if (hdr->cluster != 1 && hdr->cluster != 2 && hdr->cluster != 4) return SLIDE_ERR_UNSUPPORTED;
+  if (hdr->cluster != 2 && hdr->cluster != 4) return SLIDE_ERR_UNSUPPORTED;
   if (hdr->np % hdr->cluster) return SLIDE_ERR_INVALID;
   ResidentPlan *p = new ResidentPlan();
   p->hdr = *hdr;
   p->n_rops = n_rops;
   p->smem_bytes = (size_t)hdr->smem_floats * 4;
-  if (p->smem_bytes > 227 * 1024 - sizeof(slide_rop) * 2 - 64) {
+  if (p->smem_bytes > (size_t)RES_MAX_DYN_SMEM) {
     delete p;
     return SLIDE_ERR_UNSUPPORTED;
   }
@@ -744,7 +820,7 @@ static int launch_resident_t(const ResidentPlan *p, const ResArgs &a, cudaStream
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
   auto kern = resident_kernel<CL, PRECISE>;
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)sizeof(slide_rop) * 2 - 64);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_MAX_DYN_SMEM);
     if (e != cudaSuccess) return cuda_rc(e);
     configured[dev] = true;
   }
@@ -770,14 +846,13 @@ int resident_launch(const ResidentPlan *p, char *arena, const char *weights, cud
   ResArgs a;
   a.rops = p->rops;
   a.n_rops = p->n_rops;
-  a.arena = arena;
-  a.weights = weights;
+  a.arena = reinterpret_cast<float *>(arena);
+  a.weights = reinterpret_cast<const float *>(weights);
   a.scratch = p->scratch;
   a.done = p->done;
   a.plan = p->hdr;
   const bool pr = p->hdr.precise != 0;
   switch (p->hdr.cluster) {
-    case 1: return pr ? launch_resident_t<1, true>(p, a, st) : launch_resident_t<1, false>(p, a, st);
     case 2: return pr ? launch_resident_t<2, true>(p, a, st) : launch_resident_t<2, false>(p, a, st);
     case 4: return pr ? launch_resident_t<4, true>(p, a, st) : launch_resident_t<4, false>(p, a, st);
   }

@@ -31,12 +31,12 @@ RCONST, RENUM, RV = P._parse_header(_HDR, r"SLIDE_R\w+")
 NI, NF = RCONST["SLIDE_ROP_NI"], RCONST["SLIDE_ROP_NF"]
 WCH, WPAD, NBLK, WSTAGES = RCONST["SLIDE_RES_WCHUNK"], RCONST["SLIDE_RES_WPAD"], RCONST["SLIDE_RES_NBLK"], RCONST["SLIDE_RES_WSTAGES"]
 WLD = WCH + WPAD
-ROP_DTYPE = np.dtype([("kind", "<i4"), ("f", "<f4", (NF,)), ("i", "<i8", (NI,))])
+ROP_DTYPE = np.dtype([("kind", "<i4"), ("f", "<f4", (NF,)), ("i", "<i4", (NI,))])
 PLAN_DTYPE = np.dtype([("first", "<i4"), ("count", "<i4"), ("cluster", "<i4"), ("np", "<i4"), ("smem_floats", "<i4"),
                        ("stats_off", "<i4"), ("stats_floats", "<i4"), ("wstage_off", "<i4"), ("wstage_floats", "<i4"),
                        ("scratch_bytes", "<i4"), ("step_off", "<i8"), ("precise", "<i4"), ("batch", "<i4"),
                        ("reserved", "<i4", (2,))])
-assert ROP_DTYPE.itemsize == 16 + 8 * NI and PLAN_DTYPE.itemsize == 64
+assert ROP_DTYPE.itemsize == 16 + 4 * NI and PLAN_DTYPE.itemsize == 64
 RKIND = RENUM["slide_rop_kind"]
 SMEM_LIMIT_FLOATS = (227 * 1024 - 2 * ROP_DTYPE.itemsize - 64) // 4
 STAGE_FLOATS = (NBLK + 8) * WLD
@@ -74,6 +74,12 @@ def _ld_smem(C):
     while ld % 8 != 4:
         ld += 4
     return ld
+
+
+def _log2(v):
+    if v < 1 or v & (v - 1):
+        raise Unsupported("%d rows per point (a power of two is required)" % v)
+    return int(v).bit_length() - 1
 
 
 def tf32_rna(a):
@@ -295,7 +301,7 @@ class Planner(object):
         dst = self._opnd(rop, "RC_DST", f["CP_DST"], write=True)
         if src.level != "point" or dst.level != "point":
             raise Unsupported("COPY_COLS of pair-level tensors")
-        rop.i.update(RC_ROWS=self.np, RC_COLS=f["CP_NCOLS"], RC_OWNED=0, RC_RPP=1, RC_PUBLISH=0)
+        rop.i.update(RC_ROWS=self.np, RC_COLS=f["CP_NCOLS"], RC_OWNED=0)
         self._emit(rop)
 
     def _lower_knn(self, f, fl, note, loads):
@@ -356,11 +362,11 @@ class Planner(object):
             if rows % 16 or (rows > 128 and rows % 128) or (rows < 128 and rows not in (16, 32, 64)):
                 raise Unsupported("GEMM over %d resident rows" % rows)
             buf, npad, nchunk = pack_weight(w[n0:n0 + nb], self.precise)
-            rop.i.update(RG_M=rows, RG_K=K, RG_N=nb, RG_PAIRROWS=int(pair), RG_RPP=a_rt.rpp,
+            rop.i.update(RG_M=rows, RG_K=K, RG_N=nb, RG_PAIRROWS=int(pair), RG_RPP_SHIFT=_log2(a_rt.rpp),
                          RG_WCH=self.b.weight(buf.reshape(-1)), RG_NCHUNK=nchunk, RG_NPAD=npad,
                          RG_BIAS=f["GEMM_BIAS_W"] + 4 * n0 if f["GEMM_BIAS_W"] >= 0 else -1, RG_ACT=f["GEMM_ACT"],
                          RG_ST_CG=f["GEMM_ST_CG"], RG_ST_NNORM=f["GEMM_ST_NNORM"], RG_ST_CHOFF=f["GEMM_ST_CHOFF"] + n0,
-                         RG_ST_OWNED=0, RG_SMK=smk, RG_NEXT_WCH=-1, RG_NEXT_NPAD=0, RG_NEXT_NCHUNK=0)
+                         RG_ST_OWNED=0, RG_SMK=smk, RG_NEXT_WCH=-1, RG_NEXT_NPAD=0, RG_NEXT_NCHUNK=0, RG_NEXT_PF=0)
             rop.f[0] = float(f["GEMM_ST_WEIGHT"])
             if smk:
                 if c_rt.level != "point" or not pair or a_rt.rpp != smk:
@@ -449,7 +455,7 @@ class Planner(object):
             rop.touch.append(rt)
             if rt.level != "point":
                 raise Unsupported("external pair-level input %s" % rt.name)
-            rop.i.update(RC_ROWS=self.np, RC_COLS=base.C, RC_OWNED=0, RC_RPP=1, RC_PUBLISH=0)
+            rop.i.update(RC_ROWS=self.np, RC_COLS=base.C, RC_OWNED=0)
             head.append(rop)
         for rt in self.rt.values():
             if not (rt.external and getattr(rt, "smem_written", False)):
@@ -462,7 +468,7 @@ class Planner(object):
             rop.ops["RC_SRC"] = ("smem", rt, 0)
             rop.ops["RC_DST"] = ("arena_s", base.off, base.ld, base.R * base.ld * 4)
             rop.touch.append(rt)
-            rop.i.update(RC_ROWS=self.np, RC_COLS=base.C, RC_OWNED=1, RC_RPP=1, RC_PUBLISH=0)
+            rop.i.update(RC_ROWS=self.np, RC_COLS=base.C, RC_OWNED=1)
             tail.append(rop)
         # 2. STATSX after the last producer of every partial statistics buffer
         body = []
@@ -481,9 +487,12 @@ class Planner(object):
         # a DDPM update must come before the stores of the shadows it reads?  (it writes x in the arena directly)
         self.rops = head + body + tail
         # 3. the "next GEMM" prefetch chain
-        gemms = [r for r in self.rops if r.kind == "RS_GEMM"]
-        for a, nxt in zip(gemms, gemms[1:]):
-            a.i.update(RG_NEXT_WCH=nxt.i["RG_WCH"], RG_NEXT_NPAD=nxt.i["RG_NPAD"], RG_NEXT_NCHUNK=nxt.i["RG_NCHUNK"])
+        gi = [i for i, r in enumerate(self.rops) if r.kind == "RS_GEMM"]
+        for ia, ib in zip(gi, gi[1:]):
+            a, nxt = self.rops[ia], self.rops[ib]
+            between_pair = any(r.kind == "RS_PAIR" for r in self.rops[ia + 1:ib])  # RS_PAIR uses ring stages 1 + 2
+            a.i.update(RG_NEXT_WCH=nxt.i["RG_WCH"], RG_NEXT_NPAD=nxt.i["RG_NPAD"], RG_NEXT_NCHUNK=nxt.i["RG_NCHUNK"],
+                       RG_NEXT_PF=1 if between_pair else 2)
         # 4. shared-memory layout
         self._allocate()
 
@@ -616,30 +625,65 @@ class Planner(object):
         self.scratch_bytes = (scratch_cur + 255) // 256 * 256
         self.smem_floats = (self.peak + 8 + 3) // 4 * 4
 
+    # operand base name -> (offset field, stride field, [is-global field, sample-stride field])
+    _OPERANDS = {
+        "RG_A": ("RG_A", "RG_ALD"), "RG_C": ("RG_C", "RG_CLD"), "RG_EV": ("RG_EV", "RG_EVLD"), "RG_RES": ("RG_RES", "RG_RESLD"),
+        "RP_U": ("RP_U", "RP_ULD"), "RP_XYZ": ("RP_XYZ", "RP_XLD"), "RP_CTR": ("RP_CTR", "RP_CLD"), "RP_OUT": ("RP_OUT", "RP_OLD"),
+        "RP_RES": ("RP_RES", "RP_RLD"), "RX_X": ("RX_X", "RX_XLD"), "RX_ADD": ("RX_ADD", "RX_ADDLD"),
+        "RK_Q": ("RK_Q", "RK_QLD"), "RK_REF": ("RK_REF", "RK_RLD"),
+        "RC_SRC": ("RC_SRC", "RC_SLD", "RC_SRC_G", "RC_SSTRIDE"), "RC_DST": ("RC_DST", "RC_DLD", "RC_DST_G", "RC_DSTRIDE"),
+        "RD_X": ("RD_X", "RD_XLD"), "RD_EPS": ("RD_EPS", "RD_ELD"), "RD_XG": ("RD_XG", "RD_XGLD", None, "RD_XGSTRIDE"),
+        "RD_X0C": ("RD_X0C", "RD_X0CLD", None, "RD_X0CSTRIDE"), "RD_MASK": ("RD_MASK", None, None, "RD_MASKSTRIDE"),
+    }
+    # byte offsets into the weight blob / the arena that the record carries as float indices
+    _W_BYTES = ("RG_WCH", "RG_BIAS", "RG_NEXT_WCH", "RP_WX", "RP_WC", "RP_WD", "RP_WW", "RP_BIAS", "RX_GAMMA", "RX_BETA", "RD_TABLE")
+    _A_BYTES = ("RD_NOISE",)
+
     def _bind(self, rop):
-        """Resolve symbolic operands to the numbers of the slide_rop record."""
+        """Resolve symbolic operands to the numbers of the slide_rop record (32-bit float indices, -1 = absent)."""
         vals = dict(rop.i)
         for field, o in rop.ops.items():
             if field.endswith("#"):
                 vals[field[:-1]] = -1 if o is None else o.off
                 continue
-            base = RV[field]
+            spec = self._OPERANDS[field]
+            off_f, ld_f = spec[0], spec[1]
+            g_f = spec[2] if len(spec) > 2 else None
+            ss_f = spec[3] if len(spec) > 3 else None
+            off, ld, is_g, ss = -1, 0, 0, 0
             if o is None:
-                quad = (0, 0, 0, 0)
+                pass
             elif o[0] == "smem":
                 rt, col = o[1], o[2]
-                quad = (1, rt.off + col, rt.ld, 0)
-            elif o[0] == "arena_s":
-                quad = (2, o[1], o[2], o[3])
-            elif o[0] == "arena":
-                quad = (3, o[1], o[2], 0)
+                off, ld = rt.off + col, rt.ld
+                if len(spec) > 2 and g_f is None:
+                    raise Unsupported("%s must live in the arena" % field)
+            elif o[0] in ("arena_s", "arena"):
+                assert o[1] % 4 == 0 and o[3] % 4 == 0
+                off, ld, is_g, ss = o[1] // 4, o[2], 1, o[3] // 4
+                if len(spec) == 2 and field != "RX_ADD":
+                    raise Unsupported("%s must live in shared memory" % field)
             else:
                 raise AssertionError(o)
-            for j, v in enumerate(quad):
-                vals[(base, j)] = v
+            vals[off_f] = off
+            if ld_f is not None:
+                vals[ld_f] = ld
+            if g_f is not None:
+                vals[g_f] = is_g
+            if ss_f is not None:
+                vals[ss_f] = ss
         for field, (key, which) in rop.stats_sym.items():
             s = self.stats[key]
             vals[field] = s["off_t"] if which == "total" else s["off_p"]
+        for k in self._W_BYTES + self._A_BYTES:
+            if k in vals and vals[k] >= 0:
+                assert vals[k] % 4 == 0
+                vals[k] //= 4
+        if rop.kind in ("RS_SPILL", "RS_FILL"):
+            vals["RL_SCRATCH"] //= 4
+        for k, v in vals.items():
+            if not (-2 ** 31 <= int(v) < 2 ** 31):
+                raise Unsupported("offset %s = %d does not fit 32 bits" % (k, v))
         return vals
 
     # ---- output --------------------------------------------------------------------------------------------------------
@@ -647,10 +691,9 @@ class Planner(object):
         rec = np.zeros(len(self.final), dtype=ROP_DTYPE)
         for i, rop in enumerate(self.final):
             rec[i]["kind"] = RKIND[rop.kind]
-            vals = rop.bound if hasattr(rop, "bound") else dict(rop.i)
+            vals = rop.bound if hasattr(rop, "bound") else self._bind(rop)
             for key, v in vals.items():
-                idx = key[0] + key[1] if isinstance(key, tuple) else RV[key]
-                rec[i]["i"][idx] = int(v)
+                rec[i]["i"][RV[key]] = int(v)
             for j, v in enumerate(rop.f):
                 rec[i]["f"][j] = v
         hdr = np.zeros(1, dtype=PLAN_DTYPE)

@@ -1,5 +1,5 @@
 """Time one position-DDPM step as a sample-resident kernel (clusters of 2 / 4, TF32 / 3xTF32) next to the per-record
-executor.  usage: python tools/time_resident.py [B]"""
+executor.  usage: python tools/time_resident.py [B] [cluster:precise,...]"""
 import os
 import sys
 
@@ -17,7 +17,10 @@ def main():
     d = pos["diffusion_config"]
     sd = weights.random_state_dict(weights.load_json("schema_position_ddpm.json"), 1)
     table = engine.position_table(d["T"], d["beta_0"], d["beta_T"])
-    for cluster, precise in ((4, False), (2, False), (4, True), (0, False)):
+    configs = ((4, False), (2, False), (4, True), (0, False))
+    if len(sys.argv) > 2:  # e.g. "4:0,2:0"
+        configs = tuple((int(c.split(":")[0]), bool(int(c.split(":")[1]))) for c in sys.argv[2].split(","))
+    for cluster, precise in configs:
         b, h = engine.build_ddpm(pos["pointnet_config"], sd, B, 1000, table, 0,
                                  resident=dict(cluster=cluster, precise=precise) if cluster else None)
         prog = Program(b)
