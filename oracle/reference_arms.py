@@ -1,0 +1,189 @@
+"""The reference's OWN sampling code timed on this box -- baselines for bench.py (test / measurement infrastructure,
+never imported by slide_b200/).
+
+Two arms, both driving the UNMODIFIED python of SLIDE-3D/SLIDE mirrored under baseline/_ref (baseline/fetch_reference.py):
+  util.sampling (pointnet2/util.py:197-259), LatentDiffusion.denoise_and_reconstruct (diffusion_utils/diffusion.py:346-404),
+  PointNet2CloudCondition / PointAutoencoder (models/*.py) and the reference's `pointnet2_ops` python package.
+
+  cpu   "the reference's CPU path": the native ops the reference only has for CUDA (`pointnet2_ops._ext`) and pytorch3d
+        (not installed anywhere offline) are supplied by the C oracle (oracle/ops.py); everything above them is the
+        reference's code on CPU tensors with all host threads.  `Tensor.cuda()` / `.to(cuda)` are no-ops here.
+        kind = "reference".  Without the mirror the bit-identical port oracle/ref_model.py is timed: kind = "port".
+  gpu   "the reference's eager GPU path on the same B200": `pointnet2_ops._ext` = the reference's own CUDA extension
+        compiled for sm_100a (oracle/_ref, oracle/build_ref.py); pytorch3d's ops = slide_b200's drop-in (pytorch3d is
+        not installable offline -- stated in the result); torch eager with its defaults (cuDNN TF32).
+
+Both time a BOUNDED sample (K steps of each DDPM at a reduced batch + one decode) through the reference's own loops
+(`use_a_precomputed_XT` / `n_steps` are the reference's parameters for partial chains) and scale to 1000 + 1000 steps.
+usage: python -m oracle.reference_arms cpu|gpu [--budget SECONDS] [--batch B] [--category airplane]   -> one JSON line
+"""
+import argparse
+import copy
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+MIRROR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def mirror_available():
+    return os.path.isdir(os.path.join(MIRROR, "pointnet2", "models"))
+
+
+def _build_reference_models(cfg, device):
+    """The reference's modules from the shipped hyper-parameters, random-init weights with the checkpoint schema."""
+    import torch
+    from models.pointnet2_with_pcld_condition import PointNet2CloudCondition
+    from models.autoencoder import PointAutoencoder
+    from slide_b200 import pipeline
+    sds = pipeline.default_state_dicts()
+    pos = PointNet2CloudCondition(copy.deepcopy(cfg["position_ddpm"]["pointnet_config"])).eval()
+    pos.load_state_dict(sds["position"], strict=True)
+    lat = PointNet2CloudCondition(copy.deepcopy(cfg["latent_ddpm"]["pointnet_config"])).eval()
+    lat.load_state_dict(sds["latent"], strict=True)
+    aec = cfg["autoencoder"]
+    ae = PointAutoencoder(copy.deepcopy(aec["encoder"]), copy.deepcopy(aec["decoders"]),
+                          apply_kl_regularization=aec["apply_kl_regularization"], kl_weight=aec["kl_weight"]).eval()
+    ae.load_state_dict(sds["autoencoder"], strict=True)
+    return pos.to(device), lat.to(device), ae.to(device)
+
+
+def _time_reference_loops(cfg, B, K, device, sync):
+    """K steps of util.sampling, K steps + decode of LatentDiffusion.denoise_and_reconstruct, one decode alone."""
+    import torch
+    import util as ref_util
+    from diffusion_utils.diffusion import LatentDiffusion
+    pos, lat, ae = _build_reference_models(cfg, device)
+    d = cfg["position_ddpm"]["diffusion_config"]
+    dh = ref_util.calc_diffusion_hyperparams(d["T"], d["beta_0"], d["beta_T"])
+    for key in ("Alpha", "Alpha_bar", "Sigma"):
+        dh[key] = dh[key].to(device)
+    label = torch.full((B,), int(cfg["label"]), dtype=torch.long, device=device)
+    ld = LatentDiffusion(copy.deepcopy(cfg["latent_ddpm"]["standard_diffusion_config"]), ae, device=device)
+    kp = (torch.rand(B, 16, 3) - 0.5).to(device)
+    out = {}
+    with torch.no_grad():
+        def run_pos(k):
+            return ref_util.sampling(pos, (B, 16, 3), dh, label=label, verbose=False, print_every_n_steps=10 ** 9,
+                                     use_a_precomputed_XT=True, step=k, XT=torch.zeros(B, 16, 3, device=device))
+
+        def run_lat(k):
+            return ld.denoise_and_reconstruct(B, lat, 3, (16, 3 + cfg["latent_ddpm"]["pointnet_config"]["in_fea_dim"]),
+                                              label=label, n_steps=k, keypoint=kp)
+
+        run_pos(1)
+        run_lat(1)  # warm-up (includes one decode)
+        sync()
+        t0 = time.time()
+        run_pos(K)
+        sync()
+        out["pos_s_per_step"] = (time.time() - t0) / K
+        feat = torch.randn(B, 16, cfg["latent_ddpm"]["pointnet_config"]["in_fea_dim"], device=device)
+        t0 = time.time()
+        ae.decode(kp, feat, label=label)
+        sync()
+        out["decode_s"] = time.time() - t0
+        t0 = time.time()
+        run_lat(K)
+        sync()
+        out["lat_s_per_step"] = max(time.time() - t0 - out["decode_s"], 1e-9) / K
+    per_shape = (1000 * out["pos_s_per_step"] + 1000 * out["lat_s_per_step"] + out["decode_s"]) / B
+    out.update(batch=B, steps_timed=K)
+    return 1.0 / per_shape, out
+
+
+def cpu_arm(cfg, budget=20.0, B=16):
+    """-> (shapes/s, cores, kind, sample, detail)"""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if not mirror_available():
+        from oracle import ref_model
+        from slide_b200 import pipeline
+        sds = pipeline.default_state_dicts()
+        label = torch.zeros(B, dtype=torch.long)
+        per_shape, detail = 0.0, {}
+        with torch.no_grad():
+            for key, name, C in (("position_ddpm", "position", 3), ("latent_ddpm", "latent", 51)):
+                pc = cfg[key]["pointnet_config"]
+                P = ref_model.Params(sds[name])
+                x = torch.randn(B, 16, C)
+                ref_model.cloud_condition_net(x, P, pc, ts=torch.ones(B) * 500, label=label)
+                n, t0 = 0, time.time()
+                while n < 3 or (time.time() - t0 < budget / 3 and n < 50):
+                    ref_model.cloud_condition_net(x, P, pc, ts=torch.ones(B) * 500, label=label)
+                    n += 1
+                detail[name + "_s_per_step"] = (time.time() - t0) / n
+                per_shape += 1000 * detail[name + "_s_per_step"] / B
+            P = ref_model.Params(sds["autoencoder"])
+            t0 = time.time()
+            ref_model.decode(torch.rand(2, 16, 3) - 0.5, torch.randn(2, 16, 48), P, cfg["autoencoder"]["decoders"], label[:2])
+            detail["decode_s_b2"] = time.time() - t0
+            per_shape += detail["decode_s_b2"] / 2
+        return (1.0 / per_shape, torch.get_num_threads(), "port",
+                "oracle/ref_model.py (bit-identical port): denoiser forwards at batch %d scaled to 1000+1000 steps + decode of 2 shapes" % B,
+                detail)
+    from oracle import ops
+    ops.install_reference_stubs(reference_root=MIRROR)
+    # the reference moves tensors with .cuda(): no-ops on the CPU arm (device placement only, arithmetic untouched)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    K = 2
+    value, detail = _time_reference_loops(cfg, B, K, torch.device("cpu"), lambda: None)
+    # spend the rest of the budget on more steps if the first pass was quick
+    spent = K * (detail["pos_s_per_step"] + detail["lat_s_per_step"]) + 2 * detail["decode_s"]
+    if spent < budget / 3:
+        K2 = int(min(20, max(K, (budget - spent) / max(detail["pos_s_per_step"] + detail["lat_s_per_step"], 1e-6))))
+        if K2 > K:
+            value, detail = _time_reference_loops(cfg, B, K2, torch.device("cpu"), lambda: None)
+    sample = ("unmodified util.sampling + LatentDiffusion.denoise_and_reconstruct: %d steps of each DDPM at batch %d + one "
+              "decode, scaled to 1000+1000 steps; native ops = C oracle" % (detail["steps_timed"], B))
+    return value, torch.get_num_threads(), "reference", sample, detail
+
+
+def gpu_arm(cfg, B=256, K=10):
+    """The reference's eager GPU path on cuda:0 -> (shapes/s, detail)."""
+    import torch
+    import slide_b200
+    from oracle import build_ref
+    ext = build_ref.load_module()
+    if ext is None or not mirror_available():
+        raise RuntimeError("needs oracle/_ref (the reference's CUDA extension) and baseline/_ref (its python)")
+    sys.modules["pointnet2_ops._ext"] = ext
+    # the reference's python package first, then the drop-in directory (only its `pytorch3d` is picked up from there)
+    sys.path.insert(0, slide_b200.DROPIN_DIR)
+    sys.path.insert(0, os.path.join(MIRROR, "pointnet2"))
+    sys.path.insert(0, os.path.join(MIRROR, "pointnet2_ops_lib"))
+    import pointnet2_ops
+    assert pointnet2_ops.__file__.startswith(MIRROR), pointnet2_ops.__file__
+    pointnet2_ops._ext = ext
+    dev = torch.device("cuda", 0)
+    value, detail = _time_reference_loops(cfg, B, K, dev, torch.cuda.synchronize)
+    detail["pointnet2_ops"] = "reference python package + its own CUDA extension built for sm_100a (oracle/_ref)"
+    detail["pytorch3d"] = "slide_b200 drop-in (pytorch3d 0.7.0 is not installable offline)"
+    return value, detail
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("arm", choices=["cpu", "gpu"])
+    ap.add_argument("--budget", type=float, default=20.0)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--category", default="airplane")
+    args = ap.parse_args()
+    from slide_b200 import weights
+    cfg = weights.load_json("pipeline_%s.json" % args.category)
+    if args.arm == "cpu":
+        v, cores, kind, sample, detail = cpu_arm(cfg, args.budget, args.batch or 16)
+        print(json.dumps({"value": v, "unit": "shapes/s", "cores": cores, "kind": kind, "sample": sample, "detail": detail}))
+    else:
+        v, detail = gpu_arm(cfg, args.batch or 256, args.steps)
+        print(json.dumps({"value": v, "unit": "shapes/s", "kind": "reference eager on the same GPU", "detail": detail}))
+
+
+if __name__ == "__main__":
+    main()
