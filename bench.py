@@ -5,11 +5,19 @@ DDPM + decode to 2048-point clouds at batch 256 (BASELINE.json), one process per
   python bench.py --gpus 1 --steps 2 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
          bench.py --gpus N --steps K --warmup W
-  python bench.py --impl reference ...      # the CPU path (oracle port of the reference's modules) on the host cores
+  python bench.py --impl reference ...      # the reference's own CPU path: its UNMODIFIED python (baseline/_ref) on the host cores
 
 A "step" is one full pass of the pipeline over one batch of 256 synthetic shapes (random-init weights with the
 reference's state-dict schema, labels = airplane).  `value` times the device path with inputs resident in HBM;
-`e2e` adds the pinned host->device copies of every input and the device->host read of the clouds.
+`e2e` adds, every step, the host-side RNG draws the reference's loop makes (x_T, 1000 position-noise tensors, FPS start
+indices), the pinned host->device copies of every input and the device->host read of the clouds.
+
+Besides the headline (weak scaling, 256 shapes per GPU) the same JSON line carries
+  strong      BASELINE config 4 as written: global batch 256, chair, sharded 256/N per GPU (scaling "strong")
+  configs     BASELINE configs 1 (FPS + ball query, timed beside the reference's own .cu from oracle/_ref), 2, 3 and 5
+  reference_gpu_eager   the reference's eager GPU path (its python + its CUDA extension built for sm_100a) on this box
+  parity      epsilon of both denoisers at batch 256, default dispatch vs the fp32 FFMA backend, same process
+(--no-extras skips them).
 """
 import argparse
 import json
@@ -92,39 +100,146 @@ def ncu_traffic():
         return None
 
 
-def cpu_path(cfg, seconds_budget=20.0):
-    """The reference's CPU path for this pipeline: its python modules as restated in oracle/ref_model.py (checked
-    bit-for-bit against the real modules by tests/golden/make_golden.py) over the C oracle ops, all host cores.
-    Bounded sample: a few denoiser forwards at batch 16 + one decode of 2 shapes, scaled to 1000+1000 steps."""
+def run_json(cmd, timeout):
+    """Run a helper process (keeps its monkey-patches / module stubs out of this one) and parse its last JSON line."""
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout,
+                           env=dict(os.environ, PYTHONPATH=ROOT))
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
+def time_events(fn, iters, warm=3):
+    """Mean microseconds per call of fn() on the current stream (CUDA events, warm-up first)."""
     import torch
-    from oracle import ref_model
-    from slide_b200 import pipeline
-    torch.set_num_threads(os.cpu_count() or 1)
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / iters
+
+
+def config1_index_ops():
+    """BASELINE config 1: FPS (2048 -> 1024) + ball query (r = 0.2, nsample = 32) on one 1 x 2048 x 3 cloud -- the
+    reference's own unit -- through the C ABI, next to the reference's own kernels (oracle/_ref, its .cu
+    compiled for sm_100a) on the same inputs and the same box; outputs compared bit for bit."""
+    import torch
+    from slide_b200 import install_dropin
+    install_dropin()
+    from pointnet2_ops import _ext as ours
+    torch.manual_seed(7)
+    xyz = torch.rand(1, 2048, 3, device="cuda")
+    idx = ours.furthest_point_sampling(xyz, 1024)
+    new_xyz = ours.gather_points(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+    out = {"workload": "FPS 2048->1024 + ball_query r=0.2 ns=32, 1x2048x3",
+           "fps_us": time_events(lambda: ours.furthest_point_sampling(xyz, 1024), 50),
+           "ball_query_us": time_events(lambda: ours.ball_query(new_xyz, xyz, 0.2, 32), 200)}
+    # algorithmic bytes (SURVEY 8d): FPS 12 N + 4 m, ball query 12 N + 12 m + 4 m ns
+    out["fps_algorithmic_bytes"] = 12 * 2048 + 4 * 1024
+    out["ball_query_algorithmic_bytes"] = 12 * 2048 + 12 * 1024 + 4 * 1024 * 32
+    try:
+        from oracle import build_ref
+        ref = build_ref.load_module()
+    except Exception:  # noqa: BLE001
+        ref = None
+    if ref is not None:
+        out["reference_fps_us"] = time_events(lambda: ref.furthest_point_sampling(xyz, 1024), 50)
+        out["reference_ball_query_us"] = time_events(lambda: ref.ball_query(new_xyz, xyz, 0.2, 32), 200)
+        out["bit_exact_vs_reference"] = bool(torch.equal(ref.furthest_point_sampling(xyz, 1024), idx) and
+                                             torch.equal(ref.ball_query(new_xyz, xyz, 0.2, 32),
+                                                         ours.ball_query(new_xyz, xyz, 0.2, 32)))
+        out["speedup_fps"] = out["reference_fps_us"] / out["fps_us"]
+        out["speedup_ball_query"] = out["reference_ball_query_us"] / out["ball_query_us"]
+    else:
+        out["reference"] = "oracle/_ref not built"
+    return out
+
+
+def sampler_step_us(sampler, replays=4):
+    """Device microseconds per sampling step of a DDPMSampler (graph replays of `graph_steps` steps each)."""
+    import torch
+    sampler.x_view().normal_()
+    sampler.run(sampler.graph_steps)  # captures on first use
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sampler.run(sampler.graph_steps * replays)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (sampler.graph_steps * replays)
+
+
+def eps_parity(sampler, seed):
+    """One denoiser forward at t = T/2 under the default dispatch and under the fp32 FFMA backend on identical inputs
+    -> max |d eps| / max |eps|.  The default dispatch is what the timed region ran."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(sampler.x_view().shape, device="cuda", generator=g)
+    first, count = sampler.builder.segments["forward"]
+    eps = []
+    for backend in ("auto", "simt"):
+        sampler.prog.set_gemm_backend(backend)
+        sampler.x_view().copy_(x)
+        sampler.prog.set_step(sampler.T // 2)
+        sampler.prog.run(first, count)
+        torch.cuda.synchronize()
+        eps.append(sampler.prog.download(sampler.h["eps"]).float().clone())
+    sampler.prog.set_gemm_backend("auto")
+    scale = float(eps[1].abs().max())
+    return float((eps[0] - eps[1]).abs().max()) / max(scale, 1e-12)
+
+
+def extra_configs(cfg, args):
+    """BASELINE configs 2, 3, 5 (and 1) on this GPU -- single-GPU parity-test cases of BASELINE.json, timed here so that
+    the driver's record carries them.  Each runs the full workload once after one warm-up pass."""
+    import torch
+    from slide_b200 import engine, pipeline
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = {"config1": config1_index_ops()}
     sds = pipeline.default_state_dicts()
-    Bs = 16
-    label = torch.zeros(Bs, dtype=torch.long)
-    per_shape = 0.0
-    detail = {}
-    with torch.no_grad():
-        for key, name, C in (("position_ddpm", "position", 3), ("latent_ddpm", "latent", 51)):
-            pc = cfg[key]["pointnet_config"]
-            P = ref_model.Params(sds[name])
-            x = torch.randn(Bs, 16, C)
-            ref_model.cloud_condition_net(x, P, pc, ts=torch.ones(Bs) * 500, label=label)  # warm-up
-            n, t0 = 0, time.time()
-            while n < 3 or (time.time() - t0 < seconds_budget / 3 and n < 50):
-                ref_model.cloud_condition_net(x, P, pc, ts=torch.ones(Bs) * 500, label=label)
-                n += 1
-            dt = (time.time() - t0) / n
-            detail[name + "_s_per_step_b%d" % Bs] = dt
-            per_shape += 1000 * dt / Bs
-        P = ref_model.Params(sds["autoencoder"])
-        kp, feat = torch.rand(2, 16, 3) - 0.5, torch.randn(2, 16, 48)
-        t0 = time.time()
-        ref_model.decode(kp, feat, P, cfg["autoencoder"]["decoders"], label[:2])
-        detail["decode_s_b2"] = time.time() - t0
-        per_shape += detail["decode_s_b2"] / 2
-    return 1.0 / per_shape, torch.get_num_threads(), detail
+    # config 2: position DDPM, 16 latent points, airplane, 1000 steps, batch 32
+    d = cfg["position_ddpm"]["diffusion_config"]
+    pos = pipeline.DDPMSampler(cfg["position_ddpm"]["pointnet_config"], sds["position"], 32,
+                               engine.position_table(d["T"], d["beta_0"], d["beta_T"]), 0, 0, d["T"], dev, backend=args.backend)
+    pos.set_labels(torch.full((32,), cfg["label"], dtype=torch.long, device=dev))
+    pos.noise_view().normal_()
+
+    def run_pos():
+        pos.x_view().normal_()
+        pos.run()
+    us = time_events(run_pos, 1, warm=1)
+    out["config2"] = {"workload": "position DDPM 1000 steps, batch 32, airplane", "ms": us / 1e3, "us_per_step": us / d["T"],
+                      "shapes_per_s": 32 / (us / 1e6), "launches_per_step": pos.launches_per_step(),
+                      "finite": bool(torch.isfinite(pos.x_view()).all().item())}
+    del pos
+    # config 3: feature DDPM on fixed keypoints + decode to 2048 points, batch 128
+    p3 = pipeline.SlidePipeline(cfg, 128, backend=args.backend, decode_chunk=min(args.decode_chunk, 128))
+    labels = torch.full((128,), cfg["label"], dtype=torch.long)
+    torch.manual_seed(3)
+    p3.draw_host_inputs(labels, skip_position=True)
+    p3.stage_inputs()
+    kp = (torch.rand(128, 16, 3, device=dev) - 0.5)
+    us = time_events(lambda: p3.sample_resident(keypoints=kp), 1, warm=1)
+    out["config3"] = {"workload": "feature DDPM 1000 steps on fixed keypoints + decode to 2048 pts, batch 128, airplane",
+                      "ms": us / 1e3, "shapes_per_s": 128 / (us / 1e6), "finite": bool(torch.isfinite(p3.out).all().item())}
+    del p3
+    torch.cuda.empty_cache()
+    # config 5: autoencoder encode + decode sweep (tools/bench_autoencoder.py), batch 512, one GPU
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_autoencoder.py"), "--batch", "512", "--reps", "1"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    rows = [json.loads(line) for line in r.stdout.splitlines() if line.startswith("{")]
+    out["config5"] = [{k: row[k] for k in ("points", "batch", "encode_ms", "decode_ms", "shapes_per_s", "hbm_roofline", "finite")}
+                      for row in rows] or {"error": (r.stderr or r.stdout)[-300:]}
+    return out
 
 
 def main():
@@ -138,6 +253,7 @@ def main():
     ap.add_argument("--ddpm-steps", type=int, default=None, help="DEBUG ONLY: truncate both DDPM loops (invalid as a benchmark)")
     ap.add_argument("--backend", default="auto", choices=["auto", "simt"])
     ap.add_argument("--decode-chunk", type=int, default=128)
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip strong / configs / reference_gpu_eager")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -150,20 +266,27 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        vals = []
+        # The reference's own CPU implementation of the path: its UNMODIFIED python (baseline/_ref: util.sampling,
+        # LatentDiffusion.denoise_and_reconstruct, PointNet2CloudCondition, PointAutoencoder) on all host cores, the native
+        # ops it only ships for CUDA supplied by the C oracle.  Each step of this arm is a bounded sample (a few steps of
+        # each DDPM at batch 16 + one decode) scaled to the full workload; kind = "port" only if the mirror is absent.
+        from oracle import reference_arms
+        budget = max(4.0, min(12.0, 150.0 / max(args.warmup + args.steps, 1)))
+        vals, wall0 = [], time.time()
         for i in range(args.warmup + args.steps):
-            v, cores, detail = cpu_path(cfg, seconds_budget=12.0)
+            v, cores, kind, sample, detail = reference_arms.cpu_arm(cfg, budget, 16)
             if i >= args.warmup:
                 vals.append(v)
         v = sum(vals) / len(vals)
-        sample = "3+ denoiser forwards per DDPM at batch 16 scaled to 1000 steps, decode of 2 shapes; per step of this arm"
         print(json.dumps({
             "impl": "reference", "metric": "shapes/sec (1000-step DDPM + decode to 2048 pts) @ bs256", "value": v,
             "unit": "shapes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * args.batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "global_batch": args.batch, "timing": "host wall clock, extrapolated"},
-            "cpu_baseline": {"value": v, "unit": "shapes/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload, "global_batch": args.batch,
+                       "timing": "host wall clock of a bounded sample, scaled to 1000+1000 steps + decode of 256 shapes",
+                       "wall_s": time.time() - wall0},
+            "cpu_baseline": {"value": v, "unit": "shapes/s", "cores": cores, "kind": kind, "sample": sample + "; per step of this arm"},
             "e2e": {"value": v, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "detail": detail}))
         return
@@ -212,14 +335,21 @@ def main():
     ms_value = ev0.elapsed_time(ev1) / args.steps
     launches = lib.launch_count() // max(args.steps, 1)
     # ---- arm 2: end to end through the public API, host buffers in, host buffer out -------------------------
+    # every step: the host RNG draws of the reference's loop (util.py:131-136,225,253; diffusion.py:373; the decoder's FPS
+    # start indices), pinned H2D of all inputs, the three stages, D2H of the clouds
     barrier()
     t0 = time.time()
+    rng_s = 0.0
     for _ in range(args.steps):
+        tr = time.time()
+        pipe.draw_host_inputs(labels)
+        rng_s += time.time() - tr
         host = pipe.sample_to_host()
         if world > 1:
             gathered = pipeline.all_gather_outputs(pipe.out, world)
     barrier()
     ms_e2e = 1e3 * (time.time() - t0) / args.steps
+    ms_rng = 1e3 * rng_s / args.steps
     wall1 = time.time()
     clock_info = clocks.stop(wall0, wall1) if clocks else None
 
@@ -229,6 +359,36 @@ def main():
     ms_value, ms_e2e = t.tolist()
     finite = bool(torch.isfinite(out).all().item())
     tc_err = lib.load().slide_tc_error()
+
+    # ---- BASELINE config 4 as written: global batch 256, chair, SHARDED 256 / N per GPU (strong scaling); the reference
+    # splits the evaluation batch the same way (pointnet2/mesh_evaluation.py:51 int(eval_batch_size / world_size))
+    strong = None
+    if args.ddpm_steps is None and not args.no_extras and 256 % world == 0:
+        cfg_s = weights.load_json("pipeline_chair.json")
+        sp = pipeline.SlidePipeline(cfg_s, 256, rank=rank, world=world, backend=args.backend,
+                                    decode_chunk=min(args.decode_chunk, 256 // world))
+        torch.manual_seed(1)
+        sp.draw_host_inputs(torch.full((256,), cfg_s["label"], dtype=torch.long))
+        g_s = pipeline.all_gather_outputs(sp.sample(), world)  # warm-up (captures the graphs)
+        sp.stage_inputs()
+        ns = max(1, min(args.steps, 2))
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(ns):
+            g_s = pipeline.all_gather_outputs(sp.sample_resident(), world)
+        s1.record()
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1) / ns], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms_s = float(ts.item())
+        strong = {"scaling": "strong", "value": 256 / (ms_s / 1e3), "unit": "shapes/s", "ms_per_step": ms_s, "steps": ns,
+                  "warmup": 1, "global_batch": 256, "per_gpu_batch": 256 // world, "category": "chair", "n_gpus": world,
+                  "gathered_shape": list(g_s.shape), "finite": bool(torch.isfinite(g_s).all().item()),
+                  "launches_per_step": {"position": sp.pos.launches_per_step(), "latent": sp.lat.launches_per_step()}}
+        del sp, g_s
+        torch.cuda.empty_cache()
 
     roof = None
     cpu = None
@@ -289,11 +449,26 @@ def main():
                         "CUDA-event time; whole_step_* = reference-formulation FLOPs (1151.7 GFLOP/shape) / device time. "
                         "Operands are TF32 (nominal dense peak = half of bf16); peak shown is the measured bf16 figure."
                         % n_launch}
+        extras = {}
+        parity = None
         if args.ddpm_steps is None:
-            v, cores, detail = cpu_path(cfg)
-            cpu = {"value": v, "unit": "shapes/s", "cores": cores, "kind": "port",
-                   "sample": "denoiser forwards at batch 16 scaled to 1000+1000 steps + decode of 2 shapes", "detail": detail}
-        valid = args.ddpm_steps is None and finite and tc_err == 0
+            # same-process check that the launched instantiations compute the right thing: eps of both denoisers at this
+            # batch, default dispatch (what was timed) vs the fp32 FFMA backend; record-level parity vs the oracle at the
+            # same batch sizes is tests/test_gpu_baseline_sizes.py
+            parity = {"position_eps_rel_err": eps_parity(pipe.pos, 11), "latent_eps_rel_err": eps_parity(pipe.lat, 12),
+                      "tolerance": 5e-3, "what": "max |eps_auto - eps_fp32| / max |eps_fp32| at batch %d, t = T/2" % Bl}
+            parity["ok"] = bool(parity["position_eps_rel_err"] < 5e-3 and parity["latent_eps_rel_err"] < 5e-3)
+            cpu = run_json([sys.executable, "-m", "oracle.reference_arms", "cpu", "--budget", "20", "--batch", "16",
+                            "--category", args.category], 240)
+            cpu = {k: cpu.get(k) for k in ("value", "unit", "cores", "kind", "sample", "detail", "error") if k in cpu}
+        if args.ddpm_steps is None and not args.no_extras and world == 1:
+            extras["reference_gpu_eager"] = run_json([sys.executable, "-m", "oracle.reference_arms", "gpu", "--batch",
+                                                      str(args.batch), "--steps", "10", "--category", args.category], 300)
+            try:
+                extras["configs"] = extra_configs(cfg, args)
+            except Exception as e:  # noqa: BLE001
+                extras["configs"] = {"error": repr(e)[:300]}
+        valid = args.ddpm_steps is None and finite and tc_err == 0 and bool(parity and parity["ok"])
         print(json.dumps({
             "metric": "shapes/sec (1000-step DDPM + decode to 2048 pts) @ bs256", "value": B / (ms_value / 1e3),
             "unit": "shapes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value,
@@ -303,9 +478,10 @@ def main():
                        "l2": "inputs larger than L2 (noise tensors 49 MB + 836 MB per GPU)", "valid": valid,
                        "ddpm_steps": args.ddpm_steps or 1000, "backend": args.backend},
             "e2e": {"value": B / (ms_e2e / 1e3), "unit": "shapes/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
-                    "d2h_bytes_per_step": pipe.d2h_bytes(), "ms_per_step": ms_e2e},
+                    "d2h_bytes_per_step": pipe.d2h_bytes(), "ms_per_step": ms_e2e, "host_rng_ms_per_step": ms_rng,
+                    "includes": "host RNG draws (reference call order), pinned H2D, 3 stages, D2H"},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roof, "cpu_baseline": cpu,
-            "finite": finite, "tc_error": tc_err}))
+            "finite": finite, "tc_error": tc_err, "parity": parity, "strong": strong, **extras}))
     if world > 1:
         dist.destroy_process_group()
 
