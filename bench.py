@@ -154,9 +154,12 @@ def config1_index_ops():
     if ref is not None:
         out["reference_fps_us"] = time_events(lambda: ref.furthest_point_sampling(xyz, 1024), 50)
         out["reference_ball_query_us"] = time_events(lambda: ref.ball_query(new_xyz, xyz, 0.2, 32), 200)
-        out["bit_exact_vs_reference"] = bool(torch.equal(ref.furthest_point_sampling(xyz, 1024), idx) and
-                                             torch.equal(ref.ball_query(new_xyz, xyz, 0.2, 32),
-                                                         ours.ball_query(new_xyz, xyz, 0.2, 32)))
+        def same(a, b):
+            a, b = (a if isinstance(a, (tuple, list)) else (a,)), (b if isinstance(b, (tuple, list)) else (b,))
+            return len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b))
+        out["bit_exact_vs_reference"] = bool(same(ref.furthest_point_sampling(xyz, 1024), idx) and
+                                             same(ref.ball_query(new_xyz, xyz, 0.2, 32),
+                                                  ours.ball_query(new_xyz, xyz, 0.2, 32)))
         out["speedup_fps"] = out["reference_fps_us"] / out["fps_us"]
         out["speedup_ball_query"] = out["reference_ball_query_us"] / out["ball_query_us"]
     else:

@@ -160,6 +160,16 @@ struct slide_rop;
 int slide_program_set_resident(slide_program *p, const struct slide_resident_plan *plan, const struct slide_rop *rops,
                                int n_rops);
 int slide_program_use_resident(slide_program *p, int enable);
+/* Slice of torch's CUDA normal_() stream (replaces the T full-batch torch.randn_like calls of the feature DDPM's loop,
+ * pointnet2/diffusion_utils/diffusion.py:88, on a rank that owns only part of the batch).  For call s = 0..n_calls-1 of
+ * normal_() on a contiguous fp32 tensor of `numel` elements -- Philox4_32_10 (seed, offset + s * offset_increment), ATen's
+ * grid-stride mapping with `grid_full` = min(sm_count * (max_threads_per_sm / 256), ceil(numel / 256)) blocks of 256
+ * threads and offset_increment = ((numel - 1) / (1024 * grid_full) + 1) * 4 -- writes elements
+ * [slice_begin, slice_begin + slice_len) to out[row * out_call_stride + 0..slice_len), row = s (reverse = 0) or
+ * n_calls - 1 - s (reverse = 1), bit-identical to what the full draw puts there.  One launch. */
+int slide_philox_normal_slice(float *out, long long out_call_stride, int n_calls, int reverse, unsigned long long seed,
+                              unsigned long long offset, unsigned long long offset_increment, long long numel,
+                              long long slice_begin, long long slice_len, int grid_full, slide_stream_t stream);
 /* Kernels launched by one pass over ops [first, first+count). */
 int slide_program_launches(slide_program *p, int first, int count);
 

@@ -24,7 +24,7 @@ SYMBOLS = [
     "slide_program_create", "slide_program_destroy", "slide_program_arena", "slide_program_weights",
     "slide_program_run", "slide_program_capture", "slide_program_replay", "slide_program_launches",
     "slide_program_set_gemm_backend", "slide_tc_error", "slide_tc_reset_error", "slide_tc_reload_tuning",
-    "slide_program_set_resident", "slide_program_use_resident",
+    "slide_program_set_resident", "slide_program_use_resident", "slide_philox_normal_slice",
 ]
 
 
@@ -59,6 +59,10 @@ def load():
         lib.slide_program_set_gemm_backend.argtypes = [ctypes.c_void_p, ctypes.c_int]
         lib.slide_program_set_resident.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         lib.slide_program_use_resident.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.slide_philox_normal_slice.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_ulonglong,
+                                                  ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
+                                                  ctypes.c_void_p]
         _lib = lib
     return _lib
 

@@ -16,7 +16,7 @@ memory, RNG, streams and (multi-GPU) the NCCL all-gather.
 import numpy as np
 import torch
 
-from . import engine, weights
+from . import engine, rng, weights
 from .program import Program
 
 
@@ -266,16 +266,10 @@ class SlidePipeline(object):
         x = self.lat.x_view().view(self.Bl, 16, self.lat.C)
         x.copy_(self._lat_xT_dev)
         x[:, :, 0:3] = kp
+        # the reference's randn_like sequence (diffusion.py:88): T draws of the FULL batch, of which this rank keeps its
+        # rows -- one seeked-Philox launch (rng.py), bit-identical to the T torch.randn calls and to any world size
         nz = self.lat.noise_view().view(self.T_lat, self.Bl, 16, self.lat.C)
-        if self.world == 1:
-            for i in range(self.T_lat - 1, -1, -1):  # the reference's randn_like sequence (diffusion.py:88)
-                torch.randn((self.Bl, 16, self.lat.C), device=dev, out=nz[i])
-        else:
-            full = torch.empty(self.B, 16, self.lat.C, device=dev)
-            lo = self.rank * self.Bl
-            for i in range(self.T_lat - 1, -1, -1):
-                torch.randn((self.B, 16, self.lat.C), device=dev, out=full)
-                nz[i].copy_(full[lo:lo + self.Bl])
+        self.noise_path = rng.randn_sequence(nz, (self.B, 16, self.lat.C), self.rank * self.Bl, reverse=True)
         self.lat.run(self.ddpm_steps)
         feat = x[:, :, 3:].contiguous()
         self.keypoint, self.keypoint_feature = kp, feat  # (Bl,16,3), (Bl,16,F): what the reference also returns

@@ -29,6 +29,15 @@ def main():
     kp = pipe.pos.x_view().view(256, 16, 3)[:pipe.dec.chunk].contiguous()
     feat = pipe.lat.x_view().view(256, 16, pipe.lat.C)[:pipe.dec.chunk, :, 3:].contiguous()
     pipe.dec.run(kp, feat, pipe._labels[:pipe.dec.chunk], pipe._starts_dev[:, :pipe.dec.chunk], pipe.out[:pipe.dec.chunk])
+    if "--config1" in sys.argv:  # BASELINE config 1 through the drop-in _ext: FPS 2048 -> 1024 + ball query r=0.2 ns=32
+        from slide_b200 import install_dropin
+        install_dropin()
+        from pointnet2_ops import _ext
+        torch.manual_seed(7)
+        xyz = torch.rand(1, 2048, 3, device="cuda")
+        idx = _ext.furthest_point_sampling(xyz, 1024)
+        new_xyz = _ext.gather_points(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+        _ext.ball_query(new_xyz, xyz, 0.2, 32)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 
