@@ -337,6 +337,7 @@ def main():
     barrier()
     ms_value = ev0.elapsed_time(ev1) / args.steps
     launches = lib.launch_count() // max(args.steps, 1)
+    stages = pipe.stage_ms()  # of the last timed step
     # ---- arm 2: end to end through the public API, host buffers in, host buffer out -------------------------
     # every step: the host RNG draws of the reference's loop (util.py:131-136,225,253; diffusion.py:373; the decoder's FPS
     # start indices), pinned H2D of all inputs, the three stages, D2H of the clouds
@@ -484,7 +485,8 @@ def main():
                     "d2h_bytes_per_step": pipe.d2h_bytes(), "ms_per_step": ms_e2e, "host_rng_ms_per_step": ms_rng,
                     "includes": "host RNG draws (reference call order), pinned H2D, 3 stages, D2H"},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roof, "cpu_baseline": cpu,
-            "finite": finite, "tc_error": tc_err, "parity": parity, "strong": strong, **extras}))
+            "finite": finite, "tc_error": tc_err, "parity": parity, "stages_ms": stages,
+            "noise_path": getattr(pipe, "noise_path", None), "strong": strong, **extras}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -29,6 +29,33 @@ inline int cuda_rc(cudaError_t e) {
   return SLIDE_OK;
 }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// Every kernel of this library starts with pdl_wait(): when it was launched with the programmatic-serialization
+// attribute (launch_k below) its CTAs may become resident while the previous kernel of the stream is still running, and
+// this instruction blocks them until that kernel has COMPLETED and its writes are visible -- so nothing a kernel does
+// after its first instruction can race with its predecessor.  pdl_trigger() (placed right after the wait) lets the NEXT
+// kernel's CTAs be scheduled as soon as all of this kernel's CTAs are running: launch latency and CTA start-up overlap
+// the kernel's execution instead of following it.  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_pdl_enabled;  // SLIDE_PDL (default 1); read once
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through after_launch()
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -15,6 +15,8 @@ namespace slide {
 constexpr int SBM = 64, SBN = 64, SBK = 16, STHREADS = 256;
 
 __global__ void __launch_bounds__(STHREADS) gemm_simt_kernel(GemmArgs a) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float As[SBK][SBM + 4];
   __shared__ float Ws[SBK][SBN + 4];
   __shared__ float tile[SBM][SBN + 1];
@@ -99,7 +101,7 @@ int launch_gemm_simt(const GemmArgs &a, cudaStream_t st) {
   if (a.smk > 0 && (SBM % a.smk != 0)) return SLIDE_ERR_UNSUPPORTED;  // neighbour groups must not straddle row tiles
   dim3 grid(ceil_div(a.M, SBM), ceil_div(a.N, SBN));
   if (grid.y > 65535) return SLIDE_ERR_UNSUPPORTED;
-  gemm_simt_kernel<<<grid, STHREADS, 0, st>>>(a);
+  launch_k(gemm_simt_kernel, grid, STHREADS, 0, st, a);
   return after_launch();
 }
 

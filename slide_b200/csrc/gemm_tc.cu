@@ -272,7 +272,6 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
   }
 #endif
   const int mlast = min(m0 + TBM, a.M) - 1;
-  const int step = a.step ? *a.step : 0;
   const int num_kb = (a.K + TBK - 1) / TBK;
 
   if (tid == 0) {
@@ -290,6 +289,11 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // Programmatic dependent launch: everything above is on-chip set-up (barriers, tensor-memory allocation) and may
+  // overlap the previous kernel's tail; global memory is touched only from here on.
+  pdl_wait();
+  pdl_trigger();
+  const int step = a.step ? *a.step : 0;
   const int sA0 = m0 / a.xfa.R;
   if (has_xfa)
     fill_xf_table(a.xfa, tabA, mrbuf, sA0, mlast / a.xfa.R - sA0 + 1, a.K, 0, table_stride, step, tid, TC_THREADS);
@@ -779,7 +783,6 @@ __global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
   float4 *tabA = reinterpret_cast<float4 *>(ctrl + 512 + 4 * BN * 8 + XF_MAXG * 8);  // XFA: per K column
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int step = a.step ? *a.step : 0;
   const int num_kb = (a.K + TBK - 1) / TBK;
   const int tiles_n = (a.N + BN - 1) / BN;
   const int tiles = (a.M / TBM) * tiles_n;
@@ -807,6 +810,11 @@ __global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: barriers and tensor memory are set up while the previous kernel drains; global
+  // memory (operands, statistics, the step counter) is touched only after this point.
+  pdl_wait();
+  pdl_trigger();
+  const int step = a.step ? *a.step : 0;
   TL(0, tid == 0);
 #ifdef TC_TIMELINE
   if (tid == 0 && blockIdx.x < TL_CTAS) {
@@ -1327,7 +1335,7 @@ static int launch_tc_impl(const GemmArgs &a, const float *Wp, int wp_na, cudaStr
   dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, TBM));
   if (grid.y > 65535) return SLIDE_ERR_UNSUPPORTED;
   const int dbg = tuning().debug;
-  gemm_tc_kernel<BN, STAGES, SMK, TMA_A><<<grid, TC_THREADS, total, st>>>(a, Wp, wp_na, stride, rows, dbg, tm);
+  launch_k(gemm_tc_kernel<BN, STAGES, SMK, TMA_A>, grid, TC_THREADS, total, st, a, Wp, wp_na, stride, rows, dbg, tm);
   return after_launch();
 }
 
@@ -1350,7 +1358,7 @@ static int launch_tcp(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_
   const int tiles = (a.M / TBM) * ceil_div(a.N, BN);
   const int max_grid = tuning().persist_grid > 0 ? tuning().persist_grid : sm_count();  // tests shrink it: many tiles per CTA
   const int grid = tiles < max_grid ? tiles : max_grid;
-  gemm_tcp_kernel<BN, PSTAGES, XFA, SMK><<<grid, XFA ? TCP_XFA_THREADS : TCP_THREADS, total, st>>>(a, Wp, wp_na, stride, tm);
+  launch_k(gemm_tcp_kernel<BN, PSTAGES, XFA, SMK>, grid, XFA ? TCP_XFA_THREADS : TCP_THREADS, total, st, a, Wp, wp_na, stride, tm);
   return after_launch();
 }
 
@@ -1397,6 +1405,8 @@ static int launch_tc(const GemmArgs &a, const float *Wp, int wp_na, cudaStream_t
 constexpr int PP_COLS = 64;
 
 __global__ void __launch_bounds__(256) xf_prepass_kernel(GemmArgs a, float *__restrict__ out, int ldo) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float4 tab[XF_MAXS * PP_COLS];
   __shared__ float2 mr[XF_MAXS * XF_MAXG];
   const int m0 = blockIdx.y * TBM, k0 = blockIdx.x * PP_COLS;
@@ -1455,7 +1465,7 @@ int launch_gemm_tc_prepass(const GemmArgs &a, const float *Wp, int wp_na, float 
   const GemmArgs b = prepass_args(a, scratch);
   if (!gemm_tc_eligible(b, Wp)) return TCP_NOT_APPLICABLE;
   dim3 grid(ceil_div(a.K, PP_COLS), ceil_div(a.M, TBM));
-  xf_prepass_kernel<<<grid, 256, 0, st>>>(a, scratch, b.lda);
+  launch_k(xf_prepass_kernel, grid, 256, 0, st, a, scratch, b.lda);
   const int rc = after_launch();
   if (rc != SLIDE_OK) return rc;
   return launch_gemm_tc(b, Wp, wp_na, st);

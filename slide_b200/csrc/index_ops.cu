@@ -6,6 +6,8 @@
 // tensor cores.  Index results are bit-exact with the reference, including its tie rules.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace slide {
@@ -36,6 +38,8 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float *__restrict__ xyz
                                                    int nb_log2, const int64_t *__restrict__ lengths,
                                                    const int64_t *__restrict__ Ks,
                                                    const void *__restrict__ start_raw, void *out_raw) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ uint2 slots[2][32];
   const int b = blockIdx.x;
   const int T = blockDim.x;
@@ -148,6 +152,8 @@ __global__ void __launch_bounds__(1024) fps_global_kernel(const float *__restric
                                                           const int64_t *__restrict__ Ks,
                                                           const int64_t *__restrict__ start_idx,
                                                           float *__restrict__ temp, void *out_raw) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ uint2 slots[2][32];
   const int b = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
@@ -250,7 +256,7 @@ static int launch_fps(const float *xyz, int ldx, int B, int N, int m, const int6
   const int nb_log2 = ilog2_ceil(ceil_div(N, S));
   if (s_log2 + nb_log2 > 31) return SLIDE_ERR_UNSUPPORTED;
 #define FPS_CASE(P)                                                                                      \
-  fps_kernel<P, MODE><<<B, T, 0, st>>>(xyz, ldx, N, m, s_log2, nb_log2, lengths, Ks, start, out);        \
+  launch_k(fps_kernel<P, MODE>, B, T, 0, st, xyz, ldx, N, m, s_log2, nb_log2, lengths, Ks, start, out);        \
   break;
   switch (ppt <= 1 ? 1 : ppt <= 2 ? 2 : ppt <= 4 ? 4 : ppt <= 8 ? 8 : 16) {
     case 1: FPS_CASE(1)
@@ -271,6 +277,8 @@ static int launch_fps(const float *xyz, int ldx, int B, int N, int m, const int6
 // read once per thread and reused across channels.
 __global__ void gather_cols_kernel(const float *__restrict__ points, const int *__restrict__ idx, int C, int N,
                                    int M, int c_per_block, float *__restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.z;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= M) return;
@@ -284,6 +292,8 @@ __global__ void gather_cols_kernel(const float *__restrict__ points, const int *
 
 __global__ void scatter_cols_grad_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx, int C,
                                          int N, int M, int c_per_block, float *__restrict__ grad_points) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.z;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= M) return;
@@ -307,9 +317,9 @@ static int launch_gather_cols(const float *points, const int *idx, int B, int C,
   }
   dim3 grid(ceil_div(M, threads), cy, B);
   if (!grad)
-    gather_cols_kernel<<<grid, threads, 0, st>>>(points, idx, C, N, M, cpb, out);
+    launch_k(gather_cols_kernel, grid, threads, 0, st, points, idx, C, N, M, cpb, out);
   else
-    scatter_cols_grad_kernel<<<grid, threads, 0, st>>>(points, idx, C, N, M, cpb, out);
+    launch_k(scatter_cols_grad_kernel, grid, threads, 0, st, points, idx, C, N, M, cpb, out);
   return after_launch();
 }
 
@@ -327,6 +337,8 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(const float *
                                                                    const float *__restrict__ xyz, int N, int m,
                                                                    float radius2, int nsample,
                                                                    int *__restrict__ idx, int *__restrict__ counts) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[BQ_TILE * 3];
   __shared__ int live_warps;
   const int b = blockIdx.y;
@@ -386,6 +398,8 @@ constexpr int NN_TILE = 1024;
 __global__ void __launch_bounds__(128) three_nn_kernel(const float *__restrict__ unknown,
                                                        const float *__restrict__ known, int n, int m,
                                                        float *__restrict__ dist2, int *__restrict__ idx) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[NN_TILE * 3];
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,6 +439,8 @@ __global__ void __launch_bounds__(128) three_nn_kernel(const float *__restrict__
 __global__ void three_interpolate_kernel(const float *__restrict__ points, const int *__restrict__ idx,
                                          const float *__restrict__ weight, int C, int m, int n, int c_per_block,
                                          float *__restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.z;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -445,6 +461,8 @@ __global__ void three_interpolate_kernel(const float *__restrict__ points, const
 __global__ void three_interpolate_grad_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx,
                                               const float *__restrict__ weight, int C, int n, int m,
                                               int c_per_block, float *__restrict__ grad_points) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.z;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -474,6 +492,8 @@ __global__ void __launch_bounds__(128) knn_kernel(const float *__restrict__ p1, 
                                                   int P1, int P2, const int64_t *__restrict__ lengths1,
                                                   const int64_t *__restrict__ lengths2, int K,
                                                   float *__restrict__ dists, long long *__restrict__ idx) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[KNN_TILE * 3];
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -530,7 +550,7 @@ static int launch_fps_global(const float *xyz, int B, int N, int m, const int64_
   const int s_log2 = ilog2_ceil(S);
   const int nb_log2 = ilog2_ceil(ceil_div(N, S));
   if (s_log2 + nb_log2 > 31) return SLIDE_ERR_UNSUPPORTED;
-  fps_global_kernel<MODE><<<B, 1024, 0, st>>>(xyz, N, m, s_log2, nb_log2, lengths, Ks, start, temp, out);
+  launch_k(fps_global_kernel<MODE>, B, 1024, 0, st, xyz, N, m, s_log2, nb_log2, lengths, Ks, start, temp, out);
   return after_launch();
 }
 
@@ -540,6 +560,11 @@ int program_fps(int mode, const float *xyz, int ldx, int B, int N, int m, const 
 }
 
 long long g_launch_count = 0;
+static int pdl_from_env() {
+  const char *e = getenv("SLIDE_PDL");
+  return e ? atoi(e) != 0 : 1;
+}
+int g_pdl_enabled = pdl_from_env();
 static thread_local cudaError_t g_last_error = cudaSuccess;
 void set_cuda_error(cudaError_t e) { g_last_error = e; }
 
@@ -617,7 +642,7 @@ int slide_ball_query(const float *new_xyz, const float *xyz, int B, int N, int m
   if (B == 0 || m == 0) return SLIDE_OK;
   if (B > 65535) return SLIDE_ERR_UNSUPPORTED;
   dim3 grid(ceil_div(m, BQ_WARPS), B);
-  ball_query_kernel<<<grid, BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(new_xyz, xyz, N, m, radius * radius,
+  launch_k(ball_query_kernel, grid, BQ_WARPS * 32, 0, (cudaStream_t)stream, new_xyz, xyz, N, m, radius * radius,
                                                                       nsample, idx, counts);
   return after_launch();
 }
@@ -628,7 +653,7 @@ int slide_three_nn(const float *unknown, const float *known, int B, int n, int m
   if (B == 0 || n == 0) return SLIDE_OK;
   if (B > 65535) return SLIDE_ERR_UNSUPPORTED;
   dim3 grid(ceil_div(n, 128), B);
-  three_nn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(unknown, known, n, m, dist2, idx);
+  launch_k(three_nn_kernel, grid, 128, 0, (cudaStream_t)stream, unknown, known, n, m, dist2, idx);
   return after_launch();
 }
 
@@ -643,9 +668,9 @@ static int launch_interp(const float *a, const int *idx, const float *w, int B, 
   }
   dim3 grid(ceil_div(n, 256), cy, B);
   if (!grad)
-    three_interpolate_kernel<<<grid, 256, 0, st>>>(a, idx, w, C, m, n, cpb, out);
+    launch_k(three_interpolate_kernel, grid, 256, 0, st, a, idx, w, C, m, n, cpb, out);
   else
-    three_interpolate_grad_kernel<<<grid, 256, 0, st>>>(a, idx, w, C, n, m, cpb, out);
+    launch_k(three_interpolate_grad_kernel, grid, 256, 0, st, a, idx, w, C, n, m, cpb, out);
   return after_launch();
 }
 
@@ -671,13 +696,13 @@ int slide_knn_points(const float *p1, const float *p2, int B, int P1, int P2, in
   dim3 grid(ceil_div(P1, threads), B);
   cudaStream_t st = (cudaStream_t)stream;
   if (K <= 8)
-    knn_kernel<8><<<grid, threads, 0, st>>>(p1, p2, P1, P2, lengths1, lengths2, K, dists, (long long *)idx);
+    launch_k(knn_kernel<8>, grid, threads, 0, st, p1, p2, P1, P2, lengths1, lengths2, K, dists, (long long *)idx);
   else if (K <= 16)
-    knn_kernel<16><<<grid, threads, 0, st>>>(p1, p2, P1, P2, lengths1, lengths2, K, dists, (long long *)idx);
+    launch_k(knn_kernel<16>, grid, threads, 0, st, p1, p2, P1, P2, lengths1, lengths2, K, dists, (long long *)idx);
   else if (K <= 32)
-    knn_kernel<32><<<grid, threads, 0, st>>>(p1, p2, P1, P2, lengths1, lengths2, K, dists, (long long *)idx);
+    launch_k(knn_kernel<32>, grid, threads, 0, st, p1, p2, P1, P2, lengths1, lengths2, K, dists, (long long *)idx);
   else
-    knn_kernel<64><<<grid, threads, 0, st>>>(p1, p2, P1, P2, lengths1, lengths2, K, dists, (long long *)idx);
+    launch_k(knn_kernel<64>, grid, threads, 0, st, p1, p2, P1, P2, lengths1, lengths2, K, dists, (long long *)idx);
   return after_launch();
 }
 

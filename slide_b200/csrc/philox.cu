@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(256) philox_normal_slice_kernel(float *__restr
                                                                   unsigned long long offset0, unsigned long long inc,
                                                                   long long slice_begin, long long slice_len,
                                                                   long long threads_full) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)n_calls * slice_len;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long s = e / slice_len, r = e - s * slice_len;
@@ -51,7 +53,7 @@ extern "C" int slide_philox_normal_slice(float *out, long long out_call_stride, 
   const long long total = (long long)n_calls * slice_len;
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
-  philox_normal_slice_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+  launch_k(philox_normal_slice_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, 
       out, out_call_stride, n_calls, reverse, seed, offset, offset_increment, slice_begin, slice_len, 256LL * grid_full);
   return after_launch();
 }

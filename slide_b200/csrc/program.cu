@@ -19,6 +19,8 @@ namespace slide {
 // STEP_BEGIN: zero the statistics region, decrement the step counter
 // =====================================================================================================
 __global__ void step_begin_kernel(uint4 *__restrict__ zero, size_t n16, int *__restrict__ step) {
+  pdl_wait();
+  pdl_trigger();
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = i0; i < n16; i += stride) zero[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -36,6 +38,8 @@ template <int KCAP>
 __global__ void __launch_bounds__(128) knn_prog_kernel(const float *__restrict__ q, int ldq, int P1,
                                                        const float *__restrict__ ref, int ldr, int P2, int K,
                                                        int *__restrict__ idx, float *__restrict__ d2) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[PK_TILE * 3];
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,6 +106,8 @@ __global__ void __launch_bounds__(256) group_rows_kernel(int mode, const float *
                                                     const int *__restrict__ idx, int K, const float *__restrict__ d2,
                                                     float *__restrict__ out, int ldo, int inc_abs, int inc_ctr,
                                                     long long rows) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -159,6 +165,8 @@ __global__ void __launch_bounds__(256) group_elem_kernel(int mode, const float *
                                                     const int *__restrict__ idx, int K, const float *__restrict__ d2,
                                                     float *__restrict__ out, int ldo, int inc_abs, int inc_ctr,
                                                     long long rows, int W) {
+  pdl_wait();
+  pdl_trigger();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * W) return;
   const long long row = e / W;
@@ -205,6 +213,8 @@ __global__ void __launch_bounds__(256) softmax_wsum_kernel(const float *__restri
                                                            const float *__restrict__ Vt, int ldv, XFd xf,
                                                            const int *__restrict__ step_ptr, float *__restrict__ out,
                                                            int ldo, long long rows, int K, int C) {
+  pdl_wait();
+  pdl_trigger();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * C) return;
   const long long i = e / C;
@@ -255,6 +265,8 @@ __global__ void __launch_bounds__(256) softmax_wsum_kernel(const float *__restri
 // =====================================================================================================
 __global__ void copy_cols_kernel(const float *__restrict__ src, int lds, float *__restrict__ dst, int ldd,
                                  long long rows, int n) {
+  pdl_wait();
+  pdl_trigger();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * n) return;
   const long long r = e / n;
@@ -268,6 +280,8 @@ __global__ void ddpm_update_kernel(int mode, float *__restrict__ x, int ldx, con
                                    const float *__restrict__ noise, long long rows, int ncols, int col0,
                                    const float *__restrict__ table, const int *__restrict__ step_ptr, float clamp,
                                    const float *__restrict__ x0c, int ldx0c, const float *__restrict__ mask) {
+  pdl_wait();
+  pdl_trigger();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * ncols) return;
   const long long r = e / ncols;
@@ -303,6 +317,8 @@ __global__ void ddpm_update_kernel(int mode, float *__restrict__ x, int ldx, con
 
 __global__ void gather_rows_kernel(const float *__restrict__ src, int lds, int N, const int *__restrict__ idx, int m,
                                    float *__restrict__ dst, int ldd, int ncols, long long total_rows) {
+  pdl_wait();
+  pdl_trigger();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total_rows * ncols) return;
   const long long r = e / ncols;  // (sample, j)
@@ -315,6 +331,8 @@ __global__ void gather_rows_kernel(const float *__restrict__ src, int lds, int N
 __global__ void upsample_kernel(const float *__restrict__ coarse, int ldc, int coarse_c,
                                 const float *__restrict__ disp, int ldd, float *__restrict__ out, int ldo,
                                 long long rows, int factor, int Fd, float inv_sqrt_f, float scale) {
+  pdl_wait();
+  pdl_trigger();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * factor * Fd) return;
   const long long orow = e / Fd;
@@ -328,6 +346,8 @@ __global__ void upsample_kernel(const float *__restrict__ coarse, int ldc, int c
 
 __global__ void temb_kernel(const float *__restrict__ ts, const float *__restrict__ freq, int half,
                             float *__restrict__ out, int ldo, int rows) {
+  pdl_wait();
+  pdl_trigger();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * half) return;
   const int r = e / half, j = e - r * half;
@@ -371,6 +391,8 @@ struct PairArgs {
 // coordinate and residual loads of the whole batch are independent) instead of index -> gather chains per row.
 template <int RB, bool HAS_RES>
 __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
+  pdl_wait();
+  pdl_trigger();
   // thread = 4 consecutive columns (128-bit U gathers / residual loads / stores); the per-row index, coordinate and
   // distance loads are amortised over the 4 outputs
   const int s = blockIdx.y;
@@ -542,6 +564,8 @@ __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
 // out[s,c] = max_r xf(X)[s*R + r, c]: thread per (sample, column), coalesced in c (Pnet2Stage's global max-pool)
 __global__ void colmax_kernel(const float *__restrict__ X, int ldx, int R, int C, XFd xf,
                               const int *__restrict__ step_ptr, float *__restrict__ out, int ldo, int B) {
+  pdl_wait();
+  pdl_trigger();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)B * C) return;
   const int s = (int)(e / C), c = (int)(e - (long long)s * C);
@@ -581,6 +605,8 @@ __global__ void colmax_kernel(const float *__restrict__ X, int ldx, int R, int C
 // DiagonalGaussianDistribution: mode, or mean + exp(0.5 * clamp(logvar, -30, 20)) * noise (op by op like torch)
 __global__ void kl_kernel(const float *__restrict__ P, int ldp, int C, const float *__restrict__ noise, int ldn,
                           float *__restrict__ out, int ldo, long long rows) {
+  pdl_wait();
+  pdl_trigger();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * C) return;
   const long long r = e / C;
@@ -667,7 +693,7 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       const size_t n16 = (size_t)q[SB_ZERO_BYTES] / 16;
       unsigned g = grid_for((long long)n16, 256);
       if (g > 1184) g = 1184;
-      step_begin_kernel<<<g, 256, 0, st>>>(AP<uint4>(p, q[SB_ZERO_OFF]), n16, AP<int>(p, q[SB_STEP]));
+      launch_k(step_begin_kernel, g, 256, 0, st, AP<uint4>(p, q[SB_ZERO_OFF]), n16, AP<int>(p, q[SB_STEP]));
       return after_launch();
     }
     case SLIDE_OP_KNN: {
@@ -680,13 +706,13 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       float *d2 = AP<float>(p, q[KNN_D2]);
       const int ldq = (int)q[KNN_LDQ], ldr = (int)q[KNN_LDR];
       if (K <= 4)
-        knn_prog_kernel<4><<<grid, threads, 0, st>>>(qq, ldq, P1, rr, ldr, P2, K, idx, d2);
+        launch_k(knn_prog_kernel<4>, grid, threads, 0, st, qq, ldq, P1, rr, ldr, P2, K, idx, d2);
       else if (K <= 8)
-        knn_prog_kernel<8><<<grid, threads, 0, st>>>(qq, ldq, P1, rr, ldr, P2, K, idx, d2);
+        launch_k(knn_prog_kernel<8>, grid, threads, 0, st, qq, ldq, P1, rr, ldr, P2, K, idx, d2);
       else if (K <= 16)
-        knn_prog_kernel<16><<<grid, threads, 0, st>>>(qq, ldq, P1, rr, ldr, P2, K, idx, d2);
+        launch_k(knn_prog_kernel<16>, grid, threads, 0, st, qq, ldq, P1, rr, ldr, P2, K, idx, d2);
       else
-        knn_prog_kernel<32><<<grid, threads, 0, st>>>(qq, ldq, P1, rr, ldr, P2, K, idx, d2);
+        launch_k(knn_prog_kernel<32>, grid, threads, 0, st, qq, ldq, P1, rr, ldr, P2, K, idx, d2);
       return after_launch();
     }
     case SLIDE_OP_GROUP: {
@@ -694,7 +720,7 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       const int mode = (int)q[GRP_MODE];
       const int W = (int)q[GRP_C] + (mode == 0 ? 3 + (q[GRP_ABS] ? 3 : 0) + (q[GRP_CENTER] ? 3 : 0) : 11);
       if (W <= 16) {
-        group_elem_kernel<<<grid_for(rows * W, 256), 256, 0, st>>>(
+        launch_k(group_elem_kernel, grid_for(rows * W, 256), 256, 0, st, 
             mode, AP<float>(p, q[GRP_F]), (int)q[GRP_LDF], (int)q[GRP_C], AP<float>(p, q[GRP_XYZ]), (int)q[GRP_LDX],
             (int)q[GRP_N], AP<float>(p, q[GRP_CTR]), (int)q[GRP_LDCTR], (int)q[GRP_NP], AP<int>(p, q[GRP_IDX]),
             (int)q[GRP_K], AP<float>(p, q[GRP_D2]), AP<float>(p, q[GRP_OUT]), (int)q[GRP_LDO], (int)q[GRP_ABS],
@@ -702,7 +728,7 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       } else {
         unsigned g = grid_for(rows * 32, 256);
         if (g > 148 * 16) g = 148 * 16;
-        group_rows_kernel<<<g, 256, 0, st>>>(
+        launch_k(group_rows_kernel, g, 256, 0, st, 
             mode, AP<float>(p, q[GRP_F]), (int)q[GRP_LDF], (int)q[GRP_C], AP<float>(p, q[GRP_XYZ]), (int)q[GRP_LDX],
             (int)q[GRP_N], AP<float>(p, q[GRP_CTR]), (int)q[GRP_LDCTR], (int)q[GRP_NP], AP<int>(p, q[GRP_IDX]),
             (int)q[GRP_K], AP<float>(p, q[GRP_D2]), AP<float>(p, q[GRP_OUT]), (int)q[GRP_LDO], (int)q[GRP_ABS],
@@ -751,7 +777,7 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
     case SLIDE_OP_SOFTMAX_WSUM: {
       const long long rows = q[SM_ROWS];
       const int C = (int)q[SM_C];
-      softmax_wsum_kernel<<<grid_for(rows * C, 256), 256, 0, st>>>(
+      launch_k(softmax_wsum_kernel, grid_for(rows * C, 256), 256, 0, st, 
           AP<float>(p, q[SM_S]), (int)q[SM_LDS], AP<float>(p, q[SM_V]), (int)q[SM_LDV], make_xf(p, q + SM_XFV),
           AP<int>(p, q[SM_STEP]), AP<float>(p, q[SM_OUT]), (int)q[SM_LDO], rows, (int)q[SM_K], C);
       return after_launch();
@@ -759,14 +785,14 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
     case SLIDE_OP_COPY_COLS: {
       const long long rows = q[CP_ROWS];
       const int n = (int)q[CP_NCOLS];
-      copy_cols_kernel<<<grid_for(rows * n, 256), 256, 0, st>>>(AP<float>(p, q[CP_SRC]), (int)q[CP_LDS],
+      launch_k(copy_cols_kernel, grid_for(rows * n, 256), 256, 0, st, AP<float>(p, q[CP_SRC]), (int)q[CP_LDS],
                                                                AP<float>(p, q[CP_DST]), (int)q[CP_LDD], rows, n);
       return after_launch();
     }
     case SLIDE_OP_DDPM_UPDATE: {
       const long long rows = q[DD_ROWS];
       const int n = (int)q[DD_NCOLS];
-      ddpm_update_kernel<<<grid_for(rows * n, 256), 256, 0, st>>>(
+      launch_k(ddpm_update_kernel, grid_for(rows * n, 256), 256, 0, st, 
           (int)q[DD_MODE], AP<float>(p, q[DD_X]), (int)q[DD_LDX], AP<float>(p, q[DD_EPS]), (int)q[DD_LDE],
           AP<float>(p, q[DD_NOISE]), rows, n, (int)q[DD_COL0], WP<float>(p, q[DD_TABLE_W]), AP<int>(p, q[DD_STEP]),
           op.f[0], AP<float>(p, q[DD_X0C]), (int)q[DD_LDX0C], AP<float>(p, q[DD_MASK]));
@@ -778,7 +804,7 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
     case SLIDE_OP_GATHER_ROWS: {
       const long long total = (long long)q[GA_B] * q[GA_M];
       const int n = (int)q[GA_NCOLS];
-      gather_rows_kernel<<<grid_for(total * n, 256), 256, 0, st>>>(AP<float>(p, q[GA_SRC]), (int)q[GA_LDS],
+      launch_k(gather_rows_kernel, grid_for(total * n, 256), 256, 0, st, AP<float>(p, q[GA_SRC]), (int)q[GA_LDS],
                                                                   (int)q[GA_N], AP<int>(p, q[GA_IDX]), (int)q[GA_M],
                                                                   AP<float>(p, q[GA_DST]), (int)q[GA_LDD], n, total);
       return after_launch();
@@ -786,14 +812,14 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
     case SLIDE_OP_UPSAMPLE: {
       const long long rows = q[UP_ROWS];
       const int factor = (int)q[UP_FACTOR], Fd = (int)q[UP_F];
-      upsample_kernel<<<grid_for(rows * factor * Fd, 256), 256, 0, st>>>(
+      launch_k(upsample_kernel, grid_for(rows * factor * Fd, 256), 256, 0, st, 
           AP<float>(p, q[UP_COARSE]), (int)q[UP_LDC], (int)q[UP_COARSE_C], AP<float>(p, q[UP_DISP]), (int)q[UP_LDD],
           AP<float>(p, q[UP_OUT]), (int)q[UP_LDO], rows, factor, Fd, op.f[0], op.f[1]);
       return after_launch();
     }
     case SLIDE_OP_TEMB: {
       const int rows = (int)q[TE_ROWS], half = (int)q[TE_HALF];
-      temb_kernel<<<grid_for((long long)rows * half, 256), 256, 0, st>>>(
+      launch_k(temb_kernel, grid_for((long long)rows * half, 256), 256, 0, st, 
           AP<float>(p, q[TE_TS]), WP<float>(p, q[TE_FREQ_W]), half, AP<float>(p, q[TE_OUT]), (int)q[TE_LDO], rows);
       return after_launch();
     }
@@ -851,16 +877,16 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       const int threads = cols4 >= 256 ? 256 : ((cols4 + 31) / 32) * 32;
       dim3 grid(ceil_div(a.np, pb), B);
       if (a.res)
-        pair_kernel<4, true><<<grid, threads, 0, st>>>(a);
+        launch_k(pair_kernel<4, true>, grid, threads, 0, st, a);
       else
-        pair_kernel<8, false><<<grid, threads, 0, st>>>(a);
+        launch_k(pair_kernel<8, false>, grid, threads, 0, st, a);
       return after_launch();
     }
     case SLIDE_OP_COLMAX: {
       const int B = (int)q[CM_B], C = (int)q[CM_C];
       XFd xf = make_xf(p, q + CM_XF);
       if (xf.stats && xf.R != (int)q[CM_R]) return SLIDE_ERR_UNSUPPORTED;
-      colmax_kernel<<<grid_for((long long)B * C, 128), 128, 0, st>>>(AP<float>(p, q[CM_X]), (int)q[CM_LDX], (int)q[CM_R], C,
+      launch_k(colmax_kernel, grid_for((long long)B * C, 128), 128, 0, st, AP<float>(p, q[CM_X]), (int)q[CM_LDX], (int)q[CM_R], C,
                                                                    xf, AP<int>(p, q[CM_STEP]), AP<float>(p, q[CM_OUT]),
                                                                    (int)q[CM_LDO], B);
       return after_launch();
@@ -868,7 +894,7 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
     case SLIDE_OP_KL: {
       const long long rows = q[KL_ROWS];
       const int C = (int)q[KL_C];
-      kl_kernel<<<grid_for(rows * C, 256), 256, 0, st>>>(AP<float>(p, q[KL_P]), (int)q[KL_LDP], C,
+      launch_k(kl_kernel, grid_for(rows * C, 256), 256, 0, st, AP<float>(p, q[KL_P]), (int)q[KL_LDP], C,
                                                          AP<float>(p, q[KL_NOISE]), (int)q[KL_LDN],
                                                          AP<float>(p, q[KL_OUT]), (int)q[KL_LDO], rows);
       return after_launch();

@@ -248,6 +248,10 @@ class SlidePipeline(object):
         latent_ddpm_keypoint_conditional_generation.py with --keypoint_file).  complete_x0 (Bl,16,3+F) + keypoint_mask
         (Bl,16): local resampling (--local_resampling; the pipeline must have been built with local_resampling=True)."""
         dev = self.device
+        if not hasattr(self, "_stage_ev"):
+            self._stage_ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = self._stage_ev
+        ev[0].record()
         if keypoints is None:
             # 1. position DDPM
             self.pos.x_view().copy_(self._pos_xT_dev.view(-1, 3))
@@ -255,6 +259,7 @@ class SlidePipeline(object):
             kp = self.pos.x_view().view(self.Bl, 16, 3)
         else:
             kp = keypoints.to(dev).float().view(self.Bl, 16, 3)
+        ev[1].record()
         if self.lat.local_resampling:
             if complete_x0 is None:  # plain sampling through a resampling-capable program: re-sample everything
                 complete_x0 = torch.zeros(self.Bl, 16, self.lat.C, device=dev)
@@ -271,11 +276,20 @@ class SlidePipeline(object):
         nz = self.lat.noise_view().view(self.T_lat, self.Bl, 16, self.lat.C)
         self.noise_path = rng.randn_sequence(nz, (self.B, 16, self.lat.C), self.rank * self.Bl, reverse=True)
         self.lat.run(self.ddpm_steps)
+        ev[2].record()
         feat = x[:, :, 3:].contiguous()
         self.keypoint, self.keypoint_feature = kp, feat  # (Bl,16,3), (Bl,16,F): what the reference also returns
         # 3. decode
         self.dec.run(kp.contiguous(), feat, self._labels, self._starts_dev, self.out)
+        ev[3].record()
         return self.out
+
+    def stage_ms(self):
+        """Device milliseconds of the last sample_resident() call: position DDPM, feature DDPM (incl. its noise draw), decode."""
+        ev = self._stage_ev
+        ev[3].synchronize()
+        return {"position_ddpm": ev[0].elapsed_time(ev[1]), "latent_ddpm": ev[1].elapsed_time(ev[2]),
+                "decode": ev[2].elapsed_time(ev[3])}
 
     def sample(self):
         """Public entry: host buffers in (pinned), device tensor out."""
