@@ -39,7 +39,7 @@ inline int cuda_rc(cudaError_t e) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-extern int g_pdl_enabled;  // SLIDE_PDL (default 1); read once
+extern int g_pdl_enabled;  // SLIDE_PDL (default 0: measured neutral-to-negative under graph replay, profiles/r02_pdl_ab.txt); read once
 
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {

@@ -48,7 +48,8 @@ __device__ int g_tc_error = 0;  // set when a barrier wait times out (never in a
 // Phase stamps of every CTA (tuning builds only: -DTC_TIMELINE, see tools/tc_timeline.py).  Slot layout per CTA:
 // 0 start | 1 prologue done | 2 first A loads issued | 3 first stage published | 4 last stage published |
 // 5 first stage seen by the MMA thread | 6 last commit issued | 7 accumulator ready | 8 resid table done |
-// 9 chunks drained | 10 after the closing barrier | 11 end | 12 globaltimer at start | 13 SM id
+// 9 chunks drained | 10 after the closing barrier | 11 end | 12 globaltimer at start | 13 SM id |
+// 14 first chunk read from tensor memory (warp 0) | 15 first chunk done (warp 0)
 #ifdef TC_TIMELINE
 constexpr int TL_SLOTS = 16, TL_CTAS = 8192;
 __device__ unsigned long long g_tc_tl[TL_SLOTS * TL_CTAS];
@@ -558,6 +559,7 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
+      TL(14, tid == 0 && c0 == 0);
       // transpose: thread (= row) writes its 32 columns; afterwards lane = column
 #pragma unroll
       for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
@@ -712,6 +714,7 @@ __global__ void __maxnreg__(TC_MAXNREG) gemm_tc_kernel(GemmArgs a, const float *
         }
       }
       __syncwarp();
+      TL(15, tid == 0 && c0 == 0);
     }
   }
   TL(9, tid == 0);

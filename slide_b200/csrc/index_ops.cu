@@ -562,7 +562,7 @@ int program_fps(int mode, const float *xyz, int ldx, int B, int N, int m, const 
 long long g_launch_count = 0;
 static int pdl_from_env() {
   const char *e = getenv("SLIDE_PDL");
-  return e ? atoi(e) != 0 : 1;
+  return e ? atoi(e) != 0 : 0;
 }
 int g_pdl_enabled = pdl_from_env();
 static thread_local cudaError_t g_last_error = cudaSuccess;

@@ -77,11 +77,12 @@ def main():
         starts = np.sort(t[:, 12] - g0)
         print("   CTA start times (us): p10 %.1f p50 %.1f p90 %.1f max %.1f" % tuple(
             np.percentile(starts, q) / 1e3 for q in (10, 50, 90, 100)))
-        for s in range(1, 12):
+        for s in list(range(1, 9)) + [14, 15] + list(range(9, 12)):
             if (t[:, s] == 0).all():
                 continue
             d = t[:, s] - t[:, 0]
-            print("   %-12s at median %7.0f cyc  p90 %7.0f" % (NAMES[s], np.median(d), np.percentile(d, 90)))
+            name = NAMES[s] if s < 12 else {14: "chunk0-read", 15: "chunk0-done"}[s]
+            print("   %-12s at median %7.0f cyc  p90 %7.0f" % (name, np.median(d), np.percentile(d, 90)))
 
 
 if __name__ == "__main__":
