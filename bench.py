@@ -220,9 +220,23 @@ def extra_configs(cfg, args):
         pos.x_view().normal_()
         pos.run()
     us = time_events(run_pos, 1, warm=1)
-    out["config2"] = {"workload": "position DDPM 1000 steps, batch 32, airplane", "ms": us / 1e3, "us_per_step": us / d["T"],
+    out["config2"] = {"workload": "position DDPM 1000 steps, batch 32, airplane", "executor": "one kernel per record",
+                      "ms": us / 1e3, "us_per_step": us / d["T"],
                       "shapes_per_s": 32 / (us / 1e6), "launches_per_step": pos.launches_per_step(),
                       "finite": bool(torch.isfinite(pos.x_view()).all().item())}
+    del pos
+    # the same chain as ONE sample-resident kernel per step (what SlidePipeline picks at this batch size)
+    pos = pipeline.DDPMSampler(cfg["position_ddpm"]["pointnet_config"], sds["position"], 32,
+                               engine.position_table(d["T"], d["beta_0"], d["beta_T"]), 0, 0, d["T"], dev, backend=args.backend,
+                               resident=dict(cluster=4, precise=False))
+    if pos.resident:
+        pos.set_labels(torch.full((32,), cfg["label"], dtype=torch.long, device=dev))
+        pos.noise_view().normal_()
+        us = time_events(run_pos, 1, warm=1)
+        out["config2"]["resident"] = {"executor": "sample-resident kernel, cluster of 4 CTAs per sample", "ms": us / 1e3,
+                                      "us_per_step": us / d["T"], "shapes_per_s": 32 / (us / 1e6),
+                                      "launches_per_step": pos.launches_per_step(),
+                                      "finite": bool(torch.isfinite(pos.x_view()).all().item())}
     del pos
     # config 3: feature DDPM on fixed keypoints + decode to 2048 points, batch 128
     p3 = pipeline.SlidePipeline(cfg, 128, backend=args.backend, decode_chunk=min(args.decode_chunk, 128))

@@ -166,9 +166,15 @@ class SlidePipeline(object):
     """position DDPM -> latent DDPM -> decode for `local_batch` shapes on this GPU (rank `rank` of `world`)."""
 
     def __init__(self, cfg, global_batch, rank=0, world=1, device=None, state_dicts=None, decode_chunk=128,
-                 ddpm_steps=None, backend="auto", local_resampling=False, position_sampler=None):
+                 ddpm_steps=None, backend="auto", local_resampling=False, position_sampler=None,
+                 position_resident="auto"):
         """position_sampler: None = the 1000-step ancestral sampler (util.sampling), or the FastDPM STEP sampler
-        dict(method="step", length=L, schedule="linear"|"quadratic", kappa=k) (util_fastdpmv2.fast_sampling_function_v2)."""
+        dict(method="step", length=L, schedule="linear"|"quadratic", kappa=k) (util_fastdpmv2.fast_sampling_function_v2).
+        position_resident: how the position DDPM's step is executed -- None = one kernel per record, dict(cluster=2|4,
+        precise=bool) = ONE sample-resident kernel per step (resident.py), "auto" = resident when this GPU's batch fits
+        one wave of clusters (batch <= SMs / 2), where the step is bound by per-kernel latency (measured on B200 at
+        batch 32: 276 us / step resident, cluster 4, against 413 us for 62 record kernels; at batch 256 the record path
+        wins, 757 against 1250 us)."""
         assert global_batch % world == 0
         self.cfg, self.B, self.rank, self.world = cfg, global_batch, rank, world
         self.Bl = global_batch // world
@@ -178,11 +184,18 @@ class SlidePipeline(object):
         d = pos["diffusion_config"]
         self.T_lat = lat["standard_diffusion_config"]["num_diffusion_timesteps"]
         self.position_sampler = position_sampler
+        if position_resident == "auto":
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            position_resident = None
+            if self.Bl * 4 <= sms:
+                position_resident = dict(cluster=4, precise=False)
+            elif self.Bl * 2 <= sms:
+                position_resident = dict(cluster=2, precise=False)
         if position_sampler is None:
             self.T_pos = d["T"]
             self.pos = DDPMSampler(pos["pointnet_config"], sds["position"], self.Bl,
                                    engine.position_table(d["T"], d["beta_0"], d["beta_T"]), 0, 0, self.T_pos, self.device,
-                                   backend=backend)
+                                   backend=backend, resident=position_resident)
         else:
             ps = position_sampler
             ts, table = engine.fast_position_schedule(ps["method"], ps["length"], ps["schedule"], ps["kappa"], d)
