@@ -1108,18 +1108,12 @@ __global__ void __launch_bounds__(XFA ? TCP_XFA_THREADS : TCP_THREADS, 1)
           continue;
         }
         float ssum = 0.f, ssq = 0.f;
-        // all 32 staged values of the lane's column are requested at once: under load (tensor-core operand reads, the
-        // copy engine and the transform warps share the 128 B/clk shared-memory pipe) a shared-memory load takes ~350
-        // cycles, and four dependent batches of 8 paid that four times per chunk (tools/tc_timeline.py)
-        float tv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tv[i] = tbuf[i * 33 + lane];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int mb = mw + 8 * q;
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = tv[8 * q + i] + bias;
+          for (int i = 0; i < 8; ++i) v[i] = tbuf[(8 * q + i) * 33 + lane] + bias;
           if (a.ev) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += evc[q];
