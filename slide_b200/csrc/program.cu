@@ -561,6 +561,224 @@ __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
   }
 }
 
+// ---- PAIR with the source rows staged in shared memory ---------------------------------------------------------------
+// For the denoisers the neighbours of a point come from the sample's own 16 points, so the whole gather source fits on
+// chip: the CTA first builds  Us[j][n] = U[j][n] + x_j . wx[n]  for every source point j of its sample and
+// Vs[i][n] = c_i . wc[n] + bias[n]  for its points (the same fused-multiply-add chains, in the same order, as the
+// gather kernel above: results are bit-identical), then every output row is  act(Us[idx] + Vs[i] (+ the two distance
+// terms) (+ the transformed residual))  -- one 16-byte shared-memory read, 4 adds and one 16-byte store per 4 outputs, no
+// dependent global gather and no per-row address arithmetic (the gather kernel spends ~47 instructions per output).
+// Thread = (row group rg, 4 columns ct); rows of a group are processed 4 at a time so that the residual loads and the
+// stores of 4 rows are in flight together.
+constexpr int PS_THREADS = 256;
+constexpr int PS_MAX_SRC = 64;
+
+template <bool HAS_RES, bool HAS_D2>
+__global__ void __launch_bounds__(PS_THREADS) pair_smem_kernel(PairArgs a, int CT, int RG, int ldn) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) float ps_smem[];
+  const int s = blockIdx.y;
+  const int p0 = blockIdx.x * a.pb;
+  const int pbl = min(a.pb, a.np - p0);
+  const int rows = pbl * a.K;
+  float *Us = ps_smem;                                   // [nsrc][ldn]
+  float *Vs = Us + (size_t)a.nsrc * ldn;                 // [pb][ldn]
+  float *part = Vs + (size_t)a.pb * ldn;                 // [RG][ldn][2] column sums per row group
+  int *idx_s = reinterpret_cast<int *>(part + (size_t)RG * ldn * 2);  // [pb * K]
+  float *dk_s = reinterpret_cast<float *>(idx_s + a.pb * a.K);        // [pb * K] squared distances
+  float *w_s = dk_s + a.pb * a.K;                                       // [pb * K] interpolation weights
+  const int tid = threadIdx.x;
+  const int rg = tid / CT, ct = tid - rg * CT;
+  const bool live = rg < RG;
+  const int n = 4 * ct;
+  const int step = a.step ? *a.step : 0;
+  const size_t prow0 = ((size_t)s * a.np + p0) * a.K;
+
+  // ---- per-row scalars
+  for (int r = tid; r < rows; r += PS_THREADS) {
+    idx_s[r] = __ldg(a.idx + prow0 + r);
+    if (HAS_D2) dk_s[r] = __ldg(a.d2 + prow0 + r);
+  }
+  if (HAS_D2) {
+    __syncthreads();
+    if (tid < pbl) {
+      // the reference's left-to-right fp32 sum over the K neighbours, then w_k = (1 / (d_k + 1e-8)) / sum
+      float inv_sum = 0.f;
+      for (int k = 0; k < a.K; ++k) inv_sum = __fadd_rn(inv_sum, __fdiv_rn(1.0f, __fadd_rn(dk_s[tid * a.K + k], 1e-8f)));
+      for (int k = 0; k < a.K; ++k)
+        w_s[tid * a.K + k] = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(dk_s[tid * a.K + k], 1e-8f)), inv_sum);
+    }
+  }
+  // ---- per-column constants of this thread's 4 columns
+  bool on[4];
+  float wx[4][3], wc[4][3], bias[4], wd[4], ww[4], rsc[4], rsh[4], radd[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    on[u] = live && n + u < a.N;
+    const int nn = on[u] ? n + u : 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      wx[u][d] = __ldg(a.wx + nn * 3 + d);
+      wc[u][d] = __ldg(a.wc + nn * 3 + d);
+    }
+    bias[u] = a.bias ? __ldg(a.bias + nn) : 0.f;
+    wd[u] = HAS_D2 ? __ldg(a.wd + nn) : 0.f;
+    ww[u] = HAS_D2 ? __ldg(a.ww + nn) : 0.f;
+    rsc[u] = 1.f;
+    rsh[u] = 0.f;
+    radd[u] = 0.f;
+    if (HAS_RES) {
+      if (a.xfr.stats) {
+        const int ch = a.xfr.choff + nn;
+        if (ch < a.xfr.nnorm) {
+          const int G = a.xfr.nnorm / a.xfr.cg;
+          const double *st = a.xfr.stats + ((size_t)s * G + ch / a.xfr.cg) * 2;
+          const double m = st[0] * (double)a.xfr.inv_count;
+          double var = st[1] * (double)a.xfr.inv_count - m * m;
+          var = var < 0.0 ? 0.0 : var;
+          rsc[u] = (float)(1.0 / sqrt(var + (double)SLIDE_GN_EPS)) * __ldg(a.xfr.gamma + ch);
+          rsh[u] = __ldg(a.xfr.beta + ch) - (float)m * rsc[u];
+        }
+      }
+      if (a.xfr.addvec) {
+        const long long arow = a.xfr.addmode == 0 ? s : (a.xfr.addmode == 1 ? step : 0);
+        radd[u] = a.xfr.addvec[arow * a.xfr.addld + nn];
+      }
+    }
+  }
+  const bool any = on[0], full = on[3];
+  // ---- stage Us (all source points of the sample) and Vs (this CTA's points)
+  if (any) {
+    for (int j = rg; j < a.nsrc; j += RG) {
+      const float *x = a.xyz + ((size_t)s * a.nsrc + j) * a.ldx;
+      const float x0 = __ldg(x), x1 = __ldg(x + 1), x2 = __ldg(x + 2);
+      const float4 u4 = __ldg(reinterpret_cast<const float4 *>(a.U + ((size_t)s * a.nsrc + j) * a.ldu + n));
+      const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+      float t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = fmaf(x2, wx[u][2], fmaf(x1, wx[u][1], fmaf(x0, wx[u][0], uu[u])));
+      *reinterpret_cast<float4 *>(Us + (size_t)j * ldn + n) = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    for (int il = rg; il < pbl; il += RG) {
+      const float *c = a.ctr + ((size_t)s * a.np + p0 + il) * a.ldctr;
+      const float c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+      float t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = fmaf(c2, wc[u][2], fmaf(c1, wc[u][1], fmaf(c0, wc[u][0], bias[u])));
+      *reinterpret_cast<float4 *>(Vs + (size_t)il * ldn + n) = make_float4(t[0], t[1], t[2], t[3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- output rows
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (any) {
+    for (int r0 = rg; r0 < rows; r0 += 4 * RG) {
+      float4 r4[4];
+      bool ron[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int r = r0 + b * RG;
+        ron[b] = r < rows;
+        r4[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (HAS_RES && ron[b]) {
+          const float *rp = a.res + (prow0 + r) * a.ldr + n;
+          if (full) {
+            r4[b] = __ldcs(reinterpret_cast<const float4 *>(rp));
+          } else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (on[u]) t[u] = rp[u];
+            r4[b] = make_float4(t[0], t[1], t[2], t[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (!ron[b]) continue;
+        const int r = r0 + b * RG;
+        const int il = r / a.K;
+        const float4 u4 = *reinterpret_cast<const float4 *>(Us + (size_t)idx_s[r] * ldn + n);
+        const float4 v4 = *reinterpret_cast<const float4 *>(Vs + (size_t)il * ldn + n);
+        float v[4] = {u4.x + v4.x, u4.y + v4.y, u4.z + v4.z, u4.w + v4.w};
+        const float rr[4] = {r4[b].x, r4[b].y, r4[b].z, r4[b].w};
+        float dk = 0.f, w = 0.f;
+        if (HAS_D2) {
+          dk = dk_s[r];
+          w = w_s[r];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float t = v[u];
+          if (HAS_D2) t = fmaf(w, ww[u], fmaf(dk, wd[u], t));
+          if (HAS_RES) {
+            float q = fmaf(rr[u], rsc[u], rsh[u]);
+            if (a.xfr.relu) q = fmaxf(q, 0.f);
+            t += q + radd[u];
+          }
+          if (a.act == 1) t = fmaxf(t, 0.f);
+          v[u] = on[u] ? t : 0.f;
+          ssum[u] += v[u];
+          ssq[u] = fmaf(v[u], v[u], ssq[u]);
+        }
+        float *op = a.out + (prow0 + r) * a.ldo + n;
+        if (full) {
+          *reinterpret_cast<float4 *>(op) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (on[u]) op[u] = v[u];
+        }
+      }
+    }
+  }
+  // ---- statistics: column sums per row group -> per GroupNorm group -> one fp64 atomic pair per group
+  if (a.st_stats) {
+    if (any) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<float2 *>(part + ((size_t)rg * ldn + n + u) * 2) = make_float2(ssum[u], ssq[u]);
+    }
+    __syncthreads();
+    const int G = a.st_nnorm / a.st_cg;
+    const int lim = min(a.N, a.st_nnorm - a.st_choff);  // local columns [0, lim) are normalised channels
+    if (lim > 0) {
+      const int g_first = a.st_choff / a.st_cg, g_last = (a.st_choff + lim - 1) / a.st_cg;
+      for (int gi = g_first + tid; gi <= g_last; gi += PS_THREADS) {
+        const int c0 = max(0, gi * a.st_cg - a.st_choff), c1 = min(lim, (gi + 1) * a.st_cg - a.st_choff);
+        float ts = 0.f, tq = 0.f;
+        for (int g = 0; g < RG; ++g)
+          for (int c = c0; c < c1; ++c) {
+            const float2 v = *reinterpret_cast<const float2 *>(part + ((size_t)g * ldn + c) * 2);
+            ts += v.x;
+            tq += v.y;
+          }
+        double *slot = a.st_stats + ((size_t)s * G + gi) * 2;
+        atomicAdd(slot, (double)ts * (double)a.st_weight);
+        atomicAdd(slot + 1, (double)tq * (double)a.st_weight);
+      }
+    }
+  }
+}
+
+template <bool HAS_RES, bool HAS_D2>
+static int launch_pair_smem(const PairArgs &a, int B, int CT, int RG, int ldn, size_t smem, cudaStream_t st) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pair_smem_kernel<HAS_RES, HAS_D2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         160 * 1024);
+    if (e != cudaSuccess) return cuda_rc(e);
+    configured[dev] = true;
+  }
+  dim3 grid(ceil_div(a.np, a.pb), B);
+  launch_k(pair_smem_kernel<HAS_RES, HAS_D2>, grid, PS_THREADS, smem, st, a, CT, RG, ldn);
+  return after_launch();
+}
+
 // out[s,c] = max_r xf(X)[s*R + r, c]: thread per (sample, column), coalesced in c (Pnet2Stage's global max-pool)
 __global__ void colmax_kernel(const float *__restrict__ X, int ldx, int R, int C, XFd xf,
                               const int *__restrict__ step_ptr, float *__restrict__ out, int ldo, int B) {
@@ -650,7 +868,7 @@ namespace {
 
 // PAIR launch-shape knobs: environment read once (slide_tc_reload_tuning() re-reads)
 bool g_pair_tuning_loaded = false;
-int g_pair_min_ctas = 2368, g_pair_min_rows = 32;
+int g_pair_min_ctas = 2368, g_pair_min_rows = 32, g_pair_smem = 1;
 
 template <typename T>
 inline T *AP(slide_program *p, int64_t off) {
@@ -858,21 +1076,37 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       if (!a.U || !a.out || !a.idx || a.K <= 0 || B <= 0 || B > 65535) return SLIDE_ERR_INVALID;
       if (a.d2 && (!a.wd || !a.ww)) return SLIDE_ERR_INVALID;
       if (a.res && a.xfr.stats && a.xfr.R != a.np * a.K) return SLIDE_ERR_UNSUPPORTED;
-      // points per CTA: aim for >= 16 CTAs per SM overall, at least 32 rows per CTA
-      int pb = a.np;
-      // A/B on B200 (feature-DDPM step): (592 CTAs, 64 rows) 1764 us, (2368, 32) 1750 us, (4736, 16) 1784 us
-      if (!g_pair_tuning_loaded) {
-        const char *e_ctas = getenv("SLIDE_PAIR_MIN_CTAS"), *e_rows = getenv("SLIDE_PAIR_MIN_ROWS");
-        g_pair_min_ctas = e_ctas ? atoi(e_ctas) : 2368;
-        g_pair_min_rows = e_rows ? atoi(e_rows) : 32;
-        g_pair_tuning_loaded = true;
-      }
-      const int min_ctas = g_pair_min_ctas, min_rows = g_pair_min_rows;
-      while (pb > 1 && (long long)B * ceil_div(a.np, pb) < min_ctas && pb * a.K > min_rows) pb = (pb + 1) / 2;
-      a.pb = pb;
       if (((uintptr_t)a.U & 15) || (a.ldu & 3) || ((uintptr_t)a.out & 15) || (a.ldo & 3) ||
           (a.res && (((uintptr_t)a.res & 15) || (a.ldr & 3))))
         return SLIDE_ERR_UNSUPPORTED;  // 128-bit row accesses
+      if (!g_pair_tuning_loaded) {
+        const char *e_ctas = getenv("SLIDE_PAIR_MIN_CTAS"), *e_rows = getenv("SLIDE_PAIR_MIN_ROWS"),
+                   *e_smem = getenv("SLIDE_PAIR_SMEM");
+        g_pair_min_ctas = e_ctas ? atoi(e_ctas) : 2368;
+        g_pair_min_rows = e_rows ? atoi(e_rows) : 32;
+        g_pair_smem = e_smem ? atoi(e_smem) : 1;
+        g_pair_tuning_loaded = true;
+      }
+      // small gather source (the denoisers: the sample's own 16 points): stage it in shared memory
+      if (g_pair_smem && a.nsrc <= PS_MAX_SRC && a.N <= 4 * PS_THREADS) {
+        const int CT = ceil_div(a.N, 4), RG = PS_THREADS / CT, ldn = 4 * CT;
+        int pbs = a.np < 4 ? a.np : 4;  // points per CTA: 64 rows at K = 16; fewer when the grid would be under 4 waves
+        while (pbs > 1 && (long long)B * ceil_div(a.np, pbs) < 592) pbs = (pbs + 1) / 2;
+        const size_t smem = ((size_t)(a.nsrc + pbs + 2 * RG) * ldn + 3 * (size_t)pbs * a.K) * 4;
+        if (smem <= 160 * 1024) {
+          a.pb = pbs;
+          if (a.res) return a.d2 ? launch_pair_smem<true, true>(a, B, CT, RG, ldn, smem, st)
+                                 : launch_pair_smem<true, false>(a, B, CT, RG, ldn, smem, st);
+          return a.d2 ? launch_pair_smem<false, true>(a, B, CT, RG, ldn, smem, st)
+                      : launch_pair_smem<false, false>(a, B, CT, RG, ldn, smem, st);
+        }
+      }
+      // points per CTA: aim for >= 16 CTAs per SM overall, at least 32 rows per CTA
+      int pb = a.np;
+      // A/B on B200 (feature-DDPM step): (592 CTAs, 64 rows) 1764 us, (2368, 32) 1750 us, (4736, 16) 1784 us
+      const int min_ctas = g_pair_min_ctas, min_rows = g_pair_min_rows;
+      while (pb > 1 && (long long)B * ceil_div(a.np, pb) < min_ctas && pb * a.K > min_rows) pb = (pb + 1) / 2;
+      a.pb = pb;
       const int cols4 = ceil_div(a.N, 4);
       const int threads = cols4 >= 256 ? 256 : ((cols4 + 31) / 32) * 32;
       dim3 grid(ceil_div(a.np, pb), B);
