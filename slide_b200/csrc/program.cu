@@ -595,20 +595,10 @@ __global__ void __launch_bounds__(PS_THREADS) pair_smem_kernel(PairArgs a, int C
   const int step = a.step ? *a.step : 0;
   const size_t prow0 = ((size_t)s * a.np + p0) * a.K;
 
-  // ---- per-row scalars
+  // ---- per-row scalars (stored together with the staged rows: one barrier for both)
   for (int r = tid; r < rows; r += PS_THREADS) {
     idx_s[r] = __ldg(a.idx + prow0 + r);
     if (HAS_D2) dk_s[r] = __ldg(a.d2 + prow0 + r);
-  }
-  if (HAS_D2) {
-    __syncthreads();
-    if (tid < pbl) {
-      // the reference's left-to-right fp32 sum over the K neighbours, then w_k = (1 / (d_k + 1e-8)) / sum
-      float inv_sum = 0.f;
-      for (int k = 0; k < a.K; ++k) inv_sum = __fadd_rn(inv_sum, __fdiv_rn(1.0f, __fadd_rn(dk_s[tid * a.K + k], 1e-8f)));
-      for (int k = 0; k < a.K; ++k)
-        w_s[tid * a.K + k] = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(dk_s[tid * a.K + k], 1e-8f)), inv_sum);
-    }
   }
   // ---- per-column constants of this thread's 4 columns
   bool on[4];
@@ -670,6 +660,16 @@ __global__ void __launch_bounds__(PS_THREADS) pair_smem_kernel(PairArgs a, int C
     }
   }
   __syncthreads();
+  if (HAS_D2) {
+    if (tid < pbl) {
+      // the reference's left-to-right fp32 sum over the K neighbours, then w_k = (1 / (d_k + 1e-8)) / sum
+      float inv_sum = 0.f;
+      for (int k = 0; k < a.K; ++k) inv_sum = __fadd_rn(inv_sum, __fdiv_rn(1.0f, __fadd_rn(dk_s[tid * a.K + k], 1e-8f)));
+      for (int k = 0; k < a.K; ++k)
+        w_s[tid * a.K + k] = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(dk_s[tid * a.K + k], 1e-8f)), inv_sum);
+    }
+    __syncthreads();
+  }
 
   // ---- output rows
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};

@@ -146,12 +146,17 @@ class _Grouped(object):
         """convs: list of Params of every conv that reads the group.  Chooses the form and emits the GROUP record
         (materialised) or the shared U GEMM (factored).  A/B on B200 (feature / position DDPM, batch 256): factoring pays
         once the pair-level GEMMs it removes are large -- Ctot x (sum of conv widths) above ~2.5e5 -- below that the
-        tcgen05 GEMMs over the grouped tensor are cheaper than the extra U GEMM + the gather-bound PAIR kernels."""
+        tcgen05 GEMMs over the grouped tensor are cheaper than the extra U GEMM + the gather-bound PAIR kernels (large
+        gather sources: decode / encode levels)."""
         ntot = sum(int(Pc["weight"].shape[0]) for Pc in convs)
         mode = os.environ.get("SLIDE_FACTOR_GROUP", "auto")
         if getattr(self.ctx, "factor_group", None):  # resident plans need the factored form (no grouped tensor at all)
             mode = "1"
-        self.factored = (mode == "1") or (mode == "auto" and self.Ctot * ntot >= FACTOR_MIN_WORK)
+        # (round 2) with the gather source staged in shared memory (pair_smem_kernel: source = the sample's own <= 64
+        # points) PAIR is cheap, and at >= 32768 pair rows factoring wins for every module of both denoisers (B200, batch
+        # 256: position step 757 -> 710 us, feature step 1575 -> 1525 us); at batch 32 it loses (425 -> 445 us)
+        small_src = self.feats.R <= 64 and self.B * self.R >= 32768
+        self.factored = (mode == "1") or (mode == "auto" and (self.Ctot * ntot >= FACTOR_MIN_WORK or small_src))
         if not self.factored:
             self._materialise()
             return
