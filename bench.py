@@ -355,19 +355,18 @@ def main():
     # ---- arm 2: end to end through the public API, host buffers in, host buffer out -------------------------
     # every step: the host RNG draws of the reference's loop (util.py:131-136,225,253; diffusion.py:373; the decoder's FPS
     # start indices), pinned H2D of all inputs, the three stages, D2H of the clouds
+    # (the draws of step i+1 are made by the host while the GPU runs step i -- sample_to_host(next_labels=...) -- so only
+    # the first draw is exposed; every step still consumes freshly drawn inputs, drawn inside the timed region)
     barrier()
     t0 = time.time()
-    rng_s = 0.0
-    for _ in range(args.steps):
-        tr = time.time()
-        pipe.draw_host_inputs(labels)
-        rng_s += time.time() - tr
-        host = pipe.sample_to_host()
+    pipe.draw_host_inputs(labels)
+    ms_rng = 1e3 * (time.time() - t0)
+    for i in range(args.steps):
+        host = pipe.sample_to_host(next_labels=labels if i + 1 < args.steps else None)
         if world > 1:
             gathered = pipeline.all_gather_outputs(pipe.out, world)
     barrier()
     ms_e2e = 1e3 * (time.time() - t0) / args.steps
-    ms_rng = 1e3 * rng_s / args.steps
     wall1 = time.time()
     clock_info = clocks.stop(wall0, wall1) if clocks else None
 
@@ -507,8 +506,9 @@ def main():
                        "l2": "inputs larger than L2 (noise tensors 49 MB + 836 MB per GPU)", "valid": valid,
                        "ddpm_steps": args.ddpm_steps or 1000, "backend": args.backend},
             "e2e": {"value": B / (ms_e2e / 1e3), "unit": "shapes/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
-                    "d2h_bytes_per_step": pipe.d2h_bytes(), "ms_per_step": ms_e2e, "host_rng_ms_per_step": ms_rng,
-                    "includes": "host RNG draws (reference call order), pinned H2D, 3 stages, D2H"},
+                    "d2h_bytes_per_step": pipe.d2h_bytes(), "ms_per_step": ms_e2e, "host_rng_ms_per_draw": ms_rng,
+                    "includes": "host RNG draws every step (reference call order; the next step's draws overlap the GPU), "
+                                "pinned H2D, 3 stages, D2H"},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roof, "cpu_baseline": cpu,
             "finite": finite, "tc_error": tc_err, "parity": parity, "stages_ms": stages,
             "noise_path": getattr(pipe, "noise_path", None), "strong": strong, **extras}))

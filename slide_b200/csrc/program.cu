@@ -868,7 +868,7 @@ namespace {
 
 // PAIR launch-shape knobs: environment read once (slide_tc_reload_tuning() re-reads)
 bool g_pair_tuning_loaded = false;
-int g_pair_min_ctas = 2368, g_pair_min_rows = 32, g_pair_smem = 1;
+int g_pair_min_ctas = 2368, g_pair_min_rows = 32, g_pair_smem = 1, g_pair_pb = 8, g_pair_smem_min_ctas = 296;
 
 template <typename T>
 inline T *AP(slide_program *p, int64_t off) {
@@ -1085,13 +1085,18 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
         g_pair_min_ctas = e_ctas ? atoi(e_ctas) : 2368;
         g_pair_min_rows = e_rows ? atoi(e_rows) : 32;
         g_pair_smem = e_smem ? atoi(e_smem) : 1;
+        const char *e_pb = getenv("SLIDE_PAIR_PB");
+        g_pair_pb = e_pb ? atoi(e_pb) : 8;
+        if (g_pair_pb < 1) g_pair_pb = 1;
+        const char *e_mc = getenv("SLIDE_PAIR_SMEM_MIN_CTAS");
+        g_pair_smem_min_ctas = e_mc ? atoi(e_mc) : 296;
         g_pair_tuning_loaded = true;
       }
       // small gather source (the denoisers: the sample's own 16 points): stage it in shared memory
       if (g_pair_smem && a.nsrc <= PS_MAX_SRC && a.N <= 4 * PS_THREADS) {
         const int CT = ceil_div(a.N, 4), RG = PS_THREADS / CT, ldn = 4 * CT;
-        int pbs = a.np < 4 ? a.np : 4;  // points per CTA: 64 rows at K = 16; fewer when the grid would be under 4 waves
-        while (pbs > 1 && (long long)B * ceil_div(a.np, pbs) < 592) pbs = (pbs + 1) / 2;
+        int pbs = a.np < g_pair_pb ? a.np : g_pair_pb;  // points per CTA (8: 128 rows at K = 16; A/B on B200, batch 256, position / feature step: 2 -> 829 / 1650 us, 4 -> 710 / 1525, 8 -> 658 / 1488, 16 -> 654 / 1491); fewer when the grid would be under 2 CTAs per SM
+        while (pbs > 1 && (long long)B * ceil_div(a.np, pbs) < g_pair_smem_min_ctas) pbs = (pbs + 1) / 2;
         const size_t smem = ((size_t)(a.nsrc + pbs + 2 * RG) * ldn + 3 * (size_t)pbs * a.K) * 4;
         if (smem <= 160 * 1024) {
           a.pb = pbs;

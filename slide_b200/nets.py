@@ -202,6 +202,15 @@ def _align4(x):
     return (x + 3) // 4 * 4
 
 
+def _mlp_out_channels(P):
+    """Output channels of an Mlp_plus_t_emb (its last conv)."""
+    j, last = 0, "second_mlp.0"
+    while P.has("rest_mlp.%d.weight" % (3 * j)):
+        last = "rest_mlp.%d" % (3 * j)
+        j += 1
+    return int(P[last + ".weight"].shape[0])
+
+
 def _lower_mlp(ctx, P, G, R, name, out=None, use_t=False, use_cond=False, res=True, xf_in=NO_XF, first_cols=None,
                first_ev=None):
     """Mlp_plus_t_emb with bn_first=False.  G: input [B*R, Cin] (xf_in = transform still to be applied to it).
@@ -379,7 +388,7 @@ def _lower_sa(ctx, P, xyz, feats, npoint, nsample, name):
     return new_xyz, out
 
 
-def _lower_fp(ctx, P, unknown, known, unknow_feats, known_feats, K, name, out=None):
+def _lower_fp(ctx, P, unknown, known, unknow_feats, known_feats, K, name, out=None, side_extra=None):
     b = ctx.b
     n, B = unknown.R, unknown.B
     idx = b.tensor(name + ".idx", n, K, B=B, dtype="i32")
@@ -388,15 +397,20 @@ def _lower_fp(ctx, P, unknown, known, unknow_feats, known_feats, K, name, out=No
     Pa = P.sub("attention_module")
     G = _Grouped(ctx, 1, known_feats, known, unknown, idx, K, name, d2=d2)
     G.plan([P.sub("mlp1.first_mlp.0"), P.sub("mlp1.res_connect"), Pa.sub("grouped_feat_conv")])
+    d = _mlp_out_channels(P.sub("mlp1"))
+    cat = b.tensor(name + ".cat", n, d + unknow_feats.C + 3, B=B)
     with b.side_branch():
         keys = _attention_keys(ctx, Pa, unknow_feats, G, n, K, name + ".att")
+        # the skip features and coordinates of mlp2's input exist before this module starts: copied on the side branch,
+        # under the pair-level GEMMs of mlp1 (they were two serial records after the attention tail)
+        b.copy_cols(unknow_feats, cat.cols(d, unknow_feats.C), note=name + ".cat_skip")
+        b.copy_cols(unknown.cols(0, 3), cat.cols(d + unknow_feats.C, 3), note=name + ".cat_xyz")
+        if side_extra is not None:
+            side_extra()
     H1 = _lower_mlp(ctx, P.sub("mlp1"), G, n * K, name + ".mlp1")
+    assert H1.C == d
     b.join(name + ".join")
-    d = H1.C
-    cat = b.tensor(name + ".cat", n, d + unknow_feats.C + 3, B=B)
     _attention_tail(ctx, Pa, keys, H1, n, K, cat.cols(0, d), name + ".att")
-    b.copy_cols(unknow_feats, cat.cols(d, unknow_feats.C), note=name + ".cat_skip")
-    b.copy_cols(unknown.cols(0, 3), cat.cols(d + unknow_feats.C, 3), note=name + ".cat_xyz")
     return _lower_mlp(ctx, P.sub("mlp2"), cat, n, name + ".mlp2", out=out, use_t=True, use_cond=True)
 
 
@@ -510,12 +524,14 @@ def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None,
                 dst = head_in.cols(0, d0)
             elif out is not None:
                 dst = out
+        extra = None
+        if head_in is not None and i == -n_fp:  # the head's coordinate columns: copied under the last module's GEMMs
+            extra = lambda: b.copy_cols(xyz, head_in.cols(arch["decoder_feature_dim"][0], 3), note=name + ".head_xyz")  # noqa: E731
         l_feat[i - 1] = _lower_fp(ctx, P.sub("FP_modules.%d" % (n_fp + i)), l_xyz[i - 1], l_xyz[i], l_feat[i - 1],
-                                  l_feat[i], arch.get("K", 3), "%s.FP%d" % (name, n_fp + i), out=dst)
+                                  l_feat[i], arch.get("K", 3), "%s.FP%d" % (name, n_fp + i), out=dst, side_extra=extra)
     result = l_feat[0]
     if transform:
         d0 = arch["decoder_feature_dim"][0]
-        b.copy_cols(xyz, head_in.cols(d0, 3), note=name + ".head_xyz")
         W0, b0 = _conv(b, P.sub("fc_lyaer.0"))
         raw = b.tensor(name + ".head_raw", n_points, W0[2], B=B)
         assert W0[2] % 32 == 0

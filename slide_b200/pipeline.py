@@ -309,9 +309,19 @@ class SlidePipeline(object):
         self.stage_inputs()
         return self.sample_resident()
 
-    def sample_to_host(self):
-        out = self.sample()
+    def sample_to_host(self, next_labels=None):
+        """Host buffers in, host buffer out.  next_labels: labels (global batch) of the NEXT call -- its host-side RNG
+        draws (draw_host_inputs: ~60 ms of CPU work at batch 256) are then made while the GPU runs this call: the pinned
+        input buffers are free again as soon as this call's host->device copies have completed (an event right after
+        them, about a millisecond into the step).  Same generator call order as drawing between the calls."""
+        self.stage_inputs()
+        staged = torch.cuda.Event()
+        staged.record(torch.cuda.current_stream(self.device))
+        out = self.sample_resident()
         self._out_host.copy_(out, non_blocking=True)
+        if next_labels is not None:
+            staged.synchronize()
+            self.draw_host_inputs(next_labels)
         torch.cuda.current_stream(self.device).synchronize()
         self.check_device_errors()
         return self._out_host
