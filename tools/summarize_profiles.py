@@ -23,7 +23,9 @@ METRICS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "
 
 
 def launches(tag):
-    src = os.path.join(G, "launches_r1.csv")
+    src = os.path.join(G, "launches_%s.csv" % tag)
+    if not os.path.exists(src):
+        src = os.path.join(G, "launches_r1.csv")
     if not os.path.exists(src):
         return
     lines = [l for l in open(src) if l.startswith('"')]
