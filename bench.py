@@ -319,11 +319,15 @@ def main():
     # weak scaling: every GPU works on a full batch of `--batch` shapes; the job's batch is gpus x 256
     Bl = args.batch
     B = Bl * world
+    # RNG scope: like the reference's ranks, every rank draws its own 256 shapes from its own generators (seed = rank);
+    # the world-size-invariant mode (every rank draws the global batch and keeps its rows) is the generation driver's and
+    # is what the strong-scaling arm below uses
+    scope = "rank" if world > 1 else "global"
     pipe = pipeline.SlidePipeline(cfg, B, rank=rank, world=world, ddpm_steps=args.ddpm_steps, backend=args.backend,
-                                  decode_chunk=args.decode_chunk)
+                                  decode_chunk=args.decode_chunk, rng_scope=scope)
     label_id = cfg["label"]
-    labels = torch.full((B,), label_id, dtype=torch.long)
-    torch.manual_seed(0)
+    labels = torch.full((Bl if scope == "rank" else B,), label_id, dtype=torch.long)
+    torch.manual_seed(rank)
     pipe.draw_host_inputs(labels)
 
     def barrier():
@@ -504,7 +508,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "global_batch": B, "per_gpu_batch": Bl, "parallelism": "dp%d" % world,
                        "l2": "inputs larger than L2 (noise tensors 49 MB + 836 MB per GPU)", "valid": valid,
-                       "ddpm_steps": args.ddpm_steps or 1000, "backend": args.backend},
+                       "ddpm_steps": args.ddpm_steps or 1000, "backend": args.backend, "rng_scope": scope},
             "e2e": {"value": B / (ms_e2e / 1e3), "unit": "shapes/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
                     "d2h_bytes_per_step": pipe.d2h_bytes(), "ms_per_step": ms_e2e, "host_rng_ms_per_draw": ms_rng,
                     "includes": "host RNG draws every step (reference call order; the next step's draws overlap the GPU), "

@@ -167,17 +167,26 @@ class SlidePipeline(object):
 
     def __init__(self, cfg, global_batch, rank=0, world=1, device=None, state_dicts=None, decode_chunk=128,
                  ddpm_steps=None, backend="auto", local_resampling=False, position_sampler=None,
-                 position_resident="auto"):
+                 position_resident="auto", rng_scope="global"):
         """position_sampler: None = the 1000-step ancestral sampler (util.sampling), or the FastDPM STEP sampler
         dict(method="step", length=L, schedule="linear"|"quadratic", kappa=k) (util_fastdpmv2.fast_sampling_function_v2).
         position_resident: how the position DDPM's step is executed -- None = one kernel per record, dict(cluster=2|4,
         precise=bool) = ONE sample-resident kernel per step (resident.py), "auto" = resident when this GPU's batch fits
         one wave of clusters (batch <= SMs / 2), where the step is bound by per-kernel latency (measured on B200 at
         batch 32: 276 us / step resident, cluster 4, against 413 us for 62 record kernels; at batch 256 the record path
-        wins, 757 against 1250 us)."""
+        wins, 757 against 1250 us).
+        rng_scope: "global" -- every rank draws the noise of the FULL batch in the reference's call order and keeps its
+        rows, so results do not depend on the world size (the generation driver's mode); "rank" -- each rank draws only its
+        own B/W shapes from its own generators, which is what the reference's ranks do (each process samples its own
+        batch, mesh_evaluation.py:51,104-118) and keeps the host-side draw per rank constant as W grows; labels passed to
+        draw_host_inputs are then this rank's (B/W,)."""
         assert global_batch % world == 0
+        assert rng_scope in ("global", "rank")
         self.cfg, self.B, self.rank, self.world = cfg, global_batch, rank, world
         self.Bl = global_batch // world
+        self.rng_scope = rng_scope
+        # the batch the RNG streams are defined over, and where this rank's rows sit in it
+        self._rng_B, self._rng_rank, self._rng_world = (self.B, rank, world) if rng_scope == "global" else (self.Bl, 0, 1)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         sds = default_state_dicts() if state_dicts is None else state_dicts
         pos, lat = cfg["position_ddpm"], cfg["latent_ddpm"]
@@ -228,7 +237,7 @@ class SlidePipeline(object):
         skip_position: external keypoints -- the reference's latent_ddpm_keypoint_conditional_generation never draws
         position noise, so neither the position x_T nor its T noise tensors are drawn (the generator then advances
         exactly as in the reference: x_T of the latent DDPM, then the decoder's FPS start indices)."""
-        d = draw_host_inputs(self.cfg, self.B, self.rank, self.world, labels,
+        d = draw_host_inputs(self.cfg, self._rng_B, self._rng_rank, self._rng_world, labels,
                              fast_steps=None if self.position_sampler is None else self.T_pos,
                              skip_position=skip_position)
         self._skip_position = skip_position
@@ -287,7 +296,7 @@ class SlidePipeline(object):
         # the reference's randn_like sequence (diffusion.py:88): T draws of the FULL batch, of which this rank keeps its
         # rows -- one seeked-Philox launch (rng.py), bit-identical to the T torch.randn calls and to any world size
         nz = self.lat.noise_view().view(self.T_lat, self.Bl, 16, self.lat.C)
-        self.noise_path = rng.randn_sequence(nz, (self.B, 16, self.lat.C), self.rank * self.Bl, reverse=True)
+        self.noise_path = rng.randn_sequence(nz, (self._rng_B, 16, self.lat.C), self._rng_rank * self.Bl, reverse=True)
         self.lat.run(self.ddpm_steps)
         ev[2].record()
         feat = x[:, :, 3:].contiguous()
