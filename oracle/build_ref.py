@@ -3,7 +3,7 @@
 
 The reference's setup.py hard-codes Kepler..Turing arch flags (pointnet2_ops_lib/setup.py:19) that CUDA 12.9
 rejects, so the sources are compiled directly with torch.utils.cpp_extension for sm_100a.  The result can
-only run on a GPU: tests/test_gpu_ref_ext.py loads it there to pin oracle/slide_oracle.c and the
+only run on a GPU: tests/test_gpu_index_ops.py::test_against_reference_cuda_extension loads it there to pin oracle/slide_oracle.c and the
 slide_b200 kernels against the reference's real kernels (tie rules included).
 """
 import glob
