@@ -211,6 +211,38 @@ def build_encode(enc_cfg, kp_cfg, sd, B, n_points, sample_posterior=False):
     return b, h
 
 
+def build_refine(cfg, sd, B, n_in):
+    """The SAP refinement / upsampling network and the point split that follows it:
+    PointNet2CloudCondition(refine JSON).forward(X, None, ts=None, label) (pointnet2/dpsr_evaluation.py:253) and
+    point_upsample (models/point_upsample_module.py:4-46, the first_refine_coarse_points=False branch the shipped
+    JSONs use).  X [B*n_in, 3 + in_fea_dim]: xyz, normal and -- for the mirrored configs -- the +-1 indicator column,
+    which the split ignores (network_output_to_dpsr_grid, dpsr_evaluation.py:57-66).
+    Handles: x, labels, disp [B*n_in, 6*factor], fine [B*n_in*factor, 6], class_emb."""
+    if cfg.get("first_refine_coarse_points", False) or cfg.get("include_displacement_center_to_final_output", False):
+        raise NotImplementedError("first_refine_coarse_points (no shipped refine JSON sets it)")
+    b = Builder(B)
+    C = 3 + cfg["in_fea_dim"]
+    factor = cfg["point_upsample_factor"]
+    F = cfg["out_dim"] // factor if cfg["out_dim"] % factor == 0 and cfg["out_dim"] > 6 else cfg["out_dim"]
+    X = b.tensor("x", n_in, C)
+    labels = b.tensor("labels", 1, B, B=1, dtype="i32")
+    P = nets.Params(sd)
+    n_out = int(sd["fc_lyaer.3.weight"].shape[0])
+    assert n_out == F * factor, (n_out, F, factor)
+    b.begin_segment("refine")
+    b.step_begin()
+    net = nets.lower_cloud_net(b, P, cfg, X, n_in, "net", T=None, labels=labels)
+    fine = b.tensor("fine", n_in * factor, F)
+    b.upsample(X, F, net["out"], fine, factor, cfg["output_scale_factor"], note="point_upsample")
+    b.end_segment()
+    b.begin_segment("setup")
+    net["emit_setup"]()
+    b.end_segment()
+    h = dict(x=X, labels=labels, disp=net["out"], fine=fine, factor=factor, F=F)
+    h.update(net["inputs"])
+    return b, h
+
+
 def init_constants(machine, h):
     """Upload the constants a freshly created program needs before its setup segment runs: the timestep list
     0..T-1 and the class-embedding table(s).  `machine` is a Program or the CPU interpreter (same interface)."""

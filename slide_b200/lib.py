@@ -14,7 +14,7 @@ _lib = None
 
 ERRORS = {-1: "SLIDE_ERR_INVALID", -2: "SLIDE_ERR_CUDA", -3: "SLIDE_ERR_UNSUPPORTED"}
 
-# every symbol include/slide_b200.h declares (tests check that the library exports all of them)
+# every symbol include/slide_b200.h and include/slide_sap.h declare (tests check that the library exports all of them)
 SYMBOLS = [
     "slide_abi_version", "slide_last_cuda_error", "slide_launch_count", "slide_reset_launch_count",
     "slide_furthest_point_sampling", "slide_gather_points", "slide_gather_points_grad", "slide_ball_query",
@@ -25,6 +25,8 @@ SYMBOLS = [
     "slide_program_run", "slide_program_capture", "slide_program_replay", "slide_program_launches",
     "slide_program_set_gemm_backend", "slide_tc_error", "slide_tc_reset_error", "slide_tc_reload_tuning",
     "slide_program_set_resident", "slide_program_use_resident", "slide_philox_normal_slice",
+    # include/slide_sap.h
+    "slide_sap_mirror_concat", "slide_sap_unit_cube", "slide_dpsr_workspace_bytes", "slide_dpsr_forward",
 ]
 
 

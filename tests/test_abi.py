@@ -14,9 +14,11 @@ def test_library_builds_and_exports_declared_symbols():
     path = build.build()
     assert os.path.exists(path)
     handle = ctypes.CDLL(path)
-    src = open(os.path.join(ROOT, "include", "slide_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    declared = set(re.findall(r"\b(slide_[a-z0-9_]+)\s*\(", src))
+    declared = set()
+    for header in ("slide_b200.h", "slide_sap.h"):
+        src = open(os.path.join(ROOT, "include", header)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared |= set(re.findall(r"\b(slide_[a-z0-9_]+)\s*\(", src))
     assert declared, "no declarations parsed"
     assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
     for sym in declared:

@@ -1,0 +1,108 @@
+"""GPU parity of the SAP mesh-reconstruction stage through the C ABI of include/slide_sap.h, against
+oracle/sap_oracle.py (bit-identical to the REAL reference on CPU, tests/golden/make_golden_sap.py) and the golden grids.
+
+Tolerances: mirror / unit-cube map: the centroid is a parallel fp32 sum (1e-6 abs), everything after it is the same IEEE
+operations as the reference (bit-exact given the same bounding box).  DPSR: the splat accumulates with atomics and the
+transforms are this library's own radix-2 passes, so grids agree to fp32 round-off of a 128^3 transform: 2e-4 of max|phi|."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sap_oracle
+from slide_b200 import lib, sap, weights
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_sap.npz")))
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def test_mirror_concat_and_unit_cube(gold):
+    cloud = torch.from_numpy(gold["cloud"])
+    for perm in (gold["perm"], None):
+        want = sap_oracle.mirror_concat(cloud, perm)
+        got = sap.mirror_concat(cloud.cuda(), None if perm is None else torch.from_numpy(perm)).cpu()
+        assert torch.equal(got[:, :, 3:], want[:, :, 3:])           # normals and labels: exact
+        assert float((got - want).abs().max()) < 1e-6
+    g = torch.Generator().manual_seed(5)
+    pts = torch.randn(3, 5000, 6, generator=g) * torch.tensor([0.3, 0.2, 0.25, 1, 1, 1])
+    want = sap_oracle.to_unit_cube(pts[:, :, :3], explicit_normalize=True)
+    got = sap.unit_cube(pts.cuda(), explicit_normalize=True).cpu()
+    assert torch.equal(got, want)                                    # min / max are exact, the map is IEEE fp32
+    want = sap_oracle.to_unit_cube(pts[:, :, :3], scale=0.5, explicit_normalize=False)
+    got = sap.unit_cube(pts.cuda(), explicit_normalize=False, scale=0.5).cpu()
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("shift,scale", [(True, True), (False, False)])
+def test_dpsr_golden_edge_cases(gold, shift, scale):
+    V, N = torch.from_numpy(gold["edge_V"]).cuda(), torch.from_numpy(gold["edge_N"]).cuda()
+    phi = sap.DPSR((32, 32, 32), sig=2, shift=shift, scale=scale)(V, N).cpu().numpy()
+    assert _rel(phi, gold["edge_phi_%d%d" % (shift, scale)]) < 2e-4
+    if shift and scale:
+        phi = sap.DPSR((128, 128, 128), sig=2)(V, N).cpu().numpy()
+        assert _rel(phi[:, ::8, ::8, ::8], gold["edge_phi128_sub"]) < 2e-4
+
+
+@pytest.mark.parametrize("res,B,n", [(8, 3, 100), (16, 2, 777), (64, 2, 4096), (128, 2, 20480), (256, 1, 20480)])
+def test_dpsr_against_oracle(res, B, n):
+    g = torch.Generator().manual_seed(res)
+    V = (torch.rand(B, n, 3, generator=g) * 0.99).contiguous()
+    N = torch.randn(B, n, 3, generator=g)
+    want = sap_oracle.dpsr_forward(V, N, (res,) * 3, 2).numpy()
+    # strided inputs: the xyz / normal columns of one (B,n,6) tensor, as the reconstructor passes them
+    both = torch.cat([V, N], dim=2).cuda()
+    got = sap.DPSR((res,) * 3, sig=2)(both[:, :, :3], both[:, :, 3:]).cpu().numpy()
+    assert np.isfinite(got).all()
+    assert _rel(got, want) < 2e-4, _rel(got, want)
+
+
+def test_dpsr_properties_full_size():
+    """Size-independent properties at the shipped size (32 clouds x 20480 points, 128^3): linearity of the raw solve in
+    the normals, zero mean (DC removed), and the shift / scale normalisation (|phi(0)| = 0.5, mean value at the points 0)."""
+    B, n, r = 32, 20480, 128
+    g = torch.Generator().manual_seed(1)
+    V = (torch.rand(B, n, 3, generator=g) * 0.99).cuda()
+    N1, N2 = torch.randn(B, n, 3, generator=g).cuda(), torch.randn(B, n, 3, generator=g).cuda()
+    raw = sap.DPSR((r,) * 3, sig=2, shift=False, scale=False)
+    a, b = raw(V, N1).clone(), raw(V, N2).clone()
+    c = raw(V, N1 + 2 * N2)
+    scale = float(c.abs().max())
+    assert float((c - (a + 2 * b)).abs().max()) < 2e-5 * scale
+    assert float(a.mean(dim=(1, 2, 3)).abs().max()) < 1e-6 * scale
+    phi = sap.DPSR((r,) * 3, sig=2)(V, N1)
+    assert float((phi[:, 0, 0, 0].abs() - 0.5).abs().max()) < 1e-6
+    back = sap_oracle.grid_interp(phi[:2].cpu(), V[:2].cpu()).mean(dim=1)
+    assert float(back.abs().max()) < 1e-4
+    assert lib.load().slide_tc_error() == 0
+
+
+@pytest.mark.parametrize("backend,tol_disp,tol_phi", [("simt", 2e-4, 5e-4), ("auto", 6e-3, 2e-3)])
+def test_reconstructor_against_reference_golden(gold, backend, tol_disp, tol_phi):
+    """Cloud -> mirror -> refinement network -> split -> unit cube -> DPSR, against the REAL reference's outputs."""
+    cfg = weights.load_json("sap_refine.json")
+    cfg = dict(cfg, dpsr_config=dict(cfg["dpsr_config"], grid_res=32))
+    sd = weights.random_state_dict(weights.load_json("schema_sap_refine.json"), 21)
+    rec = sap.SapReconstructor(cfg, sd, 2, 2048, gemm_backend=backend)
+    out = rec.reconstruct(gold["cloud"], gold["label"], gold["perm"])
+    torch.cuda.synchronize()
+    disp = rec.prog.download(rec.h["disp"]).cpu().numpy().reshape(2, 4096, 30)
+    assert _rel(disp[:, ::8], gold["disp_rows8"]) < tol_disp
+    fine = out["refined"].cpu().numpy()
+    assert np.abs(fine[:, ::64] - gold["fine_rows64"]).max() < 1e-5
+    assert _rel(out["phi"][:1].cpu().numpy(), gold["phi_r32"]) < tol_phi
+    # and at the shipped resolution against the oracle run on the reconstructor's own refined points
+    rec128 = sap.SapReconstructor(weights.load_json("sap_refine.json"), sd, 2, 2048, gemm_backend=backend)
+    out = rec128.reconstruct(gold["cloud"], gold["label"], gold["perm"])
+    want = sap_oracle.dpsr_forward(out["points"].cpu(), out["normals"].cpu().contiguous(), (128,) * 3, 2).numpy()
+    assert _rel(out["phi"].cpu().numpy(), want) < 2e-4
+    assert lib.load().slide_tc_error() == 0
