@@ -270,6 +270,8 @@ def main():
     ap.add_argument("--ddpm-steps", type=int, default=None, help="DEBUG ONLY: truncate both DDPM loops (invalid as a benchmark)")
     ap.add_argument("--backend", default="auto", choices=["auto", "simt"])
     ap.add_argument("--decode-chunk", type=int, default=128)
+    ap.add_argument("--no-overlap", action="store_true", help="run the steps strictly one after the other (no cross-batch "
+                    "overlap of the next step's position DDPM with this step's feature DDPM)")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip strong / configs / reference_gpu_eager")
     args = ap.parse_args()
 
@@ -338,6 +340,7 @@ def main():
     for _ in range(args.warmup):
         out = pipe.sample()
         gathered = pipeline.all_gather_outputs(out, world)
+    stages = pipe.stage_ms()  # of the last warm-up step: stages back to back, nothing overlapped
     pipe.stage_inputs()  # resident-input arm: everything the step reads is in HBM before the clock starts
     barrier()
     lib.reset_launch_count()
@@ -348,14 +351,17 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for _ in range(args.steps):
-        out = pipe.sample_resident()
+    # Steps are pipelined across batches: while step i runs its feature DDPM + decode, the position DDPM of step i+1 runs
+    # on a side stream (SlidePipeline.prefetch_position).  All K position chains, K feature chains and K decodes execute
+    # inside the timed region: step 1's position chain runs un-overlapped, the last step prefetches nothing.
+    overlap = not args.no_overlap
+    for i in range(args.steps):
+        out = pipe.sample_resident(prefetch_next=overlap and i + 1 < args.steps)
         gathered = pipeline.all_gather_outputs(out, world)
     ev1.record()
     barrier()
     ms_value = ev0.elapsed_time(ev1) / args.steps
     launches = lib.launch_count() // max(args.steps, 1)
-    stages = pipe.stage_ms()  # of the last timed step
     # ---- arm 2: end to end through the public API, host buffers in, host buffer out -------------------------
     # every step: the host RNG draws of the reference's loop (util.py:131-136,225,253; diffusion.py:373; the decoder's FPS
     # start indices), pinned H2D of all inputs, the three stages, D2H of the clouds
@@ -366,7 +372,7 @@ def main():
     pipe.draw_host_inputs(labels)
     ms_rng = 1e3 * (time.time() - t0)
     for i in range(args.steps):
-        host = pipe.sample_to_host(next_labels=labels if i + 1 < args.steps else None)
+        host = pipe.sample_to_host(next_labels=labels if i + 1 < args.steps else None, overlap=overlap)
         if world > 1:
             gathered = pipeline.all_gather_outputs(pipe.out, world)
     barrier()
@@ -396,8 +402,8 @@ def main():
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for _ in range(ns):
-            g_s = pipeline.all_gather_outputs(sp.sample_resident(), world)
+        for i in range(ns):
+            g_s = pipeline.all_gather_outputs(sp.sample_resident(prefetch_next=overlap and i + 1 < ns), world)
         s1.record()
         barrier()
         ts = torch.tensor([s0.elapsed_time(s1) / ns], device="cuda", dtype=torch.float64)
@@ -508,7 +514,11 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "global_batch": B, "per_gpu_batch": Bl, "parallelism": "dp%d" % world,
                        "l2": "inputs larger than L2 (noise tensors 49 MB + 836 MB per GPU)", "valid": valid,
-                       "ddpm_steps": args.ddpm_steps or 1000, "backend": args.backend, "rng_scope": scope},
+                       "ddpm_steps": args.ddpm_steps or 1000, "backend": args.backend, "rng_scope": scope,
+                       "cross_batch_overlap": overlap,
+                       "overlap_note": "step i+1's position DDPM runs on a side stream under step i's feature DDPM + decode; "
+                                       "every chain of all K steps executes inside the timed region (stages_ms = one "
+                                       "un-overlapped warm-up step)"},
             "e2e": {"value": B / (ms_e2e / 1e3), "unit": "shapes/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
                     "d2h_bytes_per_step": pipe.d2h_bytes(), "ms_per_step": ms_e2e, "host_rng_ms_per_draw": ms_rng,
                     "includes": "host RNG draws every step (reference call order; the next step's draws overlap the GPU), "

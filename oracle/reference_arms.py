@@ -201,9 +201,116 @@ def gpu_arm(cfg, B=256, K=10):
     return value, detail
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# SAP mesh-reconstruction stage: the reference's refine network + network_output_to_dpsr_grid + DPSR
+# ---------------------------------------------------------------------------------------------------------------------
+def _stub_absent_packages():
+    """dpsr_utils/utils.py imports mesh / rendering packages at module level that exist nowhere offline and that DPSR
+    does not use; empty stand-ins let the UNMODIFIED file import."""
+    import types
+    for name, attrs in (("trimesh", {}), ("plyfile", {"PlyData": None}), ("skimage", {}), ("skimage.measure", {}),
+                        ("pytorch3d.renderer", {"PerspectiveCameras": None, "rasterize_meshes": None}),
+                        ("igl", {"adjacency_matrix": None, "connected_components": None})):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+    sys.modules["skimage"].measure = sys.modules["skimage.measure"]
+    import pytorch3d.structures as st
+    if not hasattr(st, "Meshes"):
+        st.Meshes = None
+
+
+def _reference_grid_function():
+    """network_output_to_dpsr_grid + shapenet_psr_normalize taken out of the unmodified dpsr_evaluation.py (the module
+    itself imports visualisation packages that are absent offline)."""
+    import ast
+    import numpy as np
+    import torch
+    from models.point_upsample_module import point_upsample
+    src = open(os.path.join(MIRROR, "pointnet2", "dpsr_evaluation.py")).read()
+    ns = {"torch": torch, "np": np, "point_upsample": point_upsample}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("shapenet_psr_normalize", "network_output_to_dpsr_grid"):
+            exec(compile(ast.Module([node], []), "dpsr_evaluation.py", "exec"), ns)
+    return ns["network_output_to_dpsr_grid"]
+
+
+def sap_arm(device_kind, B, reps=3):
+    """visualize_per_rank's per-batch work between loading the cloud and marching cubes (dpsr_evaluation.py:214-260):
+    mirror_and_concat -> PointNet2CloudCondition(refine JSON) -> network_output_to_dpsr_grid(DPSR 128^3), on `cpu`
+    (C-oracle native ops, all host threads) or `gpu` (eager torch + the reference's CUDA extension + cuFFT).
+    -> dict(clouds_per_s, ms per stage)."""
+    import torch
+    from slide_b200 import weights
+    if not mirror_available():
+        raise RuntimeError("needs baseline/_ref (the reference's python)")
+    gpu = device_kind == "gpu"
+    if gpu:
+        import slide_b200
+        from oracle import build_ref
+        ext = build_ref.load_module()
+        if ext is None:
+            raise RuntimeError("needs oracle/_ref (the reference's CUDA extension)")
+        sys.modules["pointnet2_ops._ext"] = ext
+        sys.path.insert(0, slide_b200.DROPIN_DIR)
+        sys.path.insert(0, os.path.join(MIRROR, "pointnet2"))
+        sys.path.insert(0, os.path.join(MIRROR, "pointnet2_ops_lib"))
+        import pointnet2_ops
+        pointnet2_ops._ext = ext
+        dev, sync = torch.device("cuda", 0), torch.cuda.synchronize
+    else:
+        from oracle import ops
+        ops.install_reference_stubs(reference_root=MIRROR)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.set_num_threads(os.cpu_count() or 1)
+        dev, sync = torch.device("cpu"), (lambda: None)
+    _stub_absent_packages()
+    from models.pointnet2_with_pcld_condition import PointNet2CloudCondition
+    from data_utils.mirror_partial import mirror_and_concat
+    from dpsr_utils.dpsr import DPSR
+    to_grid = _reference_grid_function()
+    cfg = weights.load_json("sap_refine.json")
+    pc, dc = cfg["pointnet_config"], cfg["dpsr_config"]
+    net = PointNet2CloudCondition(copy.deepcopy(pc)).eval()
+    net.load_state_dict(weights.random_state_dict(weights.load_json("schema_sap_refine.json"), 21), strict=True)
+    net = net.to(dev)
+    dpsr = DPSR(res=(dc["grid_res"],) * 3, sig=dc["psr_sigma"]).to(dev)
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand(B, 2048, 3, generator=g) - 0.5
+    nrm = torch.nn.functional.normalize(torch.randn(B, 2048, 3, generator=g), dim=2)
+    cloud = torch.cat([pts, nrm], dim=2).to(dev)
+    label = torch.zeros(B, dtype=torch.long, device=dev)
+    t = {"mirror": 0.0, "network": 0.0, "grid": 0.0}
+    with torch.no_grad():
+        for it in range(reps + 1):
+            sync()
+            t0 = time.time()
+            X = mirror_and_concat(cloud, axis=2, num_points=[], attach_label=True, permute=True)[0]
+            sync()
+            t1 = time.time()
+            disp = net(X, None, ts=None, label=label)
+            sync()
+            t2 = time.time()
+            phi, rp, rn = to_grid(X, disp, dpsr, cfg.get("scale", 1), pc, last_dim_as_indicator=True,
+                                  only_original_points_split=False, explicit_normalize=True)
+            sync()
+            t3 = time.time()
+            if it:  # first pass = warm-up
+                t["mirror"] += t1 - t0
+                t["network"] += t2 - t1
+                t["grid"] += t3 - t2
+    ms = {k: v / reps * 1e3 for k, v in t.items()}
+    total = sum(ms.values())
+    return {"clouds_per_s": B / (total / 1e3), "batch": B, "ms": ms, "total_ms": total,
+            "finite": bool(torch.isfinite(phi).all().item()),
+            "path": ("eager torch + the reference's CUDA extension (oracle/_ref) + cuFFT; pytorch3d = slide_b200 drop-in"
+                     if gpu else "unmodified python on %d host threads, native ops = C oracle" % torch.get_num_threads())}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("arm", choices=["cpu", "gpu"])
+    ap.add_argument("arm", choices=["cpu", "gpu", "sap-cpu", "sap-gpu"])
     ap.add_argument("--budget", type=float, default=20.0)
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--steps", type=int, default=10)
@@ -211,6 +318,9 @@ def main():
     args = ap.parse_args()
     from slide_b200 import weights
     cfg = weights.load_json("pipeline_%s.json" % args.category)
+    if args.arm.startswith("sap-"):
+        print(json.dumps(sap_arm(args.arm[4:], args.batch or (32 if args.arm == "sap-gpu" else 2), reps=max(1, min(args.steps, 3)))))
+        return
     if args.arm == "cpu":
         v, cores, kind, sample, detail = cpu_arm(cfg, args.budget, args.batch or 16)
         print(json.dumps({"value": v, "unit": "shapes/s", "cores": cores, "kind": kind, "sample": sample, "detail": detail}))

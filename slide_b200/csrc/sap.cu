@@ -231,7 +231,7 @@ __global__ void splat_kernel(const float *__restrict__ V, int ldv, const float *
 // ---- Z pass: real lines -> half spectra, two lines per complex transform --------------------------------------------------
 // raster f32 [lines, R]  ->  spec float2 [lines, H]
 __global__ void fft_z_forward_kernel(const float *__restrict__ raster, float2 *__restrict__ spec, long long n_pairs, int R,
-                                     int logR, int pairs_per_cta) {
+                                     int logR, int pairs_per_cta, int Hp) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float2 smem[];
@@ -241,6 +241,7 @@ __global__ void fft_z_forward_kernel(const float *__restrict__ raster, float2 *_
   fill_twiddles(tw, R);
   const long long pair0 = (long long)blockIdx.x * pairs_per_cta;
   const int np = (int)min((long long)pairs_per_cta, n_pairs - pair0);
+#pragma unroll 4
   for (int t = threadIdx.x; t < np * R; t += blockDim.x) {
     const int p = t >> logR, i = t & (R - 1);
     const float *a = raster + (pair0 + p) * 2 * R;
@@ -256,7 +257,7 @@ __global__ void fft_z_forward_kernel(const float *__restrict__ raster, float2 *_
       o = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
     else
       o = make_float2(0.5f * (zk.y + zr.y), -0.5f * (zk.x - zr.x));
-    spec[((pair0 + p) * 2 + which) * H + k] = o;
+    spec[((pair0 + p) * 2 + which) * Hp + k] = o;
   }
 }
 
@@ -265,7 +266,7 @@ __global__ void fft_z_forward_kernel(const float *__restrict__ raster, float2 *_
 // kz is base + i*es + kz.  One CTA: KZT neighbouring kz of one line set.
 template <bool INV>
 __global__ void fft_axis_kernel(float2 *__restrict__ data, int n_lo, long long stride_hi, long long stride_lo, long long es,
-                                int H, int R, int logR, int KZT) {
+                                int H, int R, int logR, int KZT) {  // H: valid kz per row (the row pitch is inside the strides)
   pdl_wait();
   pdl_trigger();
   extern __shared__ float2 smem[];
@@ -277,11 +278,13 @@ __global__ void fft_axis_kernel(float2 *__restrict__ data, int n_lo, long long s
   const int kz0 = blockIdx.y * KZT;
   const int nk = min(KZT, H - kz0);
   float2 *base = data + (long long)(o / n_lo) * stride_hi + (long long)(o % n_lo) * stride_lo + kz0;
+#pragma unroll 4
   for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
     const int i = t / KZT, k = t - i * KZT;
     if (k < nk) s[k * ldl + bitrev(i, logR)] = base[(long long)i * es + k];
   }
   fft_tile<INV>(s, tw, nk, R, logR, ldl);
+#pragma unroll 4
   for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
     const int i = t / KZT, k = t - i * KZT;
     if (k < nk) base[(long long)i * es + k] = s[k * ldl + i];
@@ -291,8 +294,8 @@ __global__ void fft_axis_kernel(float2 *__restrict__ data, int n_lo, long long s
 // ---- X pass + spectral solve + inverse X pass --------------------------------------------------------------------------------
 // spec float2 [B,3,R(x),R(y),H] (Z and Y already transformed)  ->  pot float2 [B,R(x),R(y),H] (X already inverted)
 //   Phi = sum_d (-i G N_d) w_d / (-(|w|^2) + 1e-6),  w = 2 pi k,  G = exp(-0.5 (2 sig |k| / R)^2),  Phi(0) = 0
-__global__ void solve_x_kernel(const float2 *__restrict__ spec, float2 *__restrict__ pot, int R, int logR, int H, int KZT,
-                               float sig) {
+__global__ void solve_x_kernel(const float2 *__restrict__ spec, float2 *__restrict__ pot, int R, int logR, int H, int Hp,
+                               int KZT, float sig) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float2 smem[];
@@ -303,9 +306,11 @@ __global__ void solve_x_kernel(const float2 *__restrict__ spec, float2 *__restri
   const int y = blockIdx.x & (R - 1), b = blockIdx.x >> logR;
   const int kz0 = blockIdx.y * KZT;
   const int nk = min(KZT, H - kz0);
-  const long long plane = (long long)R * H, vol = plane * R;
+  const long long plane = (long long)R * Hp, vol = plane * R;
+#pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float2 *src = spec + ((long long)b * 3 + c) * vol + (long long)y * H + kz0;
+    const float2 *src = spec + ((long long)b * 3 + c) * vol + (long long)y * Hp + kz0;
+#pragma unroll 4
     for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
       const int i = t / KZT, k = t - i * KZT;
       if (k < nk) s[(c * nk + k) * ldl + bitrev(i, logR)] = src[(long long)i * plane + k];
@@ -339,7 +344,8 @@ __global__ void solve_x_kernel(const float2 *__restrict__ spec, float2 *__restri
     ph[k * ldl + bitrev(i, logR)] = o;
   }
   fft_tile<true>(ph, tw, nk, R, logR, ldl);
-  float2 *dst = pot + (long long)b * vol + (long long)y * H + kz0;
+  float2 *dst = pot + (long long)b * vol + (long long)y * Hp + kz0;
+#pragma unroll 4
   for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
     const int i = t / KZT, k = t - i * KZT;
     if (k < nk) dst[(long long)i * plane + k] = ph[k * ldl + i];
@@ -348,20 +354,21 @@ __global__ void solve_x_kernel(const float2 *__restrict__ spec, float2 *__restri
 
 // ---- inverse Z pass: two Hermitian half spectra per complex transform -> two real lines ------------------------------------
 __global__ void fft_z_inverse_kernel(const float2 *__restrict__ pot, float *__restrict__ phi, long long n_pairs, int R,
-                                     int logR, int pairs_per_cta, float norm) {
+                                     int logR, int pairs_per_cta, float norm, int Hp) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float2 smem[];
-  const int ldl = R + 1, H = (R >> 1) + 1;
+  const int ldl = R + 1;
   float2 *tw = smem;
   float2 *s = smem + (R >> 1);
   fill_twiddles(tw, R);
   const long long pair0 = (long long)blockIdx.x * pairs_per_cta;
   const int np = (int)min((long long)pairs_per_cta, n_pairs - pair0);
+#pragma unroll 4
   for (int t = threadIdx.x; t < np * R; t += blockDim.x) {
     const int p = t >> logR, k = t & (R - 1);
-    const float2 *A = pot + (pair0 + p) * 2 * H;
-    const float2 *Bv = A + H;
+    const float2 *A = pot + (pair0 + p) * 2 * Hp;
+    const float2 *Bv = A + Hp;
     float2 z;
     if (k <= (R >> 1)) {
       float2 a = A[k], c = Bv[k];
@@ -450,12 +457,16 @@ int log2_exact(int R) {
   return (1 << l) == R ? l : -1;
 }
 
+// row pitch (in complex values) of the half spectra: R/2+1 rounded up to 32 bytes, so that every row and every 8-value
+// chunk of a row starts on a sector boundary (65 -> 68 at R = 128; the pad columns are never read or written)
+int half_pitch(int R) { return (R / 2 + 1 + 3) & ~3; }
+
 struct DpsrLayout {
   size_t raster, spec, pot, acc, scal, total;
 };
 
 DpsrLayout layout_of(int B, int R) {
-  const size_t vol = (size_t)R * R * R, hvol = (size_t)R * R * (R / 2 + 1);
+  const size_t vol = (size_t)R * R * R, hvol = (size_t)R * R * half_pitch(R);
   DpsrLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -520,7 +531,7 @@ int slide_dpsr_forward(const float *V, int ldv, const float *Nrm, int ldn, int B
   float2 *pot = (float2 *)(ws + L.pot);
   float *acc = (float *)(ws + L.acc);
   float2 *scal = (float2 *)(ws + L.scal);
-  const int H = R / 2 + 1;
+  const int H = R / 2 + 1, Hp = half_pitch(R);
   const size_t vol = (size_t)R * R * R;
   int rc;
   if ((rc = cuda_rc(cudaMemsetAsync(raster, 0, (size_t)B * 3 * vol * sizeof(float), st)))) return rc;
@@ -534,25 +545,25 @@ int slide_dpsr_forward(const float *V, int ldv, const float *Nrm, int ldn, int B
   {
     const long long n_pairs = (long long)B * 3 * R * R / 2;
     launch_k(fft_z_forward_kernel, dim3((unsigned)ceil_div_ll(n_pairs, PAIRS)), dim3(FFT_THREADS), tw_bytes + PAIRS * line_bytes,
-             st, (const float *)raster, spec, n_pairs, R, logR, PAIRS);
+             st, (const float *)raster, spec, n_pairs, R, logR, PAIRS, Hp);
     if ((rc = after_launch())) return rc;
   }
-  const long long plane = (long long)R * H, hvol = plane * R;
+  const long long plane = (long long)R * Hp, hvol = plane * R;
   // Y pass over the three normal channels: line set (b*3+c, x), element stride H
   launch_k(fft_axis_kernel<false>, dim3(B * 3 * R, ceil_div(H, KZT)), dim3(FFT_THREADS), tw_bytes + KZT * line_bytes, st, spec, R,
-           hvol, plane, (long long)H, H, R, logR, KZT);
+           hvol, plane, (long long)Hp, H, R, logR, KZT);
   if ((rc = after_launch())) return rc;
   launch_k(solve_x_kernel, dim3(R * B, ceil_div(H, KZT)), dim3(FFT_THREADS), tw_bytes + 4 * KZT * line_bytes, st,
-           (const float2 *)spec, pot, R, logR, H, KZT, sig);
+           (const float2 *)spec, pot, R, logR, H, Hp, KZT, sig);
   if ((rc = after_launch())) return rc;
   launch_k(fft_axis_kernel<true>, dim3(B * R, ceil_div(H, KZT)), dim3(FFT_THREADS), tw_bytes + KZT * line_bytes, st, pot, R, hvol,
-           plane, (long long)H, H, R, logR, KZT);
+           plane, (long long)Hp, H, R, logR, KZT);
   if ((rc = after_launch())) return rc;
   {
     const long long n_pairs = (long long)B * R * R / 2;
     const float norm = 1.0f / ((float)R * (float)R * (float)R);
     launch_k(fft_z_inverse_kernel, dim3((unsigned)ceil_div_ll(n_pairs, PAIRS)), dim3(FFT_THREADS), tw_bytes + PAIRS * line_bytes,
-             st, (const float2 *)pot, phi, n_pairs, R, logR, PAIRS, norm);
+             st, (const float2 *)pot, phi, n_pairs, R, logR, PAIRS, norm, Hp);
     if ((rc = after_launch())) return rc;
   }
   if (!shift && !scale) return SLIDE_OK;

@@ -229,6 +229,25 @@ class SlidePipeline(object):
         self._labels_host = torch.empty(self.Bl, dtype=torch.int64).pin_memory()
         self._starts_host = torch.empty(self.dec.n_levels, self.Bl, dtype=torch.int64).pin_memory()
         self._out_host = torch.empty(self.Bl, self.dec.out_points, self.dec.out_dim).pin_memory()
+        # Cross-batch overlap (see sample_resident): the position chain of the NEXT batch runs on a side stream while the
+        # feature chain + decode of the current batch run on the caller's stream.  Everything a batch reads on the device
+        # lives in one of two persistent input slots (no allocator reuse across streams), its keypoints in one of two
+        # keypoint buffers.
+        dev = self.device
+        self._in = [dict(labels=torch.zeros(self.Bl, dtype=torch.int64, device=dev),
+                         pos_xT=torch.empty(self.Bl, 16, 3, device=dev),
+                         lat_xT=torch.empty(self.Bl, 16, self.lat.C, device=dev),
+                         starts=torch.zeros(self.dec.n_levels, self.Bl, dtype=torch.int64, device=dev)) for _ in range(2)]
+        self._slot = 0                 # input slot of the batch the next sample_resident() call works on
+        self._kp = [torch.empty(self.Bl, 16, 3, device=dev) for _ in range(2)]
+        self._kp_slot = 0
+        self._prefetched = None        # dict(kp_slot, event): a position chain already issued for the next call
+        self._side = None              # side stream, created on first use
+        self._pos_done = None          # event after the latest position chain (its program arena is busy until then)
+        self._kp_read = [None, None]   # per keypoint buffer: event after the feature chain copied it
+        self._h2d_done = None          # event after the latest stage_inputs() copies (pinned buffers reusable after it)
+        self._pos_labels = None
+        self._lat_labels = None
 
     # ---- host-side RNG in the reference's call order (full batch, then this rank's slice) -------------------
     def draw_host_inputs(self, labels, skip_position=False):
@@ -249,39 +268,106 @@ class SlidePipeline(object):
         self._starts_host.copy_(d["starts"])
 
     # ---- device path -----------------------------------------------------------------------------------
-    def stage_inputs(self):
-        """Host -> device copies (pinned memory, async on the current stream) of everything draw_host_inputs staged."""
-        dev = self.device
-        labels = self._labels_host.to(dev, non_blocking=True)
-        if self._labels is None or not torch.equal(self._labels, labels):
-            self.pos.set_labels(labels)
-            self.lat.set_labels(labels)
-            self._labels = labels
-        if not getattr(self, "_skip_position", False):
+    def stage_inputs(self, slot=None):
+        """Host -> device copies (pinned memory, async on the current stream) of everything draw_host_inputs staged, into
+        input slot `slot` (default: the slot the next sample_resident() call reads)."""
+        slot = self._slot if slot is None else slot
+        d = self._in[slot]
+        d["labels"].copy_(self._labels_host, non_blocking=True)
+        d["skip_position"] = getattr(self, "_skip_position", False)
+        if not d["skip_position"]:
+            # the position program's noise table: free once the previous position chain is done (same stream or waited for
+            # by the caller, see _issue_position)
             self.pos.noise_view().copy_(self._pos_noise_host, non_blocking=True)
-            self._pos_xT_dev = self._pos_xT_host.to(dev, non_blocking=True)
-        self._lat_xT_dev = self._lat_xT_host.to(dev, non_blocking=True)
-        self._starts_dev = self._starts_host.to(dev, non_blocking=True)
+            d["pos_xT"].copy_(self._pos_xT_host, non_blocking=True)
+        d["lat_xT"].copy_(self._lat_xT_host, non_blocking=True)
+        d["starts"].copy_(self._starts_host, non_blocking=True)
+        d["labels_host"] = self._labels_host.clone()
+        self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.device))
 
-    def sample_resident(self, keypoints=None, complete_x0=None, keypoint_mask=None):
+    def _set_labels(self, which, d):
+        """Re-run a sampler's setup segment (class-embedding projections) only when the batch's labels changed."""
+        cur = self._pos_labels if which == "pos" else self._lat_labels
+        if cur is None or not torch.equal(cur, d["labels_host"]):
+            (self.pos if which == "pos" else self.lat).set_labels(d["labels"])
+            if which == "pos":
+                self._pos_labels = d["labels_host"]
+            else:
+                self._lat_labels = d["labels_host"]
+
+    def _issue_position(self, slot, kp_slot):
+        """Position DDPM of the batch in input slot `slot` on the CURRENT stream -> keypoint buffer kp_slot.
+        Returns the event recorded after it."""
+        st = torch.cuda.current_stream(self.device)
+        if self._pos_done is not None:
+            st.wait_event(self._pos_done)          # one position chain at a time (single program arena)
+        if self._kp_read[kp_slot] is not None:
+            st.wait_event(self._kp_read[kp_slot])  # the feature chain that used this buffer has copied it
+        d = self._in[slot]
+        self._set_labels("pos", d)
+        self.pos.x_view().copy_(d["pos_xT"].view(-1, 3))
+        self.pos.run(self.ddpm_steps)
+        self._kp[kp_slot].copy_(self.pos.x_view().view(self.Bl, 16, 3))
+        ev = torch.cuda.Event()
+        ev.record(st)
+        self._pos_done = ev
+        return ev
+
+    def prefetch_position(self, restage=False):
+        """Issue the position DDPM of the NEXT sample_resident() call on the side stream, so that it runs underneath the
+        feature chain + decode of the call that was just issued (measured on B200, batch 256: the two chains take
+        656 + 1486 ms back to back and 1898 ms side by side -- the position chain's point-level records leave most SMs
+        idle).  restage=True: first copy the inputs draw_host_inputs() just staged in pinned memory into the other input
+        slot (end-to-end flow); False: the next call re-uses the resident inputs of the current slot (resident-input arm).
+        Results are identical to the un-overlapped order: same programs, same inputs, disjoint buffers."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        nxt = 1 - self._slot if restage else self._slot
+        kp_slot = 1 - self._kp_slot
+        with torch.cuda.stream(self._side):
+            if restage:
+                if self._pos_done is not None:
+                    self._side.wait_event(self._pos_done)  # the noise table is being overwritten
+                self.stage_inputs(slot=nxt)
+            if self._in[nxt].get("skip_position", False):
+                self._prefetched = dict(slot=nxt, kp_slot=None, event=self._h2d_done)
+                return
+            ev = self._issue_position(nxt, kp_slot)
+        self._prefetched = dict(slot=nxt, kp_slot=kp_slot, event=ev)
+
+    def sample_resident(self, keypoints=None, complete_x0=None, keypoint_mask=None, prefetch_next=False):
         """The three stages on inputs that stage_inputs() already put in HBM; returns the (Bl, 2048, 6) device tensor.
 
         keypoints (Bl,16,3) device tensor: external keypoints -- the position DDPM is skipped (the reference's
         latent_ddpm_keypoint_conditional_generation.py with --keypoint_file).  complete_x0 (Bl,16,3+F) + keypoint_mask
-        (Bl,16): local resampling (--local_resampling; the pipeline must have been built with local_resampling=True)."""
+        (Bl,16): local resampling (--local_resampling; the pipeline must have been built with local_resampling=True).
+        prefetch_next: the caller will call sample_resident() again on the same resident inputs -- issue that call's
+        position chain now, on the side stream, under this call's feature chain (prefetch_position)."""
         dev = self.device
+        main = torch.cuda.current_stream(dev)
         if not hasattr(self, "_stage_ev"):
             self._stage_ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev = self._stage_ev
         ev[0].record()
+        pre, self._prefetched = self._prefetched, None
+        if pre is not None:
+            self._slot = pre["slot"]
+            main.wait_event(pre["event"])
+        d = self._in[self._slot]
         if keypoints is None:
-            # 1. position DDPM
-            self.pos.x_view().copy_(self._pos_xT_dev.view(-1, 3))
-            self.pos.run(self.ddpm_steps)
-            kp = self.pos.x_view().view(self.Bl, 16, 3)
+            # 1. position DDPM (already issued on the side stream by the previous call, or inline here)
+            if pre is not None and pre["kp_slot"] is not None:
+                self._kp_slot = pre["kp_slot"]
+            else:
+                self._kp_slot = 1 - self._kp_slot
+                self._issue_position(self._slot, self._kp_slot)
+            kp = self._kp[self._kp_slot]
         else:
             kp = keypoints.to(dev).float().view(self.Bl, 16, 3)
         ev[1].record()
+        self._set_labels("lat", d)
         if self.lat.local_resampling:
             if complete_x0 is None:  # plain sampling through a resampling-capable program: re-sample everything
                 complete_x0 = torch.zeros(self.Bl, 16, self.lat.C, device=dev)
@@ -291,8 +377,19 @@ class SlidePipeline(object):
             assert complete_x0 is None, "local resampling needs SlidePipeline(..., local_resampling=True)"
         # 2. latent DDPM on the generated keypoints (keypoint-conditional: xyz columns are never updated)
         x = self.lat.x_view().view(self.Bl, 16, self.lat.C)
-        x.copy_(self._lat_xT_dev)
+        x.copy_(d["lat_xT"])
         x[:, :, 0:3] = kp
+        # the keypoints leave with the result: private copy (the buffer is handed back to the position chain below)
+        if not hasattr(self, "_kp_out"):
+            self._kp_out = torch.empty(self.Bl, 16, 3, device=dev)
+        self._kp_out.copy_(kp)
+        if keypoints is None:
+            e = torch.cuda.Event()
+            e.record(main)
+            self._kp_read[self._kp_slot] = e
+        kp = self._kp_out
+        if prefetch_next and keypoints is None:
+            self.prefetch_position(restage=False)
         # the reference's randn_like sequence (diffusion.py:88): T draws of the FULL batch, of which this rank keeps its
         # rows -- one seeked-Philox launch (rng.py), bit-identical to the T torch.randn calls and to any world size
         nz = self.lat.noise_view().view(self.T_lat, self.Bl, 16, self.lat.C)
@@ -302,7 +399,7 @@ class SlidePipeline(object):
         feat = x[:, :, 3:].contiguous()
         self.keypoint, self.keypoint_feature = kp, feat  # (Bl,16,3), (Bl,16,F): what the reference also returns
         # 3. decode
-        self.dec.run(kp.contiguous(), feat, self._labels, self._starts_dev, self.out)
+        self.dec.run(kp.contiguous(), feat, d["labels"], d["starts"], self.out)
         ev[3].record()
         return self.out
 
@@ -315,22 +412,25 @@ class SlidePipeline(object):
 
     def sample(self):
         """Public entry: host buffers in (pinned), device tensor out."""
-        self.stage_inputs()
+        if self._prefetched is None:
+            self.stage_inputs()
         return self.sample_resident()
 
-    def sample_to_host(self, next_labels=None):
-        """Host buffers in, host buffer out.  next_labels: labels (global batch) of the NEXT call -- its host-side RNG
-        draws (draw_host_inputs: ~60 ms of CPU work at batch 256) are then made while the GPU runs this call: the pinned
-        input buffers are free again as soon as this call's host->device copies have completed (an event right after
-        them, about a millisecond into the step).  Same generator call order as drawing between the calls."""
-        self.stage_inputs()
-        staged = torch.cuda.Event()
-        staged.record(torch.cuda.current_stream(self.device))
+    def sample_to_host(self, next_labels=None, overlap=True):
+        """Host buffers in, host buffer out.  next_labels: labels (global batch) of the NEXT call.  Its host-side RNG
+        draws (draw_host_inputs: ~60 ms of CPU work at batch 256) are then made while the GPU runs this call -- the pinned
+        input buffers are free again as soon as this call's host->device copies have completed -- and (overlap=True) its
+        inputs are staged and its position DDPM is issued on the side stream, underneath this call's feature chain
+        (prefetch_position).  Same generator call order, same results as drawing and sampling between the calls."""
+        if self._prefetched is None:
+            self.stage_inputs()
         out = self.sample_resident()
         self._out_host.copy_(out, non_blocking=True)
         if next_labels is not None:
-            staged.synchronize()
-            self.draw_host_inputs(next_labels)
+            self._h2d_done.synchronize()
+            self.draw_host_inputs(next_labels, skip_position=getattr(self, "_skip_position", False))
+            if overlap:
+                self.prefetch_position(restage=True)
         torch.cuda.current_stream(self.device).synchronize()
         self.check_device_errors()
         return self._out_host

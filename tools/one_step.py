@@ -28,7 +28,7 @@ def main():
         s.prog.run(*s.builder.segments["step"])
     kp = pipe.pos.x_view().view(256, 16, 3)[:pipe.dec.chunk].contiguous()
     feat = pipe.lat.x_view().view(256, 16, pipe.lat.C)[:pipe.dec.chunk, :, 3:].contiguous()
-    pipe.dec.run(kp, feat, pipe._labels[:pipe.dec.chunk], pipe._starts_dev[:, :pipe.dec.chunk], pipe.out[:pipe.dec.chunk])
+    pipe.dec.run(kp, feat, pipe._in[pipe._slot]['labels'][:pipe.dec.chunk], pipe._in[pipe._slot]['starts'][:, :pipe.dec.chunk], pipe.out[:pipe.dec.chunk])
     if "--config1" in sys.argv:  # BASELINE config 1 through the drop-in _ext: FPS 2048 -> 1024 + ball query r=0.2 ns=32
         from slide_b200 import install_dropin
         install_dropin()
