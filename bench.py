@@ -256,6 +256,16 @@ def extra_configs(cfg, args):
     rows = [json.loads(line) for line in r.stdout.splitlines() if line.startswith("{")]
     out["config5"] = [{k: row[k] for k in ("points", "batch", "encode_ms", "decode_ms", "shapes_per_s", "hbm_roofline", "finite")}
                       for row in rows] or {"error": (r.stderr or r.stdout)[-300:]}
+    # the SAP mesh-reconstruction stage (refine network + DPSR), batch 32 = the shipped eval_batch_size, next
+    # to the reference's own code for the same stage on this box (eager GPU: its python + its CUDA extension + cuFFT; CPU:
+    # its python on the host cores with the C-oracle native ops, a 2-cloud sample)
+    sap = run_json([sys.executable, os.path.join(ROOT, "tools", "bench_sap.py"), "--batch", "32", "--reps", "5"], 300)
+    sap["reference_gpu_eager"] = run_json([sys.executable, "-m", "oracle.reference_arms", "sap-gpu", "--batch", "32",
+                                           "--steps", "3"], 300)
+    sap["reference_cpu"] = run_json([sys.executable, "-m", "oracle.reference_arms", "sap-cpu", "--batch", "2", "--steps", "1"], 300)
+    if "clouds_per_s" in sap and "clouds_per_s" in sap["reference_gpu_eager"]:
+        sap["speedup_vs_reference_gpu_eager"] = sap["clouds_per_s"] / sap["reference_gpu_eager"]["clouds_per_s"]
+    out["sap"] = sap
     return out
 
 

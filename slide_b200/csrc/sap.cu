@@ -24,40 +24,134 @@ namespace {
 
 constexpr int FFT_THREADS = 256;
 
-__device__ __forceinline__ int bitrev(int i, int logR) { return (int)(__brev((unsigned)i) >> (32 - logR)); }
+// ---- FFT building blocks ------------------------------------------------------------------------------------------------
+// A line of R = R1 * R2 complex values is transformed in two register-resident steps (Cooley-Tukey, four-step form):
+//   input index  n = R2 n1 + n2   held in shared memory at  n1 * P + n2      ("natural" layout, P = R2 + 1)
+//   step 1: thread (line, n2): radix-R1 transform over n1 in registers, times W_R^(n2 k1), back to the same positions
+//   step 2: thread (line, k1): radix-R2 transform over n2 in registers, back to the same positions
+//   output index k = k1 + R1 k2   held at  k1 * P + k2                          ("transposed" layout)
+// -- two shared-memory round trips and two barriers per transform instead of log2(R) of each (the first version of this
+// file ran a radix-2 pass per barrier and was bound by instruction issue and bank conflicts: ncu 67-75 % SM busy at
+// 1.6 TB/s; profiles/r02_sap_*).  The mirrored form (transposed layout in, natural layout out) exists for the inverse
+// transform that directly follows a forward one in solve_x_kernel, so the spectrum is consumed where it lies.
+template <int LOGR>
+struct Geo {
+  static constexpr int R = 1 << LOGR, L1 = LOGR / 2, R1 = 1 << L1, L2 = LOGR - L1, R2 = 1 << L2, P = R2 + 1;
+  static constexpr int LS = (R1 * P) | 1;  // odd line stride: the transposing global<->shared copies stay conflict-free
+  __device__ static __forceinline__ int in_pos(int i) { return (i >> L2) * P + (i & (R2 - 1)); }
+  __device__ static __forceinline__ int out_pos(int k) { return (k & (R1 - 1)) * P + (k >> L1); }
+};
 
-// tw[k] = exp(-2 pi i k / R), k < R/2
-__device__ __forceinline__ void fill_twiddles(float2 *tw, int R) {
-  for (int k = threadIdx.x; k < (R >> 1); k += blockDim.x) {
-    float s, c;
-    sincospif(2.0f * (float)k / (float)R, &s, &c);
-    tw[k] = make_float2(c, -s);
+__device__ constexpr float COS16[8] = {1.f, 0.92387953251f, 0.70710678119f, 0.38268343237f,
+                                       0.f, -0.38268343237f, -0.70710678119f, -0.92387953251f};
+__device__ constexpr float SIN16[8] = {0.f, 0.38268343237f, 0.70710678119f, 0.92387953251f,
+                                       1.f, 0.92387953251f, 0.70710678119f, 0.38268343237f};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// N-point transform (N <= 16) of a register array, natural order in and out: X[k] = sum_n x[n] W_N^(+-nk).
+template <int N, bool INV>
+__device__ __forceinline__ void reg_fft(float2 (&v)[N]) {
+  if constexpr (N == 2) {
+    const float2 a = v[0], b = v[1];
+    v[0] = make_float2(a.x + b.x, a.y + b.y);
+    v[1] = make_float2(a.x - b.x, a.y - b.y);
+  } else if constexpr (N > 2) {
+    float2 e[N / 2], o[N / 2];
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) e[i] = v[2 * i], o[i] = v[2 * i + 1];
+    reg_fft<N / 2, INV>(e);
+    reg_fft<N / 2, INV>(o);
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+      constexpr int step = 16 / N;
+      const int j = k * step;  // W_N^k = W_16^j
+      float2 t;
+      if (j == 0)
+        t = o[k];
+      else if (j == 4)
+        t = INV ? make_float2(-o[k].y, o[k].x) : make_float2(o[k].y, -o[k].x);  // -+ i
+      else
+        t = cmul(o[k], make_float2(COS16[j], INV ? SIN16[j] : -SIN16[j]));
+      v[k] = make_float2(e[k].x + t.x, e[k].y + t.y);
+      v[k + N / 2] = make_float2(e[k].x - t.x, e[k].y - t.y);
+    }
   }
 }
 
-// In-place radix-2 decimation-in-time FFT of `lines` lines of R complex values held bit-reversed in shared memory
-// (line l at s + l * ldl).  Unnormalised; INV uses the conjugate twiddles.  Ends with a barrier.
-template <bool INV>
-__device__ __forceinline__ void fft_tile(float2 *s, const float2 *tw, int lines, int R, int logR, int ldl) {
-  const int per_line = R >> 1;
-  const int total = lines * per_line;
-  for (int st = 0; st < logR; ++st) {
-    const int half = 1 << st;
-    __syncthreads();
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-      const int line = t >> (logR - 1);
-      const int j = t & (per_line - 1);
-      const int pos = j & (half - 1);
-      const int i0 = ((j >> st) << (st + 1)) + pos;
-      float2 w = tw[pos << (logR - 1 - st)];
+// tw[j] = exp(-2 pi i j / R), j < R
+template <int LOGR>
+__device__ __forceinline__ void fill_twiddles(float2 *tw) {
+  constexpr int R = 1 << LOGR;
+  for (int j = threadIdx.x; j < R; j += blockDim.x) {
+    float sn, cs;
+    sincospif(2.0f * (float)j / (float)R, &sn, &cs);
+    tw[j] = make_float2(cs, -sn);
+  }
+}
+
+// natural layout in -> transposed layout out.  Callers synchronise before; ends with a barrier.
+template <int LOGR, bool INV>
+__device__ __forceinline__ void fft_lines(float2 *s, const float2 *tw, int lines) {
+  using G = Geo<LOGR>;
+  for (int t = threadIdx.x; t < lines * G::R2; t += blockDim.x) {
+    const int line = t >> G::L2, n2 = t & (G::R2 - 1);
+    float2 *p = s + line * G::LS + n2;
+    float2 v[G::R1];
+#pragma unroll
+    for (int j = 0; j < G::R1; ++j) v[j] = p[j * G::P];
+    reg_fft<G::R1, INV>(v);
+    p[0] = v[0];
+#pragma unroll
+    for (int k1 = 1; k1 < G::R1; ++k1) {
+      float2 w = tw[n2 * k1];
       if (INV) w.y = -w.y;
-      float2 *p = s + line * ldl + i0;
-      const float2 a = p[0], b = p[half];
-      const float tr = w.x * b.x - w.y * b.y;
-      const float ti = w.x * b.y + w.y * b.x;
-      p[0] = make_float2(a.x + tr, a.y + ti);
-      p[half] = make_float2(a.x - tr, a.y - ti);
+      p[k1 * G::P] = cmul(v[k1], w);
     }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < lines * G::R1; t += blockDim.x) {
+    const int line = t >> G::L1, k1 = t & (G::R1 - 1);
+    float2 *p = s + line * G::LS + k1 * G::P;
+    float2 v[G::R2];
+#pragma unroll
+    for (int j = 0; j < G::R2; ++j) v[j] = p[j];
+    reg_fft<G::R2, INV>(v);
+#pragma unroll
+    for (int j = 0; j < G::R2; ++j) p[j] = v[j];
+  }
+  __syncthreads();
+}
+
+// inverse transform, transposed layout in -> natural layout out (the mirror image of fft_lines<LOGR, true>).
+template <int LOGR>
+__device__ __forceinline__ void ifft_lines_mirror(float2 *s, const float2 *tw, int lines) {
+  using G = Geo<LOGR>;
+  for (int t = threadIdx.x; t < lines * G::R1; t += blockDim.x) {
+    const int line = t >> G::L1, k1 = t & (G::R1 - 1);
+    float2 *p = s + line * G::LS + k1 * G::P;
+    float2 v[G::R2];
+#pragma unroll
+    for (int j = 0; j < G::R2; ++j) v[j] = p[j];
+    reg_fft<G::R2, true>(v);
+    p[0] = v[0];
+#pragma unroll
+    for (int n2 = 1; n2 < G::R2; ++n2) {
+      float2 w = tw[n2 * k1];
+      w.y = -w.y;
+      p[n2] = cmul(v[n2], w);
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < lines * G::R2; t += blockDim.x) {
+    const int line = t >> G::L2, n2 = t & (G::R2 - 1);
+    float2 *p = s + line * G::LS + n2;
+    float2 v[G::R1];
+#pragma unroll
+    for (int j = 0; j < G::R1; ++j) v[j] = p[j * G::P];
+    reg_fft<G::R1, true>(v);
+#pragma unroll
+    for (int j = 0; j < G::R1; ++j) p[j * G::P] = v[j];
   }
   __syncthreads();
 }
@@ -229,29 +323,32 @@ __global__ void splat_kernel(const float *__restrict__ V, int ldv, const float *
 }
 
 // ---- Z pass: real lines -> half spectra, two lines per complex transform --------------------------------------------------
-// raster f32 [lines, R]  ->  spec float2 [lines, H]
-__global__ void fft_z_forward_kernel(const float *__restrict__ raster, float2 *__restrict__ spec, long long n_pairs, int R,
-                                     int logR, int pairs_per_cta, int Hp) {
+// raster f32 [lines, R]  ->  spec float2 [lines, Hp]
+template <int LOGR>
+__global__ void __launch_bounds__(FFT_THREADS) fft_z_forward_kernel(const float *__restrict__ raster, float2 *__restrict__ spec,
+                                                                    long long n_pairs, int pairs_per_cta, int Hp) {
   pdl_wait();
   pdl_trigger();
+  using G = Geo<LOGR>;
+  constexpr int R = G::R, H = R / 2 + 1;
   extern __shared__ float2 smem[];
-  const int ldl = R + 1, H = (R >> 1) + 1;
   float2 *tw = smem;
-  float2 *s = smem + (R >> 1);
-  fill_twiddles(tw, R);
+  float2 *s = smem + R;
+  fill_twiddles<LOGR>(tw);
   const long long pair0 = (long long)blockIdx.x * pairs_per_cta;
   const int np = (int)min((long long)pairs_per_cta, n_pairs - pair0);
 #pragma unroll 4
   for (int t = threadIdx.x; t < np * R; t += blockDim.x) {
-    const int p = t >> logR, i = t & (R - 1);
+    const int p = t >> LOGR, i = t & (R - 1);
     const float *a = raster + (pair0 + p) * 2 * R;
-    s[p * ldl + bitrev(i, logR)] = make_float2(a[i], a[R + i]);
+    s[p * G::LS + G::in_pos(i)] = make_float2(a[i], a[R + i]);
   }
-  fft_tile<false>(s, tw, np, R, logR, ldl);
+  __syncthreads();
+  fft_lines<LOGR, false>(s, tw, np);
   for (int t = threadIdx.x; t < np * 2 * H; t += blockDim.x) {
     const int p = t / (2 * H), r = t - p * 2 * H;
     const int which = r >= H, k = which ? r - H : r;
-    const float2 zk = s[p * ldl + k], zr = s[p * ldl + ((R - k) & (R - 1))];
+    const float2 zk = s[p * G::LS + G::out_pos(k)], zr = s[p * G::LS + G::out_pos((R - k) & (R - 1))];
     float2 o;
     if (!which)
       o = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
@@ -263,47 +360,51 @@ __global__ void fft_z_forward_kernel(const float *__restrict__ raster, float2 *_
 
 // ---- generic in-place complex pass along a strided axis ---------------------------------------------------------------------
 // data float2; a line set o = (o_hi, o_lo), o_lo < n_lo: base = o_hi*stride_hi + o_lo*stride_lo; element i of the line at
-// kz is base + i*es + kz.  One CTA: KZT neighbouring kz of one line set.
-template <bool INV>
-__global__ void fft_axis_kernel(float2 *__restrict__ data, int n_lo, long long stride_hi, long long stride_lo, long long es,
-                                int H, int R, int logR, int KZT) {  // H: valid kz per row (the row pitch is inside the strides)
+// kz is base + i*es + kz.  One CTA: KZT neighbouring kz of one line set (KZT * 8 contiguous bytes per row).
+template <int LOGR, bool INV, int KZT>
+__global__ void __launch_bounds__(FFT_THREADS) fft_axis_kernel(float2 *__restrict__ data, int n_lo, long long stride_hi,
+                                                               long long stride_lo, long long es, int H) {
   pdl_wait();
   pdl_trigger();
+  using G = Geo<LOGR>;
+  constexpr int R = G::R;
   extern __shared__ float2 smem[];
-  const int ldl = R + 1;
   float2 *tw = smem;
-  float2 *s = smem + (R >> 1);
-  fill_twiddles(tw, R);
+  float2 *s = smem + R;
+  fill_twiddles<LOGR>(tw);
   const int o = blockIdx.x;
   const int kz0 = blockIdx.y * KZT;
   const int nk = min(KZT, H - kz0);
   float2 *base = data + (long long)(o / n_lo) * stride_hi + (long long)(o % n_lo) * stride_lo + kz0;
 #pragma unroll 4
   for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
-    const int i = t / KZT, k = t - i * KZT;
-    if (k < nk) s[k * ldl + bitrev(i, logR)] = base[(long long)i * es + k];
+    const int i = t / KZT, k = t % KZT;
+    if (k < nk) s[k * G::LS + G::in_pos(i)] = base[(long long)i * es + k];
   }
-  fft_tile<INV>(s, tw, nk, R, logR, ldl);
+  __syncthreads();
+  fft_lines<LOGR, INV>(s, tw, nk);
 #pragma unroll 4
   for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
-    const int i = t / KZT, k = t - i * KZT;
-    if (k < nk) base[(long long)i * es + k] = s[k * ldl + i];
+    const int i = t / KZT, k = t % KZT;
+    if (k < nk) base[(long long)i * es + k] = s[k * G::LS + G::out_pos(i)];
   }
 }
 
 // ---- X pass + spectral solve + inverse X pass --------------------------------------------------------------------------------
-// spec float2 [B,3,R(x),R(y),H] (Z and Y already transformed)  ->  pot float2 [B,R(x),R(y),H] (X already inverted)
+// spec float2 [B,3,R(x),R(y),Hp] (Z and Y already transformed)  ->  pot float2 [B,R(x),R(y),Hp] (X already inverted)
 //   Phi = sum_d (-i G N_d) w_d / (-(|w|^2) + 1e-6),  w = 2 pi k,  G = exp(-0.5 (2 sig |k| / R)^2),  Phi(0) = 0
-__global__ void solve_x_kernel(const float2 *__restrict__ spec, float2 *__restrict__ pot, int R, int logR, int H, int Hp,
-                               int KZT, float sig) {
+template <int LOGR, int KZT>
+__global__ void __launch_bounds__(FFT_THREADS) solve_x_kernel(const float2 *__restrict__ spec, float2 *__restrict__ pot, int H,
+                                                              int Hp, float sig) {
   pdl_wait();
   pdl_trigger();
+  using G = Geo<LOGR>;
+  constexpr int R = G::R;
   extern __shared__ float2 smem[];
-  const int ldl = R + 1;
   float2 *tw = smem;
-  float2 *s = smem + (R >> 1);  // [3 channels + 1 potential][KZT][ldl]
-  fill_twiddles(tw, R);
-  const int y = blockIdx.x & (R - 1), b = blockIdx.x >> logR;
+  float2 *s = smem + R;  // [3 channels][nk][LS]
+  fill_twiddles<LOGR>(tw);
+  const int y = blockIdx.x & (R - 1), b = blockIdx.x >> LOGR;
   const int kz0 = blockIdx.y * KZT;
   const int nk = min(KZT, H - kz0);
   const long long plane = (long long)R * Hp, vol = plane * R;
@@ -312,61 +413,66 @@ __global__ void solve_x_kernel(const float2 *__restrict__ spec, float2 *__restri
     const float2 *src = spec + ((long long)b * 3 + c) * vol + (long long)y * Hp + kz0;
 #pragma unroll 4
     for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
-      const int i = t / KZT, k = t - i * KZT;
-      if (k < nk) s[(c * nk + k) * ldl + bitrev(i, logR)] = src[(long long)i * plane + k];
+      const int i = t / KZT, k = t % KZT;
+      if (k < nk) s[(c * nk + k) * G::LS + G::in_pos(i)] = src[(long long)i * plane + k];
     }
   }
-  fft_tile<false>(s, tw, 3 * nk, R, logR, ldl);
-  float2 *ph = s + 3 * nk * ldl;
+  __syncthreads();
+  fft_lines<LOGR, false>(s, tw, 3 * nk);
+  // frequency i of line (c, k) now lies at out_pos(i); the potential replaces channel 0 in place (same position, same thread)
   const int fy = y < (R >> 1) ? y : y - R;
   const float TWO_PI = 6.2831855f;  // float32(2 pi): the reference scales a float32 frequency tensor in place
   const float wy = __fmul_rn((float)fy, TWO_PI);
   for (int t = threadIdx.x; t < nk * R; t += blockDim.x) {
-    const int k = t >> logR, i = t & (R - 1);
+    const int k = t >> LOGR, i = t & (R - 1);
     const int fx = i < (R >> 1) ? i : i - R;
     const int fz = kz0 + k;
     const double dis = sqrt((double)(fx * fx + fy * fy + fz * fz));
     const double q = (double)sig * 2.0 * dis / (double)R;
-    const float G = (float)exp(-0.5 * (q * q));
+    const float Gf = (float)exp(-0.5 * (q * q));
     const float wx = __fmul_rn((float)fx, TWO_PI), wz = __fmul_rn((float)fz, TWO_PI);
-    const float2 nx = s[(0 * nk + k) * ldl + i], ny = s[(1 * nk + k) * ldl + i], nz = s[(2 * nk + k) * ldl + i];
+    const int pos = G::out_pos(i);
+    const float2 nx = s[(0 * nk + k) * G::LS + pos], ny = s[(1 * nk + k) * G::LS + pos], nz = s[(2 * nk + k) * G::LS + pos];
     // -(i * (G z)) = (G im, -(G re)); summed over the axes in order, each term rounded as the reference's product
-    float re = __fmul_rn(__fmul_rn(nx.y, G), wx);
-    re = __fadd_rn(re, __fmul_rn(__fmul_rn(ny.y, G), wy));
-    re = __fadd_rn(re, __fmul_rn(__fmul_rn(nz.y, G), wz));
-    float im = __fmul_rn(-__fmul_rn(nx.x, G), wx);
-    im = __fadd_rn(im, __fmul_rn(-__fmul_rn(ny.x, G), wy));
-    im = __fadd_rn(im, __fmul_rn(-__fmul_rn(nz.x, G), wz));
+    float re = __fmul_rn(__fmul_rn(nx.y, Gf), wx);
+    re = __fadd_rn(re, __fmul_rn(__fmul_rn(ny.y, Gf), wy));
+    re = __fadd_rn(re, __fmul_rn(__fmul_rn(nz.y, Gf), wz));
+    float im = __fmul_rn(-__fmul_rn(nx.x, Gf), wx);
+    im = __fadd_rn(im, __fmul_rn(-__fmul_rn(ny.x, Gf), wy));
+    im = __fadd_rn(im, __fmul_rn(-__fmul_rn(nz.x, Gf), wz));
     const float lap = -__fadd_rn(__fadd_rn(__fmul_rn(wx, wx), __fmul_rn(wy, wy)), __fmul_rn(wz, wz));
     const float den = __fadd_rn(lap, 1e-6f);
     float2 o = make_float2(__fdiv_rn(re, den), __fdiv_rn(im, den));
     if (fx == 0 && fy == 0 && fz == 0) o = make_float2(0.f, 0.f);
-    ph[k * ldl + bitrev(i, logR)] = o;
+    s[k * G::LS + pos] = o;
   }
-  fft_tile<true>(ph, tw, nk, R, logR, ldl);
+  __syncthreads();
+  ifft_lines_mirror<LOGR>(s, tw, nk);
   float2 *dst = pot + (long long)b * vol + (long long)y * Hp + kz0;
 #pragma unroll 4
   for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
-    const int i = t / KZT, k = t - i * KZT;
-    if (k < nk) dst[(long long)i * plane + k] = ph[k * ldl + i];
+    const int i = t / KZT, k = t % KZT;
+    if (k < nk) dst[(long long)i * plane + k] = s[k * G::LS + G::in_pos(i)];
   }
 }
 
 // ---- inverse Z pass: two Hermitian half spectra per complex transform -> two real lines ------------------------------------
-__global__ void fft_z_inverse_kernel(const float2 *__restrict__ pot, float *__restrict__ phi, long long n_pairs, int R,
-                                     int logR, int pairs_per_cta, float norm, int Hp) {
+template <int LOGR>
+__global__ void __launch_bounds__(FFT_THREADS) fft_z_inverse_kernel(const float2 *__restrict__ pot, float *__restrict__ phi,
+                                                                    long long n_pairs, int pairs_per_cta, float norm, int Hp) {
   pdl_wait();
   pdl_trigger();
+  using G = Geo<LOGR>;
+  constexpr int R = G::R;
   extern __shared__ float2 smem[];
-  const int ldl = R + 1;
   float2 *tw = smem;
-  float2 *s = smem + (R >> 1);
-  fill_twiddles(tw, R);
+  float2 *s = smem + R;
+  fill_twiddles<LOGR>(tw);
   const long long pair0 = (long long)blockIdx.x * pairs_per_cta;
   const int np = (int)min((long long)pairs_per_cta, n_pairs - pair0);
 #pragma unroll 4
   for (int t = threadIdx.x; t < np * R; t += blockDim.x) {
-    const int p = t >> logR, k = t & (R - 1);
+    const int p = t >> LOGR, k = t & (R - 1);
     const float2 *A = pot + (pair0 + p) * 2 * Hp;
     const float2 *Bv = A + Hp;
     float2 z;
@@ -378,13 +484,14 @@ __global__ void fft_z_inverse_kernel(const float2 *__restrict__ pot, float *__re
       const float2 a = A[R - k], c = Bv[R - k];
       z = make_float2(a.x + c.y, c.x - a.y);
     }
-    s[p * ldl + bitrev(k, logR)] = z;
+    s[p * G::LS + G::in_pos(k)] = z;
   }
-  fft_tile<true>(s, tw, np, R, logR, ldl);
+  __syncthreads();
+  fft_lines<LOGR, true>(s, tw, np);
   for (int t = threadIdx.x; t < np * 2 * R; t += blockDim.x) {
     const int p = t / (2 * R), r = t - p * 2 * R;
     const int which = r >= R, i = which ? r - R : r;
-    const float2 z = s[p * ldl + i];
+    const float2 z = s[p * G::LS + G::out_pos(i)];
     phi[((pair0 + p) * 2 + which) * R + i] = (which ? z.y : z.x) * norm;
   }
 }
@@ -457,9 +564,10 @@ int log2_exact(int R) {
   return (1 << l) == R ? l : -1;
 }
 
-// row pitch (in complex values) of the half spectra: R/2+1 rounded up to 32 bytes, so that every row and every 8-value
-// chunk of a row starts on a sector boundary (65 -> 68 at R = 128; the pad columns are never read or written)
-int half_pitch(int R) { return (R / 2 + 1 + 3) & ~3; }
+// row pitch (in complex values) of the half spectra: R/2+1 rounded up to 64 bytes, so that every row and every 8-value
+// chunk of a row is a whole number of 64-byte DRAM bursts (65 -> 72 at R = 128; the pad columns are never read or
+// written).  With a 32-byte pitch (68) ncu showed 1.4-1.6x the algorithmic DRAM reads in the strided passes.
+int half_pitch(int R) { return (R / 2 + 1 + 7) & ~7; }
 
 struct DpsrLayout {
   size_t raster, spec, pot, acc, scal, total;
@@ -481,6 +589,64 @@ DpsrLayout layout_of(int B, int R) {
   L.scal = take((size_t)B * sizeof(float2));
   L.total = off;
   return L;
+}
+
+
+template <typename K>
+int opt_in_smem(K kern, size_t bytes) {
+  if (bytes <= 48 * 1024) return SLIDE_OK;
+  return cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+// The five transform launches of one batch at R = 2^LOGR.
+template <int LOGR>
+int run_transforms_t(int B, float sig, float *raster, float2 *spec, float2 *pot, float *phi, cudaStream_t st) {
+  using G = Geo<LOGR>;
+  constexpr int R = G::R, H = R / 2 + 1;
+  constexpr int KZA = R <= 128 ? 16 : 8;  // kz per CTA of the axis passes (128 / 64 contiguous bytes per row)
+  constexpr int KZS = R <= 128 ? 8 : 4;   // ... of the fused X pass (three channels resident)
+  constexpr int LINES = (2048 / R) < 8 ? 8 : ((2048 / R) > 64 ? 64 : (2048 / R));  // line pairs per CTA of the Z passes
+  const int Hp = half_pitch(R);
+  const size_t tw_bytes = (size_t)R * sizeof(float2), line_bytes = (size_t)G::LS * sizeof(float2);
+  const long long plane = (long long)R * Hp, hvol = plane * R;
+  int rc;
+  {
+    const long long n_pairs = (long long)B * 3 * R * R / 2;
+    launch_k(fft_z_forward_kernel<LOGR>, dim3((unsigned)ceil_div_ll(n_pairs, LINES)), dim3(FFT_THREADS),
+             tw_bytes + LINES * line_bytes, st, (const float *)raster, spec, n_pairs, LINES, Hp);
+    if ((rc = after_launch())) return rc;
+  }
+  // Y pass over the three normal channels: line set (b*3+c, x), element stride Hp
+  launch_k(fft_axis_kernel<LOGR, false, KZA>, dim3(B * 3 * R, ceil_div(H, KZA)), dim3(FFT_THREADS), tw_bytes + KZA * line_bytes,
+           st, spec, R, hvol, plane, (long long)Hp, H);
+  if ((rc = after_launch())) return rc;
+  if ((rc = opt_in_smem(solve_x_kernel<LOGR, KZS>, tw_bytes + 3 * KZS * line_bytes))) return rc;
+  launch_k(solve_x_kernel<LOGR, KZS>, dim3(R * B, ceil_div(H, KZS)), dim3(FFT_THREADS), tw_bytes + 3 * KZS * line_bytes, st,
+           (const float2 *)spec, pot, H, Hp, sig);
+  if ((rc = after_launch())) return rc;
+  launch_k(fft_axis_kernel<LOGR, true, KZA>, dim3(B * R, ceil_div(H, KZA)), dim3(FFT_THREADS), tw_bytes + KZA * line_bytes, st,
+           pot, R, hvol, plane, (long long)Hp, H);
+  if ((rc = after_launch())) return rc;
+  {
+    const long long n_pairs = (long long)B * R * R / 2;
+    const float norm = 1.0f / ((float)R * (float)R * (float)R);
+    launch_k(fft_z_inverse_kernel<LOGR>, dim3((unsigned)ceil_div_ll(n_pairs, LINES)), dim3(FFT_THREADS),
+             tw_bytes + LINES * line_bytes, st, (const float2 *)pot, phi, n_pairs, LINES, norm, Hp);
+    if ((rc = after_launch())) return rc;
+  }
+  return SLIDE_OK;
+}
+
+int run_transforms(int logR, int B, float sig, float *raster, float2 *spec, float2 *pot, float *phi, cudaStream_t st) {
+  switch (logR) {
+    case 3: return run_transforms_t<3>(B, sig, raster, spec, pot, phi, st);
+    case 4: return run_transforms_t<4>(B, sig, raster, spec, pot, phi, st);
+    case 5: return run_transforms_t<5>(B, sig, raster, spec, pot, phi, st);
+    case 6: return run_transforms_t<6>(B, sig, raster, spec, pot, phi, st);
+    case 7: return run_transforms_t<7>(B, sig, raster, spec, pot, phi, st);
+    case 8: return run_transforms_t<8>(B, sig, raster, spec, pot, phi, st);
+  }
+  return SLIDE_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -531,7 +697,6 @@ int slide_dpsr_forward(const float *V, int ldv, const float *Nrm, int ldn, int B
   float2 *pot = (float2 *)(ws + L.pot);
   float *acc = (float *)(ws + L.acc);
   float2 *scal = (float2 *)(ws + L.scal);
-  const int H = R / 2 + 1, Hp = half_pitch(R);
   const size_t vol = (size_t)R * R * R;
   int rc;
   if ((rc = cuda_rc(cudaMemsetAsync(raster, 0, (size_t)B * 3 * vol * sizeof(float), st)))) return rc;
@@ -539,33 +704,7 @@ int slide_dpsr_forward(const float *V, int ldv, const float *Nrm, int ldn, int B
   launch_k(splat_kernel, dim3(ceil_div(B * n, 128)), dim3(128), 0, st, V, ldv, Nrm, ldn, B, n, R, raster);
   if ((rc = after_launch())) return rc;
 
-  const int KZT = R <= 128 ? 8 : 4;
-  const int PAIRS = max(1, 1024 / R);  // 8 pairs (16 lines) per CTA at R = 128
-  const size_t tw_bytes = (size_t)(R / 2) * sizeof(float2), line_bytes = (size_t)(R + 1) * sizeof(float2);
-  {
-    const long long n_pairs = (long long)B * 3 * R * R / 2;
-    launch_k(fft_z_forward_kernel, dim3((unsigned)ceil_div_ll(n_pairs, PAIRS)), dim3(FFT_THREADS), tw_bytes + PAIRS * line_bytes,
-             st, (const float *)raster, spec, n_pairs, R, logR, PAIRS, Hp);
-    if ((rc = after_launch())) return rc;
-  }
-  const long long plane = (long long)R * Hp, hvol = plane * R;
-  // Y pass over the three normal channels: line set (b*3+c, x), element stride H
-  launch_k(fft_axis_kernel<false>, dim3(B * 3 * R, ceil_div(H, KZT)), dim3(FFT_THREADS), tw_bytes + KZT * line_bytes, st, spec, R,
-           hvol, plane, (long long)Hp, H, R, logR, KZT);
-  if ((rc = after_launch())) return rc;
-  launch_k(solve_x_kernel, dim3(R * B, ceil_div(H, KZT)), dim3(FFT_THREADS), tw_bytes + 4 * KZT * line_bytes, st,
-           (const float2 *)spec, pot, R, logR, H, Hp, KZT, sig);
-  if ((rc = after_launch())) return rc;
-  launch_k(fft_axis_kernel<true>, dim3(B * R, ceil_div(H, KZT)), dim3(FFT_THREADS), tw_bytes + KZT * line_bytes, st, pot, R, hvol,
-           plane, (long long)Hp, H, R, logR, KZT);
-  if ((rc = after_launch())) return rc;
-  {
-    const long long n_pairs = (long long)B * R * R / 2;
-    const float norm = 1.0f / ((float)R * (float)R * (float)R);
-    launch_k(fft_z_inverse_kernel, dim3((unsigned)ceil_div_ll(n_pairs, PAIRS)), dim3(FFT_THREADS), tw_bytes + PAIRS * line_bytes,
-             st, (const float2 *)pot, phi, n_pairs, R, logR, PAIRS, norm, Hp);
-    if ((rc = after_launch())) return rc;
-  }
+  if ((rc = run_transforms(logR, B, sig, raster, spec, pot, phi, st))) return rc;
   if (!shift && !scale) return SLIDE_OK;
   if (shift) {
     launch_k(interp_sum_kernel, dim3(ceil_div(n, 256), B), dim3(256), 0, st, (const float *)phi, V, ldv, n, R, acc);

@@ -89,7 +89,7 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:  # noqa: BLE001
         pass
-    hbm = float(peaks.get("hbm_gbps_sustained", peaks.get("hbm_gbps", 6538.3)))
+    hbm = float(peaks.get("hbm_gbs", 6500.0))
     dbytes = dpsr_bytes_per_cloud(R) * B
     total = sum(ms)
     print(json.dumps({

@@ -39,6 +39,7 @@ def main():
         p.lat.run()
 
     def both():
+        nonlocal s1, s2
         cur = torch.cuda.current_stream()
         s1.wait_stream(cur)
         s2.wait_stream(cur)
@@ -52,6 +53,11 @@ def main():
         cur.wait_stream(s2)
 
     out = {"batch": B, "pos_ms": timed(pos_alone), "lat_ms": timed(lat_alone), "both_ms": timed(both)}
+    lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+    out["priority_range"] = [lo, hi]
+    for name, (p1, p2) in {"lat_high": (0, -1), "pos_high": (-1, 0), "lat_highest": (0, hi)}.items():
+        s1, s2 = torch.cuda.Stream(priority=p1), torch.cuda.Stream(priority=p2)
+        out["both_ms_" + name] = timed(both)
     out["sum_ms"] = out["pos_ms"] + out["lat_ms"]
     out["overlap_gain"] = out["sum_ms"] / out["both_ms"]
     out["finite"] = bool(torch.isfinite(p.pos.x_view()).all().item() and torch.isfinite(p.lat.x_view()).all().item())

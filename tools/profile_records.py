@@ -19,6 +19,23 @@ def main():
     backend = sys.argv[3] if len(sys.argv) > 3 else "auto"
     reps = 7
     cfg = weights.load_json("pipeline_airplane.json")
+    if which == "refine":
+        # the SAP refinement network: B clouds of 4096 mirrored points, one forward + the point split
+        rc = weights.load_json("sap_refine.json")
+        sd = weights.random_state_dict(weights.load_json("schema_sap_refine.json"), 21)
+        b, h = engine.build_refine(rc["pointnet_config"], sd, B, 4096)
+        b.segments["forward"] = b.segments["refine"]
+        prog = Program(b)
+        prog.set_gemm_backend(backend)
+        engine.init_constants(prog, h)
+        prog.upload(h["labels"], torch.zeros(B, dtype=torch.int32))
+        prog.run_segment("setup")
+        g = torch.Generator().manual_seed(0)
+        x = torch.cat([torch.rand(B * 4096, 3, generator=g) - 0.5,
+                       torch.nn.functional.normalize(torch.randn(B * 4096, 3, generator=g), dim=1),
+                       torch.ones(B * 4096, 1)], dim=1)
+        prog.upload(h["x"], x)
+        return profile(b, prog, which, B, backend, reps)
     if which == "pos":
         pc = cfg["position_ddpm"]["pointnet_config"]
         d = cfg["position_ddpm"]["diffusion_config"]
@@ -36,6 +53,10 @@ def main():
     prog.upload(h["labels"], torch.zeros(B, dtype=torch.int32))
     prog.run_segment("setup")
     prog.upload(h["x"], torch.randn(B * 16, h["C"]))
+    return profile(b, prog, which, B, backend, reps)
+
+
+def profile(b, prog, which, B, backend, reps):
     first, count = b.segments["forward"]
     prog.set_step(501)
     prog.run(first, count)
