@@ -408,7 +408,7 @@ def main():
         sp.draw_host_inputs(torch.full((256,), cfg_s["label"], dtype=torch.long))
         g_s = pipeline.all_gather_outputs(sp.sample(), world)  # warm-up (captures the graphs)
         sp.stage_inputs()
-        ns = max(1, min(args.steps, 2))
+        ns = max(1, min(args.steps, 6))  # enough steps for the cross-batch pipeline to fill (first step: no overlap)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
@@ -425,6 +425,21 @@ def main():
                   "gathered_shape": list(g_s.shape), "finite": bool(torch.isfinite(g_s).all().item()),
                   "launches_per_step": {"position": sp.pos.launches_per_step(), "latent": sp.lat.launches_per_step()}}
         del sp, g_s
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE config 5 at N > 1 GPUs: the autoencoder sweep with its batch of 512 clouds sharded 512 / N per GPU
+    # (every cloud is independent: no collective); time = max over ranks.  At N = 1 the sweep is in `configs` below.
+    ae_sweep = None
+    if args.ddpm_steps is None and not args.no_extras and world > 1 and 512 % world == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_autoencoder
+        rows = bench_autoencoder.sweep(512 // world, reps=1)
+        tt = torch.tensor([[r["encode_ms"], r["decode_ms"]] for r in rows], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ae_sweep = [{"points": r["points"], "global_batch": 512, "per_gpu_batch": 512 // world, "n_gpus": world,
+                     "encode_ms": float(tt[i, 0]), "decode_ms": float(tt[i, 1]),
+                     "shapes_per_s": 512 / (float(tt[i, 0] + tt[i, 1]) / 1e3), "finite": r["finite"]}
+                    for i, r in enumerate(rows)]
         torch.cuda.empty_cache()
 
     roof = None
@@ -535,7 +550,8 @@ def main():
                                 "pinned H2D, 3 stages, D2H"},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roof, "cpu_baseline": cpu,
             "finite": finite, "tc_error": tc_err, "parity": parity, "stages_ms": stages,
-            "noise_path": getattr(pipe, "noise_path", None), "strong": strong, **extras}))
+            "noise_path": getattr(pipe, "noise_path", None), "strong": strong,
+            **({"config5_sharded": ae_sweep} if ae_sweep else {}), **extras}))
     if world > 1:
         dist.destroy_process_group()
 
