@@ -458,6 +458,7 @@ struct PairArgs {
   XFd xfr;
   const int *step;
   int pb;  // points per CTA
+  int pf;  // pair_smem_kernel: L2 prefetch distance of the residual rows, in loop iterations (0 = none)
 };
 
 // RB = rows in flight per thread.  The neighbour indices (and squared distances) of a point are fetched ONCE as a
@@ -674,6 +675,11 @@ __global__ void __launch_bounds__(PS_THREADS) pair_smem_kernel(PairArgs a, int C
     idx_s[r] = __ldg(a.idx + prow0 + r);
     if (HAS_D2) dk_s[r] = __ldg(a.d2 + prow0 + r);
   }
+  if (HAS_RES && a.pf > 0 && live && (ct & 7) == 0 && n + 3 < a.N) {
+    // the first iterations' residual rows: requested now, they arrive while the source rows are staged below
+    for (int r = rg; r < rows && r < rg + 4 * a.pf * RG; r += RG)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + (prow0 + r) * a.ldr + n));
+  }
   // ---- per-column constants of this thread's 4 columns
   bool on[4];
   float wx[4][3], wc[4][3], bias[4], wd[4], ww[4], rsc[4], rsh[4], radd[4];
@@ -746,9 +752,21 @@ __global__ void __launch_bounds__(PS_THREADS) pair_smem_kernel(PairArgs a, int C
   }
 
   // ---- output rows
+  // The residual stream is the kernel's HBM read (256 KB per CTA at N = 512).  A thread keeps 4 x 16 bytes of it in flight
+  // (registers); at 3 CTAs per SM that is 48 KB per SM, short of what 6.5 TB/s at loaded-DRAM latency needs (ncu: 2.8
+  // TB/s, 30 % occupancy, long-scoreboard stalls).  One lane per 128-byte line therefore asks L2 for the rows of the
+  // next a.pf iterations -- prefetches hold no registers -- so the loads below hit L2.
+  const bool pf_lane = HAS_RES && a.pf > 0 && full && (ct & 7) == 0;
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
   if (any) {
     for (int r0 = rg; r0 < rows; r0 += 4 * RG) {
+      if (pf_lane) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int r = r0 + (4 * a.pf + b) * RG;
+          if (r < rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + (prow0 + r) * a.ldr + n));
+        }
+      }
       float4 r4[4];
       bool ron[4];
 #pragma unroll
@@ -943,6 +961,8 @@ namespace {
 // PAIR launch-shape knobs: environment read once (slide_tc_reload_tuning() re-reads)
 bool g_pair_tuning_loaded = false;
 int g_pair_min_ctas = 2368, g_pair_min_rows = 32, g_pair_smem = 1, g_pair_pb = 8, g_pair_smem_min_ctas = 296;
+int g_pair_prefetch = 1;  // SLIDE_PAIR_PREFETCH: residual rows are prefetched into L2 this many loop iterations ahead (0 = off).
+                          // A/B on B200, batch 256, feature step: 0 -> 1486 us, 1 -> 1474, 2 -> 1477, 4 -> 1478, 8 -> 1490
 
 template <typename T>
 inline T *AP(slide_program *p, int64_t off) {
@@ -1169,6 +1189,8 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
         if (g_pair_pb < 1) g_pair_pb = 1;
         const char *e_mc = getenv("SLIDE_PAIR_SMEM_MIN_CTAS");
         g_pair_smem_min_ctas = e_mc ? atoi(e_mc) : 296;
+        const char *e_pf = getenv("SLIDE_PAIR_PREFETCH");
+        g_pair_prefetch = e_pf ? atoi(e_pf) : 1;
         g_pair_tuning_loaded = true;
       }
       // small gather source (the denoisers: the sample's own 16 points): stage it in shared memory
@@ -1179,6 +1201,7 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
         const size_t smem = ((size_t)(a.nsrc + pbs + 2 * RG) * ldn + 3 * (size_t)pbs * a.K) * 4;
         if (smem <= 160 * 1024) {
           a.pb = pbs;
+          a.pf = g_pair_prefetch;
           if (a.res) return a.d2 ? launch_pair_smem<true, true>(a, B, CT, RG, ldn, smem, st)
                                  : launch_pair_smem<true, false>(a, B, CT, RG, ldn, smem, st);
           return a.d2 ? launch_pair_smem<false, true>(a, B, CT, RG, ldn, smem, st)
