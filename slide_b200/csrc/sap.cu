@@ -79,6 +79,18 @@ __device__ __forceinline__ void reg_fft(float2 (&v)[N]) {
   }
 }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS): the next tile of a persistent CTA is in flight while the current
+// one is transformed; they hold no registers and complete in groups.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // tw[j] = exp(-2 pi i j / R), j < R
 template <int LOGR>
 __device__ __forceinline__ void fill_twiddles(float2 *tw) {
@@ -322,178 +334,280 @@ __global__ void splat_kernel(const float *__restrict__ V, int ldv, const float *
   }
 }
 
+// All transform kernels are PERSISTENT and double-buffered: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the
+// raw bytes of tile i+1 are requested (cp.async) before tile i is repacked into the padded transform layout, transformed
+// and stored, so every SM keeps 48-64 KB of reads in flight all the time (the one-tile-per-CTA version alternated load /
+// compute / store phases and sat at 2.4 TB/s with the SMs 40-57 % busy: latency-bound).
+
 // ---- Z pass: real lines -> half spectra, two lines per complex transform --------------------------------------------------
 // raster f32 [lines, R]  ->  spec float2 [lines, Hp]
-template <int LOGR>
+template <int LOGR, int LINES>
 __global__ void __launch_bounds__(FFT_THREADS) fft_z_forward_kernel(const float *__restrict__ raster, float2 *__restrict__ spec,
-                                                                    long long n_pairs, int pairs_per_cta, int Hp) {
+                                                                    long long n_pairs, int Hp) {
   pdl_wait();
   pdl_trigger();
   using G = Geo<LOGR>;
   constexpr int R = G::R, H = R / 2 + 1;
-  extern __shared__ float2 smem[];
+  extern __shared__ __align__(16) float2 smem[];
   float2 *tw = smem;
   float2 *s = smem + R;
+  float *raw0 = reinterpret_cast<float *>(s + LINES * G::LS + (((LINES * G::LS) & 1) ? 1 : 0));  // 16-byte aligned
+  constexpr int RAW_STRIDE = LINES * 2 * R;
   fill_twiddles<LOGR>(tw);
-  const long long pair0 = (long long)blockIdx.x * pairs_per_cta;
-  const int np = (int)min((long long)pairs_per_cta, n_pairs - pair0);
+  const long long n_tiles = (n_pairs + LINES - 1) / LINES;
+  auto issue = [&](long long tile, float *dst) {
+    const long long pair0 = tile * LINES;
+    const int np = (int)min((long long)LINES, n_pairs - pair0);
+    const float *src = raster + pair0 * 2 * R;
+    for (int c = threadIdx.x; c < np * 2 * R / 4; c += blockDim.x) cp_async16(dst + 4 * c, src + 4 * c);
+  };
+  long long tile = blockIdx.x;
+  int buf = 0;
+  if (tile < n_tiles) issue(tile, raw0);
+  cp_async_commit();
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x, raw0 + (buf ^ 1) * RAW_STRIDE);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const long long pair0 = tile * LINES;
+    const int np = (int)min((long long)LINES, n_pairs - pair0);
+    const float *rw = raw0 + buf * RAW_STRIDE;
 #pragma unroll 4
-  for (int t = threadIdx.x; t < np * R; t += blockDim.x) {
-    const int p = t >> LOGR, i = t & (R - 1);
-    const float *a = raster + (pair0 + p) * 2 * R;
-    s[p * G::LS + G::in_pos(i)] = make_float2(a[i], a[R + i]);
+    for (int t = threadIdx.x; t < np * R; t += blockDim.x) {
+      const int p = t >> LOGR, i = t & (R - 1);
+      s[p * G::LS + G::in_pos(i)] = make_float2(rw[p * 2 * R + i], rw[p * 2 * R + R + i]);
+    }
+    __syncthreads();
+    fft_lines<LOGR, false>(s, tw, np);
+    for (int t = threadIdx.x; t < np * 2 * H; t += blockDim.x) {
+      const int p = t / (2 * H), r = t - p * 2 * H;
+      const int which = r >= H, k = which ? r - H : r;
+      const float2 zk = s[p * G::LS + G::out_pos(k)], zr = s[p * G::LS + G::out_pos((R - k) & (R - 1))];
+      float2 o;
+      if (!which)
+        o = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
+      else
+        o = make_float2(0.5f * (zk.y + zr.y), -0.5f * (zk.x - zr.x));
+      spec[((pair0 + p) * 2 + which) * Hp + k] = o;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  fft_lines<LOGR, false>(s, tw, np);
-  for (int t = threadIdx.x; t < np * 2 * H; t += blockDim.x) {
-    const int p = t / (2 * H), r = t - p * 2 * H;
-    const int which = r >= H, k = which ? r - H : r;
-    const float2 zk = s[p * G::LS + G::out_pos(k)], zr = s[p * G::LS + G::out_pos((R - k) & (R - 1))];
-    float2 o;
-    if (!which)
-      o = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
-    else
-      o = make_float2(0.5f * (zk.y + zr.y), -0.5f * (zk.x - zr.x));
-    spec[((pair0 + p) * 2 + which) * Hp + k] = o;
-  }
+  cp_async_wait<0>();
 }
 
 // ---- generic in-place complex pass along a strided axis ---------------------------------------------------------------------
 // data float2; a line set o = (o_hi, o_lo), o_lo < n_lo: base = o_hi*stride_hi + o_lo*stride_lo; element i of the line at
-// kz is base + i*es + kz.  One CTA: KZT neighbouring kz of one line set (KZT * 8 contiguous bytes per row).
+// kz is base + i*es + kz.  One tile: KZT neighbouring kz of one line set (KZT * 8 contiguous bytes per row).
 template <int LOGR, bool INV, int KZT>
-__global__ void __launch_bounds__(FFT_THREADS) fft_axis_kernel(float2 *__restrict__ data, int n_lo, long long stride_hi,
-                                                               long long stride_lo, long long es, int H) {
+__global__ void __launch_bounds__(FFT_THREADS) fft_axis_kernel(float2 *__restrict__ data, int n_sets, int n_lo, long long stride_hi,
+                                                               long long stride_lo, long long es, int H, int Hp) {
   pdl_wait();
   pdl_trigger();
   using G = Geo<LOGR>;
-  constexpr int R = G::R;
-  extern __shared__ float2 smem[];
+  constexpr int R = G::R, CH = KZT / 2;  // 16-byte chunks per row
+  extern __shared__ __align__(16) float2 smem[];
   float2 *tw = smem;
   float2 *s = smem + R;
+  float2 *raw0 = s + KZT * G::LS + (((KZT * G::LS) & 1) ? 1 : 0);
+  constexpr int RAW_STRIDE = R * KZT;
   fill_twiddles<LOGR>(tw);
-  const int o = blockIdx.x;
-  const int kz0 = blockIdx.y * KZT;
-  const int nk = min(KZT, H - kz0);
-  float2 *base = data + (long long)(o / n_lo) * stride_hi + (long long)(o % n_lo) * stride_lo + kz0;
+  const int kchunks = (H + KZT - 1) / KZT;
+  const long long n_tiles = (long long)n_sets * kchunks;
+  auto base_of = [&](long long tile, int &kz0) -> float2 * {
+    const int o = (int)(tile / kchunks);
+    kz0 = (int)(tile % kchunks) * KZT;
+    return data + (long long)(o / n_lo) * stride_hi + (long long)(o % n_lo) * stride_lo + kz0;
+  };
+  auto issue = [&](long long tile, float2 *dst) {
+    int kz0;
+    const float2 *base = base_of(tile, kz0);
+    for (int c = threadIdx.x; c < R * CH; c += blockDim.x) {
+      const int i = c / CH, j = c % CH;
+      if (kz0 + 2 * j < Hp) cp_async16(dst + i * KZT + 2 * j, base + (long long)i * es + 2 * j);
+    }
+  };
+  long long tile = blockIdx.x;
+  int buf = 0;
+  if (tile < n_tiles) issue(tile, raw0);
+  cp_async_commit();
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x, raw0 + (buf ^ 1) * RAW_STRIDE);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    int kz0;
+    float2 *base = base_of(tile, kz0);
+    const int nk = min(KZT, H - kz0);
+    const float2 *rw = raw0 + buf * RAW_STRIDE;
 #pragma unroll 4
-  for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
-    const int i = t / KZT, k = t % KZT;
-    if (k < nk) s[k * G::LS + G::in_pos(i)] = base[(long long)i * es + k];
-  }
-  __syncthreads();
-  fft_lines<LOGR, INV>(s, tw, nk);
+    for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
+      const int i = t / KZT, k = t % KZT;
+      if (k < nk) s[k * G::LS + G::in_pos(i)] = rw[t];
+    }
+    __syncthreads();
+    fft_lines<LOGR, INV>(s, tw, nk);
 #pragma unroll 4
-  for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
-    const int i = t / KZT, k = t % KZT;
-    if (k < nk) base[(long long)i * es + k] = s[k * G::LS + G::out_pos(i)];
+    for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
+      const int i = t / KZT, k = t % KZT;
+      if (k < nk) base[(long long)i * es + k] = s[k * G::LS + G::out_pos(i)];
+    }
+    __syncthreads();
   }
+  cp_async_wait<0>();
 }
 
 // ---- X pass + spectral solve + inverse X pass --------------------------------------------------------------------------------
 // spec float2 [B,3,R(x),R(y),Hp] (Z and Y already transformed)  ->  pot float2 [B,R(x),R(y),Hp] (X already inverted)
 //   Phi = sum_d (-i G N_d) w_d / (-(|w|^2) + 1e-6),  w = 2 pi k,  G = exp(-0.5 (2 sig |k| / R)^2),  Phi(0) = 0
 template <int LOGR, int KZT>
-__global__ void __launch_bounds__(FFT_THREADS) solve_x_kernel(const float2 *__restrict__ spec, float2 *__restrict__ pot, int H,
-                                                              int Hp, float sig) {
+__global__ void __launch_bounds__(FFT_THREADS) solve_x_kernel(const float2 *__restrict__ spec, float2 *__restrict__ pot, int B,
+                                                              int H, int Hp, float sig) {
   pdl_wait();
   pdl_trigger();
   using G = Geo<LOGR>;
-  constexpr int R = G::R;
-  extern __shared__ float2 smem[];
+  constexpr int R = G::R, CH = KZT / 2;
+  extern __shared__ __align__(16) float2 smem[];
   float2 *tw = smem;
   float2 *s = smem + R;  // [3 channels][nk][LS]
+  float2 *raw0 = s + 3 * KZT * G::LS + (((3 * KZT * G::LS) & 1) ? 1 : 0);
+  constexpr int RAW_STRIDE = 3 * R * KZT;
   fill_twiddles<LOGR>(tw);
-  const int y = blockIdx.x & (R - 1), b = blockIdx.x >> LOGR;
-  const int kz0 = blockIdx.y * KZT;
-  const int nk = min(KZT, H - kz0);
+  const int kchunks = (H + KZT - 1) / KZT;
+  const long long n_tiles = (long long)B * R * kchunks;
   const long long plane = (long long)R * Hp, vol = plane * R;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float2 *src = spec + ((long long)b * 3 + c) * vol + (long long)y * Hp + kz0;
+  auto issue = [&](long long tile, float2 *dst) {
+    const int by = (int)(tile / kchunks), kz0 = (int)(tile % kchunks) * KZT;
+    const int y = by & (R - 1), b = by >> LOGR;
+    for (int c = threadIdx.x; c < 3 * R * CH; c += blockDim.x) {
+      const int ch = c / (R * CH), rem = c - ch * (R * CH);
+      const int i = rem / CH, j = rem % CH;
+      if (kz0 + 2 * j < Hp)
+        cp_async16(dst + (ch * R + i) * KZT + 2 * j,
+                   spec + ((long long)b * 3 + ch) * vol + (long long)i * plane + (long long)y * Hp + kz0 + 2 * j);
+    }
+  };
+  long long tile = blockIdx.x;
+  int buf = 0;
+  if (tile < n_tiles) issue(tile, raw0);
+  cp_async_commit();
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x, raw0 + (buf ^ 1) * RAW_STRIDE);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int by = (int)(tile / kchunks), kz0 = (int)(tile % kchunks) * KZT;
+    const int y = by & (R - 1), b = by >> LOGR;
+    const int nk = min(KZT, H - kz0);
+    const float2 *rw = raw0 + buf * RAW_STRIDE;
+#pragma unroll 4
+    for (int t = threadIdx.x; t < 3 * R * KZT; t += blockDim.x) {
+      const int ch = t / (R * KZT), rem = t - ch * (R * KZT);
+      const int i = rem / KZT, k = rem % KZT;
+      if (k < nk) s[(ch * nk + k) * G::LS + G::in_pos(i)] = rw[t];
+    }
+    __syncthreads();
+    fft_lines<LOGR, false>(s, tw, 3 * nk);
+    // frequency i of line (c, k) now lies at out_pos(i); the potential replaces channel 0 in place (same position, same thread)
+    const int fy = y < (R >> 1) ? y : y - R;
+    const float TWO_PI = 6.2831855f;  // float32(2 pi): the reference scales a float32 frequency tensor in place
+    const float wy = __fmul_rn((float)fy, TWO_PI);
+    for (int t = threadIdx.x; t < nk * R; t += blockDim.x) {
+      const int k = t >> LOGR, i = t & (R - 1);
+      const int fx = i < (R >> 1) ? i : i - R;
+      const int fz = kz0 + k;
+      const double dis = sqrt((double)(fx * fx + fy * fy + fz * fz));
+      const double q = (double)sig * 2.0 * dis / (double)R;
+      const float Gf = (float)exp(-0.5 * (q * q));
+      const float wx = __fmul_rn((float)fx, TWO_PI), wz = __fmul_rn((float)fz, TWO_PI);
+      const int pos = G::out_pos(i);
+      const float2 nx = s[(0 * nk + k) * G::LS + pos], ny = s[(1 * nk + k) * G::LS + pos], nz = s[(2 * nk + k) * G::LS + pos];
+      // -(i * (G z)) = (G im, -(G re)); summed over the axes in order, each term rounded as the reference's product
+      float re = __fmul_rn(__fmul_rn(nx.y, Gf), wx);
+      re = __fadd_rn(re, __fmul_rn(__fmul_rn(ny.y, Gf), wy));
+      re = __fadd_rn(re, __fmul_rn(__fmul_rn(nz.y, Gf), wz));
+      float im = __fmul_rn(-__fmul_rn(nx.x, Gf), wx);
+      im = __fadd_rn(im, __fmul_rn(-__fmul_rn(ny.x, Gf), wy));
+      im = __fadd_rn(im, __fmul_rn(-__fmul_rn(nz.x, Gf), wz));
+      const float lap = -__fadd_rn(__fadd_rn(__fmul_rn(wx, wx), __fmul_rn(wy, wy)), __fmul_rn(wz, wz));
+      const float den = __fadd_rn(lap, 1e-6f);
+      float2 o = make_float2(__fdiv_rn(re, den), __fdiv_rn(im, den));
+      if (fx == 0 && fy == 0 && fz == 0) o = make_float2(0.f, 0.f);
+      s[k * G::LS + pos] = o;
+    }
+    __syncthreads();
+    ifft_lines_mirror<LOGR>(s, tw, nk);
+    float2 *dst = pot + (long long)b * vol + (long long)y * Hp + kz0;
 #pragma unroll 4
     for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
       const int i = t / KZT, k = t % KZT;
-      if (k < nk) s[(c * nk + k) * G::LS + G::in_pos(i)] = src[(long long)i * plane + k];
+      if (k < nk) dst[(long long)i * plane + k] = s[k * G::LS + G::in_pos(i)];
     }
+    __syncthreads();
   }
-  __syncthreads();
-  fft_lines<LOGR, false>(s, tw, 3 * nk);
-  // frequency i of line (c, k) now lies at out_pos(i); the potential replaces channel 0 in place (same position, same thread)
-  const int fy = y < (R >> 1) ? y : y - R;
-  const float TWO_PI = 6.2831855f;  // float32(2 pi): the reference scales a float32 frequency tensor in place
-  const float wy = __fmul_rn((float)fy, TWO_PI);
-  for (int t = threadIdx.x; t < nk * R; t += blockDim.x) {
-    const int k = t >> LOGR, i = t & (R - 1);
-    const int fx = i < (R >> 1) ? i : i - R;
-    const int fz = kz0 + k;
-    const double dis = sqrt((double)(fx * fx + fy * fy + fz * fz));
-    const double q = (double)sig * 2.0 * dis / (double)R;
-    const float Gf = (float)exp(-0.5 * (q * q));
-    const float wx = __fmul_rn((float)fx, TWO_PI), wz = __fmul_rn((float)fz, TWO_PI);
-    const int pos = G::out_pos(i);
-    const float2 nx = s[(0 * nk + k) * G::LS + pos], ny = s[(1 * nk + k) * G::LS + pos], nz = s[(2 * nk + k) * G::LS + pos];
-    // -(i * (G z)) = (G im, -(G re)); summed over the axes in order, each term rounded as the reference's product
-    float re = __fmul_rn(__fmul_rn(nx.y, Gf), wx);
-    re = __fadd_rn(re, __fmul_rn(__fmul_rn(ny.y, Gf), wy));
-    re = __fadd_rn(re, __fmul_rn(__fmul_rn(nz.y, Gf), wz));
-    float im = __fmul_rn(-__fmul_rn(nx.x, Gf), wx);
-    im = __fadd_rn(im, __fmul_rn(-__fmul_rn(ny.x, Gf), wy));
-    im = __fadd_rn(im, __fmul_rn(-__fmul_rn(nz.x, Gf), wz));
-    const float lap = -__fadd_rn(__fadd_rn(__fmul_rn(wx, wx), __fmul_rn(wy, wy)), __fmul_rn(wz, wz));
-    const float den = __fadd_rn(lap, 1e-6f);
-    float2 o = make_float2(__fdiv_rn(re, den), __fdiv_rn(im, den));
-    if (fx == 0 && fy == 0 && fz == 0) o = make_float2(0.f, 0.f);
-    s[k * G::LS + pos] = o;
-  }
-  __syncthreads();
-  ifft_lines_mirror<LOGR>(s, tw, nk);
-  float2 *dst = pot + (long long)b * vol + (long long)y * Hp + kz0;
-#pragma unroll 4
-  for (int t = threadIdx.x; t < R * KZT; t += blockDim.x) {
-    const int i = t / KZT, k = t % KZT;
-    if (k < nk) dst[(long long)i * plane + k] = s[k * G::LS + G::in_pos(i)];
-  }
+  cp_async_wait<0>();
 }
 
 // ---- inverse Z pass: two Hermitian half spectra per complex transform -> two real lines ------------------------------------
-template <int LOGR>
+template <int LOGR, int LINES>
 __global__ void __launch_bounds__(FFT_THREADS) fft_z_inverse_kernel(const float2 *__restrict__ pot, float *__restrict__ phi,
-                                                                    long long n_pairs, int pairs_per_cta, float norm, int Hp) {
+                                                                    long long n_pairs, float norm, int Hp) {
   pdl_wait();
   pdl_trigger();
   using G = Geo<LOGR>;
   constexpr int R = G::R;
-  extern __shared__ float2 smem[];
+  extern __shared__ __align__(16) float2 smem[];
   float2 *tw = smem;
   float2 *s = smem + R;
+  float2 *raw0 = s + LINES * G::LS + (((LINES * G::LS) & 1) ? 1 : 0);
+  const int RAW_STRIDE = LINES * 2 * Hp;
   fill_twiddles<LOGR>(tw);
-  const long long pair0 = (long long)blockIdx.x * pairs_per_cta;
-  const int np = (int)min((long long)pairs_per_cta, n_pairs - pair0);
+  const long long n_tiles = (n_pairs + LINES - 1) / LINES;
+  auto issue = [&](long long tile, float2 *dst) {
+    const long long pair0 = tile * LINES;
+    const int np = (int)min((long long)LINES, n_pairs - pair0);
+    const float2 *src = pot + pair0 * 2 * Hp;
+    for (int c = threadIdx.x; c < np * Hp; c += blockDim.x) cp_async16(dst + 2 * c, src + 2 * c);  // Hp is even
+  };
+  long long tile = blockIdx.x;
+  int buf = 0;
+  if (tile < n_tiles) issue(tile, raw0);
+  cp_async_commit();
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x, raw0 + (buf ^ 1) * RAW_STRIDE);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const long long pair0 = tile * LINES;
+    const int np = (int)min((long long)LINES, n_pairs - pair0);
+    const float2 *rw = raw0 + buf * RAW_STRIDE;
 #pragma unroll 4
-  for (int t = threadIdx.x; t < np * R; t += blockDim.x) {
-    const int p = t >> LOGR, k = t & (R - 1);
-    const float2 *A = pot + (pair0 + p) * 2 * Hp;
-    const float2 *Bv = A + Hp;
-    float2 z;
-    if (k <= (R >> 1)) {
-      float2 a = A[k], c = Bv[k];
-      if (k == 0 || k == (R >> 1)) a.y = 0.f, c.y = 0.f;  // a real-output transform ignores these imaginary parts
-      z = make_float2(a.x - c.y, a.y + c.x);
-    } else {
-      const float2 a = A[R - k], c = Bv[R - k];
-      z = make_float2(a.x + c.y, c.x - a.y);
+    for (int t = threadIdx.x; t < np * R; t += blockDim.x) {
+      const int p = t >> LOGR, k = t & (R - 1);
+      const float2 *A = rw + p * 2 * Hp;
+      const float2 *Bv = A + Hp;
+      float2 z;
+      if (k <= (R >> 1)) {
+        float2 a = A[k], c = Bv[k];
+        if (k == 0 || k == (R >> 1)) a.y = 0.f, c.y = 0.f;  // a real-output transform ignores these imaginary parts
+        z = make_float2(a.x - c.y, a.y + c.x);
+      } else {
+        const float2 a = A[R - k], c = Bv[R - k];
+        z = make_float2(a.x + c.y, c.x - a.y);
+      }
+      s[p * G::LS + G::in_pos(k)] = z;
     }
-    s[p * G::LS + G::in_pos(k)] = z;
+    __syncthreads();
+    fft_lines<LOGR, true>(s, tw, np);
+    for (int t = threadIdx.x; t < np * 2 * R; t += blockDim.x) {
+      const int p = t / (2 * R), r = t - p * 2 * R;
+      const int which = r >= R, i = which ? r - R : r;
+      const float2 z = s[p * G::LS + G::out_pos(i)];
+      phi[((pair0 + p) * 2 + which) * R + i] = (which ? z.y : z.x) * norm;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  fft_lines<LOGR, true>(s, tw, np);
-  for (int t = threadIdx.x; t < np * 2 * R; t += blockDim.x) {
-    const int p = t / (2 * R), r = t - p * 2 * R;
-    const int which = r >= R, i = which ? r - R : r;
-    const float2 z = s[p * G::LS + G::out_pos(i)];
-    phi[((pair0 + p) * 2 + which) * R + i] = (which ? z.y : z.x) * norm;
-  }
+  cp_async_wait<0>();
 }
 
 // ---- read-back at the points, mean per sample -----------------------------------------------------------------------------------
@@ -592,10 +706,38 @@ DpsrLayout layout_of(int B, int R) {
 }
 
 
-template <typename K>
-int opt_in_smem(K kern, size_t bytes) {
+// Opt a kernel instantiation into > 48 KB of dynamic shared memory, once per device (the attribute is per function and
+// device; re-setting it on every launch stalls the stream: 33 ms per batch instead of 3).
+template <auto Kern>
+int opt_in_smem(size_t bytes) {
+  static bool done[64] = {false};
   if (bytes <= 48 * 1024) return SLIDE_OK;
-  return cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (done[dev]) return SLIDE_OK;
+  const int rc = cuda_rc(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  if (rc == SLIDE_OK) done[dev] = true;
+  return rc;
+}
+
+int sm_count_cached() {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!sms[dev]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
+  }
+  return sms[dev];
+}
+
+// persistent grid: as many CTAs as fit (shared memory / 8 per SM), never more than there are tiles
+unsigned persistent_grid(long long n_tiles, size_t smem_bytes) {
+  int per_sm = (int)((220 * 1024) / (smem_bytes + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  const long long g = (long long)sm_count_cached() * per_sm;
+  return (unsigned)(n_tiles < g ? n_tiles : g);
 }
 
 // The five transform launches of one batch at R = 2^LOGR.
@@ -603,35 +745,46 @@ template <int LOGR>
 int run_transforms_t(int B, float sig, float *raster, float2 *spec, float2 *pot, float *phi, cudaStream_t st) {
   using G = Geo<LOGR>;
   constexpr int R = G::R, H = R / 2 + 1;
-  constexpr int KZA = R <= 128 ? 16 : 8;  // kz per CTA of the axis passes (128 / 64 contiguous bytes per row)
+  constexpr int KZA = R <= 128 ? 16 : 8;  // kz per tile of the axis passes (128 / 64 contiguous bytes per row)
   constexpr int KZS = R <= 128 ? 8 : 4;   // ... of the fused X pass (three channels resident)
-  constexpr int LINES = (2048 / R) < 8 ? 8 : ((2048 / R) > 64 ? 64 : (2048 / R));  // line pairs per CTA of the Z passes
+  constexpr int LINES = (2048 / R) < 8 ? 8 : ((2048 / R) > 64 ? 64 : (2048 / R));  // line pairs per tile of the Z passes
   const int Hp = half_pitch(R);
   const size_t tw_bytes = (size_t)R * sizeof(float2), line_bytes = (size_t)G::LS * sizeof(float2);
   const long long plane = (long long)R * Hp, hvol = plane * R;
   int rc;
   {
     const long long n_pairs = (long long)B * 3 * R * R / 2;
-    launch_k(fft_z_forward_kernel<LOGR>, dim3((unsigned)ceil_div_ll(n_pairs, LINES)), dim3(FFT_THREADS),
-             tw_bytes + LINES * line_bytes, st, (const float *)raster, spec, n_pairs, LINES, Hp);
+    const size_t smem = tw_bytes + LINES * line_bytes + 16 + 2 * (size_t)LINES * 2 * R * sizeof(float);
+    if ((rc = opt_in_smem<fft_z_forward_kernel<LOGR, LINES>>(smem))) return rc;
+    launch_k(fft_z_forward_kernel<LOGR, LINES>, dim3(persistent_grid(ceil_div_ll(n_pairs, LINES), smem)), dim3(FFT_THREADS), smem,
+             st, (const float *)raster, spec, n_pairs, Hp);
     if ((rc = after_launch())) return rc;
   }
+  const int kca = ceil_div(H, KZA);
+  const size_t smem_axis = tw_bytes + KZA * line_bytes + 16 + 2 * (size_t)R * KZA * sizeof(float2);
   // Y pass over the three normal channels: line set (b*3+c, x), element stride Hp
-  launch_k(fft_axis_kernel<LOGR, false, KZA>, dim3(B * 3 * R, ceil_div(H, KZA)), dim3(FFT_THREADS), tw_bytes + KZA * line_bytes,
-           st, spec, R, hvol, plane, (long long)Hp, H);
+  if ((rc = opt_in_smem<fft_axis_kernel<LOGR, false, KZA>>(smem_axis))) return rc;
+  launch_k(fft_axis_kernel<LOGR, false, KZA>, dim3(persistent_grid((long long)B * 3 * R * kca, smem_axis)), dim3(FFT_THREADS),
+           smem_axis, st, spec, B * 3 * R, R, hvol, plane, (long long)Hp, H, Hp);
   if ((rc = after_launch())) return rc;
-  if ((rc = opt_in_smem(solve_x_kernel<LOGR, KZS>, tw_bytes + 3 * KZS * line_bytes))) return rc;
-  launch_k(solve_x_kernel<LOGR, KZS>, dim3(R * B, ceil_div(H, KZS)), dim3(FFT_THREADS), tw_bytes + 3 * KZS * line_bytes, st,
-           (const float2 *)spec, pot, H, Hp, sig);
-  if ((rc = after_launch())) return rc;
-  launch_k(fft_axis_kernel<LOGR, true, KZA>, dim3(B * R, ceil_div(H, KZA)), dim3(FFT_THREADS), tw_bytes + KZA * line_bytes, st,
-           pot, R, hvol, plane, (long long)Hp, H);
+  {
+    const size_t smem = tw_bytes + 3 * KZS * line_bytes + 16 + 2 * (size_t)3 * R * KZS * sizeof(float2);
+    if ((rc = opt_in_smem<solve_x_kernel<LOGR, KZS>>(smem))) return rc;
+    launch_k(solve_x_kernel<LOGR, KZS>, dim3(persistent_grid((long long)B * R * ceil_div(H, KZS), smem)), dim3(FFT_THREADS), smem,
+             st, (const float2 *)spec, pot, B, H, Hp, sig);
+    if ((rc = after_launch())) return rc;
+  }
+  if ((rc = opt_in_smem<fft_axis_kernel<LOGR, true, KZA>>(smem_axis))) return rc;
+  launch_k(fft_axis_kernel<LOGR, true, KZA>, dim3(persistent_grid((long long)B * R * kca, smem_axis)), dim3(FFT_THREADS),
+           smem_axis, st, pot, B * R, R, hvol, plane, (long long)Hp, H, Hp);
   if ((rc = after_launch())) return rc;
   {
     const long long n_pairs = (long long)B * R * R / 2;
     const float norm = 1.0f / ((float)R * (float)R * (float)R);
-    launch_k(fft_z_inverse_kernel<LOGR>, dim3((unsigned)ceil_div_ll(n_pairs, LINES)), dim3(FFT_THREADS),
-             tw_bytes + LINES * line_bytes, st, (const float2 *)pot, phi, n_pairs, LINES, norm, Hp);
+    const size_t smem = tw_bytes + LINES * line_bytes + 16 + 2 * (size_t)LINES * 2 * Hp * sizeof(float2);
+    if ((rc = opt_in_smem<fft_z_inverse_kernel<LOGR, LINES>>(smem))) return rc;
+    launch_k(fft_z_inverse_kernel<LOGR, LINES>, dim3(persistent_grid(ceil_div_ll(n_pairs, LINES), smem)), dim3(FFT_THREADS), smem,
+             st, (const float2 *)pot, phi, n_pairs, norm, Hp);
     if ((rc = after_launch())) return rc;
   }
   return SLIDE_OK;

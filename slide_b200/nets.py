@@ -156,7 +156,12 @@ class _Grouped(object):
         # points) PAIR is cheap, and at >= 32768 pair rows factoring wins for every module of both denoisers (B200, batch
         # 256: position step 757 -> 710 us, feature step 1575 -> 1525 us); at batch 32 it loses (425 -> 445 us)
         small_src = self.feats.R <= 64 and self.B * self.R >= 32768
-        self.factored = (mode == "1") or (mode == "auto" and (self.Ctot * ntot >= FACTOR_MIN_WORK or small_src))
+        # (round 2, after the warp kNN / PAIR work) large gather sources -- autoencoder and refinement levels, 256..4096
+        # source points -- also gain from factoring every module: encode + decode of 512 clouds 218.0 -> 213.1 ms, the SAP
+        # refinement network 10.46 -> 9.77 ms per 32 clouds (its last propagation module otherwise runs a GROUP record
+        # and three GEMMs over 1 M materialised pair rows)
+        large_src = self.feats.R > 64
+        self.factored = (mode == "1") or (mode == "auto" and (self.Ctot * ntot >= FACTOR_MIN_WORK or small_src or large_src))
         if not self.factored:
             self._materialise()
             return
