@@ -192,6 +192,7 @@ def eps_parity(sampler, seed):
     for backend in ("auto", "simt"):
         sampler.prog.set_gemm_backend(backend)
         sampler.x_view().copy_(x)
+        sampler.refresh_geometry()
         sampler.prog.set_step(sampler.T // 2)
         sampler.prog.run(first, count)
         torch.cuda.synchronize()

@@ -114,7 +114,7 @@ def fast_position_schedule(method, length, schedule, kappa, dcfg):
 # builders
 # ---------------------------------------------------------------------------------------------------
 def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0, with_noise=True,
-               local_resampling=False, ts_values=None, resident=None):
+               local_resampling=False, ts_values=None, resident=None, frozen_xyz=False):
     """One program = setup segment + step segment (+ forward-only segment) for a DDPM denoiser.
 
     mode 0: position sampler (util.sampling), mode 1: latent sampler (denoising_step), mode 2: FastDPM sampler
@@ -124,6 +124,9 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
     local_resampling (latent sampler only, diffusion.py:76-79): adds the handles x0c [B*n, C] (complete x0) and
     mask [B*n, 1] (1 = re-sample this point's features); with an all-ones mask the update equals the plain one.
     Handles: x, eps, labels, noise [T*B*n, C], ts_table, class_emb.
+    frozen_xyz (needs keep_cols >= 3): the coordinates of x never change during a chain (keypoint-conditional sampling,
+    diffusion.py:76-95 only updates the feature columns), so the neighbour searches of every module are taken out of the
+    step into a segment "geometry" that the caller runs once per chain, after x's coordinates are in place.
     resident: None, or dict(cluster=2|4, precise=bool): also compile the "step" and "forward" ranges into
     sample-resident plans (slide_b200/resident.py; one kernel per step instead of one per record) -> h["resident_plans"]
     (a list, empty when the network does not fit the resident kernel); Program.set_resident installs them.
@@ -140,7 +143,9 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
     P = nets.Params(sd)
     b.begin_segment("step")
     b.step_begin()
-    net = nets.lower_cloud_net(b, P, cfg, X, n_points, "net", T=T, labels=labels, factor_group=bool(resident))
+    assert not frozen_xyz or keep_cols >= 3
+    net = nets.lower_cloud_net(b, P, cfg, X, n_points, "net", T=T, labels=labels, factor_group=bool(resident),
+                               defer_geometry=frozen_xyz)
     fwd_count = len(b.ops) - b._seg_open[1]
     b.ddpm_update(mode, X, net["out"], noise, table_off, col0=keep_cols, clamp=clamp, x0c=x0c, mask=mask,
                   note="ddpm_update")
@@ -150,6 +155,10 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
     b.begin_segment("setup")
     net["emit_setup"]()
     b.end_segment()
+    if frozen_xyz:
+        b.begin_segment("geometry")
+        net["emit_geometry"]()
+        b.end_segment()
     h = dict(x=X, eps=net["out"], labels=labels, noise=noise, T=T, C=C, n_points=n_points)
     if local_resampling:
         h.update(x0c=x0c, mask=mask)

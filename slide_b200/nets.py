@@ -85,11 +85,20 @@ class _Ctx(object):
         self.cond2_src = cond2_src  # Tensor [B, second_condition_dim] or None
         self.inline = inline      # True: condition projections depend on run-time data -> emit them in place
         self.setup = []           # deferred setup GEMMs (emitted into the setup segment)
+        self.geom = None          # list: kNN records deferred into a per-chain "geometry" segment (frozen coordinates)
         act = cfg.get("activation", "relu")
         if act != "relu":
             raise NotImplementedError("activation %r (shipped configs use relu)" % act)
         if cfg["bn_first"] or not cfg.get("bn", True) or not cfg["res_connect"]:
             raise NotImplementedError("bn_first / bn=False / res_connect=False are not lowered")
+
+    def knn(self, q, ref, K, idx, d2=None, note=""):
+        """Neighbour search of a module.  With frozen coordinates (keypoint-conditional sampling: the xyz columns of x
+        never change during a chain) the record is deferred: the caller emits it once per chain instead of every step."""
+        if self.geom is None:
+            self.b.knn(q, ref, K, idx, d2=d2, note=note)
+        else:
+            self.geom.append(lambda: self.b.knn(q, ref, K, idx, d2=d2, note=note))
 
     def project(self, **g):
         """A per-sample / per-timestep projection feeding an additive vector."""
@@ -370,6 +379,8 @@ def _lower_sa(ctx, P, xyz, feats, npoint, nsample, name):
         new_xyz, q_feat, npnt = xyz, feats, N
     else:
         npnt = npoint
+        if ctx.geom is not None:
+            raise NotImplementedError("frozen-coordinate geometry with a down-sampling level (FPS moves with the features' order)")
         pick = b.tensor(name + ".fps", 1, npnt, B=B, dtype="i32")
         b.fps(0, xyz, npnt, pick, note=name + ".fps")
         new_xyz = b.tensor(name + ".new_xyz", npnt, 3, B=B)
@@ -378,7 +389,7 @@ def _lower_sa(ctx, P, xyz, feats, npoint, nsample, name):
         b.gather_rows(feats, pick, npnt, q_feat, note=name + ".gather_feat")
     K = min(nsample, N)
     idx = b.tensor(name + ".idx", npnt, K, B=B, dtype="i32")
-    b.knn(new_xyz, xyz, K, idx, note=name + ".knn")
+    ctx.knn(new_xyz, xyz, K, idx, note=name + ".knn")
     inc_abs, inc_ctr = cfg["include_abs_coordinate"], cfg.get("include_center_coordinate", False)
     assert cfg["model.use_xyz"]
     Pa = P.sub("attention_modules.0")
@@ -398,7 +409,7 @@ def _lower_fp(ctx, P, unknown, known, unknow_feats, known_feats, K, name, out=No
     n, B = unknown.R, unknown.B
     idx = b.tensor(name + ".idx", n, K, B=B, dtype="i32")
     d2 = b.tensor(name + ".d2", n, K, B=B)
-    b.knn(unknown, known, K, idx, d2=d2, note=name + ".knn")
+    ctx.knn(unknown, known, K, idx, d2=d2, note=name + ".knn")
     Pa = P.sub("attention_module")
     G = _Grouped(ctx, 1, known_feats, known, unknown, idx, K, name, d2=d2)
     G.plan([P.sub("mlp1.first_mlp.0"), P.sub("mlp1.res_connect"), Pa.sub("grouped_feat_conv")])
@@ -424,7 +435,7 @@ def _lower_feature_map(ctx, P, xyz, feats, new_xyz, q_feat, nsample, name, out):
     npnt, B = new_xyz.R, new_xyz.B
     K = min(nsample, xyz.R)
     idx = b.tensor(name + ".idx", npnt, K, B=B, dtype="i32")
-    b.knn(new_xyz, xyz, K, idx, note=name + ".knn")
+    ctx.knn(new_xyz, xyz, K, idx, note=name + ".knn")
     inc_abs, inc_ctr = cfg["include_abs_coordinate"], cfg.get("include_center_coordinate", False)
     Pa = P.sub("attention_module")
     G = _Grouped(ctx, 0, feats, xyz, new_xyz, idx, K, name, inc_abs=inc_abs, inc_ctr=inc_ctr)
@@ -459,7 +470,7 @@ def t_embedding_source(b, P, cfg, T, name):
     return ts, h2, emit
 
 
-def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None, factor_group=None):
+def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None, factor_group=None, defer_geometry=False):
     """Lower PointNet2CloudCondition (no condition cloud).
 
     X: arena tensor [B*n_points, 3 + in_fea_dim] (xyz first).  T: number of timesteps (DDPM denoisers) or None.
@@ -499,6 +510,8 @@ def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None,
         setup_pre.append(emit_c)
     ctx = _Ctx(b, cfg, t_src, cond_src)
     ctx.factor_group = factor_group
+    if defer_geometry:
+        ctx.geom = []
 
     Fin = X.C - 3
     assert X.R == n_points
@@ -507,7 +520,10 @@ def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None,
         feats = b.tensor(name + ".feat0", n_points, Fin + 3, B=B)
         if Fin > 0:
             b.copy_cols(X.cols(3, Fin), feats.cols(0, Fin), note=name + ".in_feat")
-        b.copy_cols(X.cols(0, 3), feats.cols(Fin, 3), note=name + ".in_xyz")
+        if ctx.geom is not None:  # frozen coordinates: the attached position columns are written once per chain
+            ctx.geom.append(lambda: b.copy_cols(X.cols(0, 3), feats.cols(Fin, 3), note=name + ".in_xyz"))
+        else:
+            b.copy_cols(X.cols(0, 3), feats.cols(Fin, 3), note=name + ".in_xyz")
     else:
         assert Fin > 0
         feats = X.cols(3, Fin)
@@ -557,7 +573,10 @@ def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None,
             fn()
         for g in ctx.setup:
             b.gemm(g["A"], g["W"], g["out"], bias=g["bias"], note=g["note"])
-    return dict(out=result, emit_setup=emit_setup, inputs=inputs, levels=(l_xyz, l_feat))
+    def emit_geometry():
+        for emit in ctx.geom or []:
+            emit()
+    return dict(out=result, emit_setup=emit_setup, emit_geometry=emit_geometry, inputs=inputs, levels=(l_xyz, l_feat))
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -24,13 +24,17 @@ class DDPMSampler(object):
     """One denoiser + its ancestral sampling loop, resident on one GPU."""
 
     def __init__(self, pointnet_cfg, sd, B, table, mode, keep_cols, T, device, graph_steps=20, backend="auto",
-                 local_resampling=False, clamp=-1.0, ts_values=None, resident=None):
+                 local_resampling=False, clamp=-1.0, ts_values=None, resident=None, frozen_xyz=None):
         """resident: None, or dict(cluster=2|4, precise=bool): run every step as ONE sample-resident kernel
-        (slide_b200/resident.py) when the network fits it; otherwise (and with backend "simt") one kernel per record."""
+        (slide_b200/resident.py) when the network fits it; otherwise (and with backend "simt") one kernel per record.
+        frozen_xyz: None = automatic (the keypoint-conditional feature DDPM: the update leaves the coordinates alone) --
+        the modules' neighbour searches run once per chain (refresh_geometry) instead of once per step."""
         self.B, self.T, self.mode = B, T, mode
+        self.frozen_xyz = (mode == 1 and keep_cols >= 3) if frozen_xyz is None else bool(frozen_xyz)
         self.builder, self.h = engine.build_ddpm(pointnet_cfg, sd, B, T, table, mode, keep_cols=keep_cols, clamp=clamp,
                                                  local_resampling=local_resampling, ts_values=ts_values,
-                                                 resident=resident if backend == "auto" else None)
+                                                 resident=resident if backend == "auto" else None,
+                                                 frozen_xyz=self.frozen_xyz)
         self.local_resampling = local_resampling
         self.prog = Program(self.builder, device)
         self.prog.set_gemm_backend(backend)
@@ -63,9 +67,16 @@ class DDPMSampler(object):
     def x_view(self):
         return self.prog.view(self.h["x"])[:, :self.C]
 
+    def refresh_geometry(self):
+        """Frozen coordinates: (re)compute the neighbour indices of every module from x's current coordinates.  Call after
+        writing x and before running the forward / step segments by hand; run() does it itself."""
+        if self.frozen_xyz:
+            self.prog.run_segment("geometry")
+
     def run(self, steps=None):
         """Run the loop from t = T-1 down (x and noise must be in place).  steps=None -> all T."""
         steps = self.T if steps is None else steps
+        self.refresh_geometry()
         first, count = self.builder.segments["step"]
         self.prog.set_step(self.T)
         if not self._captured:

@@ -100,3 +100,32 @@ def test_encode_records_match_reference(sample, golden, pipeline_cfg):
     got = m.download(h["out"]).numpy().reshape(B, 16, 48)
     want = golden["enc_sample" if sample else "enc_mode"]
     assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max())
+
+
+def test_frozen_coordinates_hoist_the_neighbour_search(golden, pipeline_cfg):
+    """engine.build_ddpm(frozen_xyz=True): the kNN records leave the step for a per-chain "geometry" segment; the chain
+    is unchanged bit for bit as long as the coordinates really do not move (keep_cols = 3)."""
+    B, T, steps = 2, 1000, 3
+    pc = pipeline_cfg["latent_ddpm"]["pointnet_config"]
+    table = engine.latent_table(pipeline_cfg["latent_ddpm"]["standard_diffusion_config"])
+    sd = common.state_dict("lat")
+    g = torch.Generator().manual_seed(9)
+    x0 = torch.randn(B * 16, 3 + pc["in_fea_dim"], generator=g)
+    out = []
+    for frozen in (False, True):
+        b, h = engine.build_ddpm(pc, sd, B, T, table, 1, keep_cols=3, with_noise=True, frozen_xyz=frozen)
+        kinds = [ir_exec.KIND_NAME[b.ops[i][0]] for i in range(*[(f, f + c) for f, c in [b.segments["step"]]][0])]
+        assert ("SLIDE_OP_KNN" in kinds) == (not frozen)
+        m = ir_exec.Machine(b)
+        common.init_machine(m, h, golden["label"])
+        m.run_segment("setup")
+        m.view(h["noise"])[...] = torch.randn(h["noise"].rows, h["C"], generator=torch.Generator().manual_seed(4)).numpy()
+        m.upload(h["x"], x0)
+        if frozen:
+            assert b.segments["geometry"][1] == 5  # four neighbour searches + the attached coordinate columns
+            m.run_segment("geometry")
+        m.set_step(T)
+        for _ in range(steps):
+            m.run_segment("step")
+        out.append(np.array(m.download(h["x"])))
+    assert np.array_equal(out[0], out[1])
