@@ -371,12 +371,13 @@ def _attention_tail(ctx, P, keys, H, npnt, K, out, name):
     return out
 
 
-def _lower_sa(ctx, P, xyz, feats, npoint, nsample, name):
-    """-> (new_xyz [B*np,3], features [B*np,Cout])."""
-    b, cfg = ctx.b, ctx.cfg
+def _sa_geometry(ctx, xyz, npoint, nsample, name):
+    """The coordinate-only part of a set-abstraction level: FPS pick, centres, neighbour indices."""
+    b = ctx.b
     N, B = xyz.R, xyz.B
+    pick = None
     if N <= npoint:
-        new_xyz, q_feat, npnt = xyz, feats, N
+        new_xyz, npnt = xyz, N
     else:
         npnt = npoint
         if ctx.geom is not None:
@@ -385,11 +386,25 @@ def _lower_sa(ctx, P, xyz, feats, npoint, nsample, name):
         b.fps(0, xyz, npnt, pick, note=name + ".fps")
         new_xyz = b.tensor(name + ".new_xyz", npnt, 3, B=B)
         b.gather_rows(xyz, pick, npnt, new_xyz, note=name + ".gather_xyz")
-        q_feat = b.tensor(name + ".qfeat", npnt, feats.C, B=B)
-        b.gather_rows(feats, pick, npnt, q_feat, note=name + ".gather_feat")
     K = min(nsample, N)
     idx = b.tensor(name + ".idx", npnt, K, B=B, dtype="i32")
     ctx.knn(new_xyz, xyz, K, idx, note=name + ".knn")
+    return dict(pick=pick, new_xyz=new_xyz, npnt=npnt, K=K, idx=idx)
+
+
+def _lower_sa(ctx, P, xyz, feats, npoint, nsample, name, geom=None, side_extra=None):
+    """-> (new_xyz [B*np,3], features [B*np,Cout]).  geom: this level's _sa_geometry if it was emitted earlier (hoisted
+    onto an earlier module's side branch); side_extra(new_xyz): extra records for this module's side branch."""
+    b, cfg = ctx.b, ctx.cfg
+    B = xyz.B
+    if geom is None:
+        geom = _sa_geometry(ctx, xyz, npoint, nsample, name)
+    new_xyz, npnt, K, idx = geom["new_xyz"], geom["npnt"], geom["K"], geom["idx"]
+    if geom["pick"] is None:
+        q_feat = feats
+    else:
+        q_feat = b.tensor(name + ".qfeat", npnt, feats.C, B=B)
+        b.gather_rows(feats, geom["pick"], npnt, q_feat, note=name + ".gather_feat")
     inc_abs, inc_ctr = cfg["include_abs_coordinate"], cfg.get("include_center_coordinate", False)
     assert cfg["model.use_xyz"]
     Pa = P.sub("attention_modules.0")
@@ -397,6 +412,8 @@ def _lower_sa(ctx, P, xyz, feats, npoint, nsample, name):
     G.plan([P.sub("mlps.0.first_mlp.0"), P.sub("mlps.0.res_connect"), Pa.sub("grouped_feat_conv")])
     with b.side_branch():
         keys = _attention_keys(ctx, Pa, q_feat, G, npnt, K, name + ".att")
+        if side_extra is not None:
+            side_extra(new_xyz)
     H = _lower_mlp(ctx, P.sub("mlps.0"), G, npnt * K, name + ".mlp", use_t=True, use_cond=True)
     b.join(name + ".join")
     out = b.tensor(name + ".out", npnt, H.C, B=B)
@@ -404,12 +421,18 @@ def _lower_sa(ctx, P, xyz, feats, npoint, nsample, name):
     return new_xyz, out
 
 
-def _lower_fp(ctx, P, unknown, known, unknow_feats, known_feats, K, name, out=None, side_extra=None):
+def _fp_geometry(ctx, unknown, known, K, name):
+    b = ctx.b
+    idx = b.tensor(name + ".idx", unknown.R, K, B=unknown.B, dtype="i32")
+    d2 = b.tensor(name + ".d2", unknown.R, K, B=unknown.B)
+    ctx.knn(unknown, known, K, idx, d2=d2, note=name + ".knn")
+    return idx, d2
+
+
+def _lower_fp(ctx, P, unknown, known, unknow_feats, known_feats, K, name, out=None, side_extra=None, geom=None):
     b = ctx.b
     n, B = unknown.R, unknown.B
-    idx = b.tensor(name + ".idx", n, K, B=B, dtype="i32")
-    d2 = b.tensor(name + ".d2", n, K, B=B)
-    ctx.knn(unknown, known, K, idx, d2=d2, note=name + ".knn")
+    idx, d2 = geom if geom is not None else _fp_geometry(ctx, unknown, known, K, name)
     Pa = P.sub("attention_module")
     G = _Grouped(ctx, 1, known_feats, known, unknown, idx, K, name, d2=d2)
     G.plan([P.sub("mlp1.first_mlp.0"), P.sub("mlp1.res_connect"), Pa.sub("grouped_feat_conv")])
@@ -528,12 +551,26 @@ def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None,
         assert Fin > 0
         feats = X.cols(3, Fin)
     l_xyz, l_feat = [xyz], [feats]
+    n_fp = len(arch["decoder_feature_dim"]) - 1
+    # Down-sampling networks (refinement / encoder clouds): everything that depends on coordinates only -- the FPS picks,
+    # centres and neighbour searches of levels >= 1 and the propagation modules' searches -- is emitted on the side branch
+    # of level 0, underneath its pair-level GEMMs, instead of serially in front of each module (FPS is one CTA per cloud).
+    sa_geoms, fp_geoms = {}, {}
+    hoist = ctx.geom is None and n_points > arch["npoint"][0] and os.environ.get("SLIDE_HOIST_GEOMETRY", "1") != "0"
+
+    def hoisted(new_xyz0):
+        xs = [xyz, new_xyz0]
+        for i in range(1, len(arch["npoint"])):
+            sa_geoms[i] = _sa_geometry(ctx, xs[i], arch["npoint"][i], arch["nsample"][i], "%s.SA%d" % (name, i))
+            xs.append(sa_geoms[i]["new_xyz"])
+        for i in range(-1, -(n_fp + 1), -1):
+            fp_geoms[i] = _fp_geometry(ctx, xs[i - 1], xs[i], arch.get("K", 3), "%s.FP%d" % (name, n_fp + i))
+
     for i, (npoint, nsample) in enumerate(zip(arch["npoint"], arch["nsample"])):
         nx, nf = _lower_sa(ctx, P.sub("SA_modules.%d" % i), l_xyz[i], l_feat[i], npoint, nsample,
-                           "%s.SA%d" % (name, i))
+                           "%s.SA%d" % (name, i), geom=sa_geoms.get(i), side_extra=hoisted if (hoist and i == 0) else None)
         l_xyz.append(nx)
         l_feat.append(nf)
-    n_fp = len(arch["decoder_feature_dim"]) - 1
     transform = cfg.get("transform_output", True)
     head_in = None
     for i in range(-1, -(n_fp + 1), -1):
@@ -549,7 +586,8 @@ def lower_cloud_net(b, P, cfg, X, n_points, name, T=None, labels=None, out=None,
         if head_in is not None and i == -n_fp:  # the head's coordinate columns: copied under the last module's GEMMs
             extra = lambda: b.copy_cols(xyz, head_in.cols(arch["decoder_feature_dim"][0], 3), note=name + ".head_xyz")  # noqa: E731
         l_feat[i - 1] = _lower_fp(ctx, P.sub("FP_modules.%d" % (n_fp + i)), l_xyz[i - 1], l_xyz[i], l_feat[i - 1],
-                                  l_feat[i], arch.get("K", 3), "%s.FP%d" % (name, n_fp + i), out=dst, side_extra=extra)
+                                  l_feat[i], arch.get("K", 3), "%s.FP%d" % (name, n_fp + i), out=dst, side_extra=extra,
+                                  geom=fp_geoms.get(i))
     result = l_feat[0]
     if transform:
         d0 = arch["decoder_feature_dim"][0]
@@ -634,8 +672,18 @@ def lower_encoder_net(b, P, cfg, X, n_points, name, labels):
         g = _lower_pnet2stage(ctx, P.sub("global_pnet"), X, n_points, name + ".pnet")
         ctx.cond_src, ctx.cond2_src = g, class_src
     l_xyz, l_feat = [xyz], [feats]
+    sa_geoms = {}
+    hoist = n_points > arch["npoint"][0] and os.environ.get("SLIDE_HOIST_GEOMETRY", "1") != "0"
+
+    def hoisted(new_xyz0):  # levels >= 1: FPS / centres / neighbour searches under level 0's GEMMs (see lower_cloud_net)
+        cur = new_xyz0
+        for i in range(1, len(arch["npoint"])):
+            sa_geoms[i] = _sa_geometry(ctx, cur, arch["npoint"][i], arch["nsample"][i], "%s.SA%d" % (name, i))
+            cur = sa_geoms[i]["new_xyz"]
+
     for i, (npoint, nsample) in enumerate(zip(arch["npoint"], arch["nsample"])):
-        nx, nf = _lower_sa(ctx, P.sub("SA_modules.%d" % i), l_xyz[i], l_feat[i], npoint, nsample, "%s.SA%d" % (name, i))
+        nx, nf = _lower_sa(ctx, P.sub("SA_modules.%d" % i), l_xyz[i], l_feat[i], npoint, nsample, "%s.SA%d" % (name, i),
+                           geom=sa_geoms.get(i), side_extra=hoisted if (hoist and i == 0) else None)
         l_xyz.append(nx)
         l_feat.append(nf)
     tables = [(table, emb_w)] if class_src is not None else []
