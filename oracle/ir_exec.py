@@ -280,9 +280,12 @@ class Machine(object):
         xyz = self.A(g("PR_XYZ"), B * Ns, g("PR_LDX"), 3).reshape(B, Ns, 3)
         ctr = self.A(g("PR_CTR"), B * npnt, g("PR_LDCTR"), 3).reshape(B, npnt, 3)
         bi = np.arange(B)[:, None, None]
-        wx = self.W(g("PR_WX_W"), N, 3)
         wc = self.W(g("PR_WC_W"), N, 3)
-        out = U[bi, idx] + xyz[bi, idx] @ wx.T + (ctr @ wc.T)[:, :, None, :]
+        if g("PR_WX_W") >= 0:
+            wx = self.W(g("PR_WX_W"), N, 3)
+            out = U[bi, idx] + xyz[bi, idx] @ wx.T + (ctr @ wc.T)[:, :, None, :]
+        else:  # the neighbour-coordinate term is already part of U
+            out = U[bi, idx] + (ctr @ wc.T)[:, :, None, :]
         if g("PR_BIAS_W") >= 0:
             out = out + self.Wv(g("PR_BIAS_W"), N)
         if g("PR_D2") >= 0:

@@ -464,7 +464,11 @@ struct PairArgs {
 // RB = rows in flight per thread.  The neighbour indices (and squared distances) of a point are fetched ONCE as a
 // lane-parallel row and broadcast with shuffles, so a batch of RB rows costs one memory latency (the U gathers,
 // coordinate and residual loads of the whole batch are independent) instead of index -> gather chains per row.
-template <int RB, bool HAS_RES>
+// LITE: the caller folded the neighbour-coordinate term into U (U'[j] = f_j W_f^T + x_j wx^T, one K = 3 GEMM over the source
+// points; a.wx == nullptr), so a row is U'[idx] + (per-point centre term): no coordinate loads, 12 fewer FMAs and 36 fewer
+// live registers per thread -- the large-source PAIR records of the autoencoder / refinement levels are bound by exactly that
+// (127 registers -> 15 warps per SM, ncu: 48 % SM busy at 0.3-2.5 TB/s).
+template <int RB, bool HAS_RES, bool LITE>
 __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
   pdl_wait();
   pdl_trigger();
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
       const int nn = on[u] ? n + u : 0;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        wx[u][d] = __ldg(a.wx + nn * 3 + d);
+        wx[u][d] = LITE ? 0.f : __ldg(a.wx + nn * 3 + d);
         wc[u][d] = __ldg(a.wc + nn * 3 + d);
       }
       bias[u] = a.bias ? __ldg(a.bias + nn) : 0.f;
@@ -546,10 +550,14 @@ __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
             const int j = __shfl_sync(0xffffffffu, jrow, (k0 + b) & 31);
             dk[b] = __shfl_sync(0xffffffffu, drow, (k0 + b) & 31);
             const size_t row = prow + kc + k0 + b;
-            const float *x = a.xyz + ((size_t)s * a.nsrc + j) * a.ldx;
-            xs[b][0] = __ldg(x);
-            xs[b][1] = __ldg(x + 1);
-            xs[b][2] = __ldg(x + 2);
+            if (!LITE) {
+              const float *x = a.xyz + ((size_t)s * a.nsrc + j) * a.ldx;
+              xs[b][0] = __ldg(x);
+              xs[b][1] = __ldg(x + 1);
+              xs[b][2] = __ldg(x + 2);
+            } else {
+              xs[b][0] = xs[b][1] = xs[b][2] = 0.f;
+            }
             uu[b] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (any) uu[b] = __ldg(reinterpret_cast<const float4 *>(a.U + ((size_t)s * a.nsrc + j) * a.ldu + n));
             r4[b] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -575,7 +583,8 @@ __global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
             if (a.d2) w = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(dk[b], 1e-8f)), inv_sum);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              float t = fmaf(xs[b][2], wx[u][2], fmaf(xs[b][1], wx[u][1], fmaf(xs[b][0], wx[u][0], v[u]))) + vterm[u];
+              float t = LITE ? v[u] + vterm[u]
+                             : fmaf(xs[b][2], wx[u][2], fmaf(xs[b][1], wx[u][1], fmaf(xs[b][0], wx[u][0], v[u]))) + vterm[u];
               if (a.d2) t = fmaf(w, ww[u], fmaf(dk[b], wd[u], t));
               if (HAS_RES) {
                 float r = fmaf(rr[u], rsc[u], rsh[u]);
@@ -1194,7 +1203,8 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
         g_pair_tuning_loaded = true;
       }
       // small gather source (the denoisers: the sample's own 16 points): stage it in shared memory
-      if (g_pair_smem && a.nsrc <= PS_MAX_SRC && a.N <= 4 * PS_THREADS) {
+      if (!a.wc) return SLIDE_ERR_INVALID;
+      if (a.wx && g_pair_smem && a.nsrc <= PS_MAX_SRC && a.N <= 4 * PS_THREADS) {
         const int CT = ceil_div(a.N, 4), RG = PS_THREADS / CT, ldn = 4 * CT;
         int pbs = a.np < g_pair_pb ? a.np : g_pair_pb;  // points per CTA (8: 128 rows at K = 16; A/B on B200, batch 256, position / feature step: 2 -> 829 / 1650 us, 4 -> 710 / 1525, 8 -> 658 / 1488, 16 -> 654 / 1491); fewer when the grid would be under 2 CTAs per SM
         while (pbs > 1 && (long long)B * ceil_div(a.np, pbs) < g_pair_smem_min_ctas) pbs = (pbs + 1) / 2;
@@ -1217,10 +1227,16 @@ int run_op(slide_program *p, const slide_op &op, cudaStream_t st) {
       const int cols4 = ceil_div(a.N, 4);
       const int threads = cols4 >= 256 ? 256 : ((cols4 + 31) / 32) * 32;
       dim3 grid(ceil_div(a.np, pb), B);
-      if (a.res)
-        launch_k(pair_kernel<4, true>, grid, threads, 0, st, a);
-      else
-        launch_k(pair_kernel<8, false>, grid, threads, 0, st, a);
+      if (!a.wx) {  // coordinate term already inside U
+        if (a.res)
+          launch_k(pair_kernel<4, true, true>, grid, threads, 0, st, a);
+        else
+          launch_k(pair_kernel<8, false, true>, grid, threads, 0, st, a);
+      } else if (a.res) {
+        launch_k(pair_kernel<4, true, false>, grid, threads, 0, st, a);
+      } else {
+        launch_k(pair_kernel<8, false, false>, grid, threads, 0, st, a);
+      }
       return after_launch();
     }
     case SLIDE_OP_COLMAX: {

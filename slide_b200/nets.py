@@ -125,6 +125,7 @@ class _Grouped(object):
         self.C = feats.C
         self.Ctot = self.C + (11 if mode == 1 else 3 + 3 * int(inc_abs) + 3 * int(inc_ctr))
         self.factored = None  # decided in plan(): depends on how wide the convs reading the group are
+        self.lite = False
         self.G = None
         self.U = None
         self.slices = {}
@@ -181,7 +182,8 @@ class _Grouped(object):
             w = w.reshape(w.shape[0], -1)
             assert w.shape[1] == self.Ctot, (w.shape, self.Ctot)
             wf, wx, wc, wd, ww = self._split(w)
-            self.slices[Pc.prefix] = dict(off=off, N=w.shape[0], wx=b.weight(np.ascontiguousarray(wx)),
+            self.slices[Pc.prefix] = dict(off=off, N=w.shape[0], wx_value=np.ascontiguousarray(wx),
+                                          wx=b.weight(np.ascontiguousarray(wx)),
                                           wc=b.weight(np.ascontiguousarray(wc)),
                                           wd=b.weight(wd) if wd is not None else -1,
                                           ww=b.weight(ww) if ww is not None else -1,
@@ -198,6 +200,16 @@ class _Grouped(object):
             W = W + b.weight_matrix_tc(wcat)
         self.U = b.tensor(self.name + ".U", self.feats.R, off, B=self.B)
         b.gemm(self.feats, W, self.U, note=self.name + ".U")
+        # Large gather sources: fold the neighbour-coordinate term x_j wx^T into U as well (one K = 3 fp32 GEMM over the
+        # source points, in place), so that the PAIR records neither load coordinates nor carry wx -- see pair_kernel<LITE>.
+        self.lite = self.feats.R > 64 and os.environ.get("SLIDE_PAIR_LITE", "1") != "0"
+        if self.lite:
+            wxcat = np.zeros((off, 3), dtype=np.float32)
+            for Pc in convs:
+                sl = self.slices[Pc.prefix]
+                wxcat[sl["off"]:sl["off"] + sl["N"]] = sl["wx_value"]
+            xoff, xld = b.weight_matrix(wxcat)
+            b.gemm(self.xyz, (xoff, xld, off, 3), self.U, resid=self.U, note=self.name + ".Ux")
 
     def linear(self, Pc, out, act=None, resid=None, xfr=NO_XF, stats=None, st_choff=0, note=""):
         b = self.b
@@ -207,7 +219,8 @@ class _Grouped(object):
                    note=note)
             return
         sl = self.slices[Pc.prefix]
-        b.pair(self.U.cols(sl["off"], sl["N"]), self.xyz, self.ctr, self.idx, self.K, out, sl["wx"], sl["wc"],
+        b.pair(self.U.cols(sl["off"], sl["N"]), self.xyz, self.ctr, self.idx, self.K, out,
+               -1 if getattr(self, "lite", False) else sl["wx"], sl["wc"],
                bias=sl["bias"], d2=self.d2 if self.mode == 1 else None, wd=sl["wd"], ww=sl["ww"], act=act, resid=resid,
                xfr=xfr, stats=stats, st_choff=st_choff, note=note)
 
