@@ -464,12 +464,15 @@ struct PairArgs {
 // RB = rows in flight per thread.  The neighbour indices (and squared distances) of a point are fetched ONCE as a
 // lane-parallel row and broadcast with shuffles, so a batch of RB rows costs one memory latency (the U gathers,
 // coordinate and residual loads of the whole batch are independent) instead of index -> gather chains per row.
+#ifndef PAIR_MIN_BLOCKS
+#define PAIR_MIN_BLOCKS 1  // A/B knob (register cap of the gather kernel: 1 -> 116-127 registers, 3 -> 80, 4 -> 64 + spills)
+#endif
 // LITE: the caller folded the neighbour-coordinate term into U (U'[j] = f_j W_f^T + x_j wx^T, one K = 3 GEMM over the source
 // points; a.wx == nullptr), so a row is U'[idx] + (per-point centre term): no coordinate loads, 12 fewer FMAs and 36 fewer
 // live registers per thread -- the large-source PAIR records of the autoencoder / refinement levels are bound by exactly that
 // (127 registers -> 15 warps per SM, ncu: 48 % SM busy at 0.3-2.5 TB/s).
 template <int RB, bool HAS_RES, bool LITE>
-__global__ void __launch_bounds__(256) pair_kernel(PairArgs a) {
+__global__ void __launch_bounds__(256, PAIR_MIN_BLOCKS) pair_kernel(PairArgs a) {
   pdl_wait();
   pdl_trigger();
   // thread = 4 consecutive columns (128-bit U gathers / residual loads / stores); the per-row index, coordinate and
