@@ -457,12 +457,24 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_axis_kernel(float2 *__restric
   cp_async_wait<0>();
 }
 
+// spec_gaussian_filter (dpsr_utils/utils.py:65-71) as a table over |k|^2 = 0 .. 3 (R/2)^2: float32(exp(-0.5 (2 sig |k| / R)^2)),
+// evaluated in float64 like the reference.  12 289 entries at R = 128; keeps the fp64 exp / sqrt out of the solve kernel.
+__global__ void gauss_table_kernel(float *__restrict__ gtab, int n, float sig, int R) {
+  pdl_wait();
+  pdl_trigger();
+  const int k2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k2 >= n) return;
+  const double dis = sqrt((double)k2);
+  const double q = (double)sig * 2.0 * dis / (double)R;
+  gtab[k2] = (float)exp(-0.5 * (q * q));
+}
+
 // ---- X pass + spectral solve + inverse X pass --------------------------------------------------------------------------------
 // spec float2 [B,3,R(x),R(y),Hp] (Z and Y already transformed)  ->  pot float2 [B,R(x),R(y),Hp] (X already inverted)
 //   Phi = sum_d (-i G N_d) w_d / (-(|w|^2) + 1e-6),  w = 2 pi k,  G = exp(-0.5 (2 sig |k| / R)^2),  Phi(0) = 0
 template <int LOGR, int KZT>
 __global__ void __launch_bounds__(FFT_THREADS) solve_x_kernel(const float2 *__restrict__ spec, float2 *__restrict__ pot, int B,
-                                                              int H, int Hp, float sig) {
+                                                              int H, int Hp, const float *__restrict__ gtab) {
   pdl_wait();
   pdl_trigger();
   using G = Geo<LOGR>;
@@ -516,9 +528,7 @@ __global__ void __launch_bounds__(FFT_THREADS) solve_x_kernel(const float2 *__re
       const int k = t >> LOGR, i = t & (R - 1);
       const int fx = i < (R >> 1) ? i : i - R;
       const int fz = kz0 + k;
-      const double dis = sqrt((double)(fx * fx + fy * fy + fz * fz));
-      const double q = (double)sig * 2.0 * dis / (double)R;
-      const float Gf = (float)exp(-0.5 * (q * q));
+      const float Gf = __ldg(gtab + fx * fx + fy * fy + fz * fz);  // the filter depends on |k|^2 only (gauss_table_kernel)
       const float wx = __fmul_rn((float)fx, TWO_PI), wz = __fmul_rn((float)fz, TWO_PI);
       const int pos = G::out_pos(i);
       const float2 nx = s[(0 * nk + k) * G::LS + pos], ny = s[(1 * nk + k) * G::LS + pos], nz = s[(2 * nk + k) * G::LS + pos];
@@ -684,8 +694,10 @@ int log2_exact(int R) {
 int half_pitch(int R) { return (R / 2 + 1 + 7) & ~7; }
 
 struct DpsrLayout {
-  size_t raster, spec, pot, acc, scal, total;
+  size_t raster, spec, pot, acc, scal, gtab, total;
 };
+
+int gauss_table_size(int R) { return 3 * (R / 2) * (R / 2) + 1; }
 
 DpsrLayout layout_of(int B, int R) {
   const size_t vol = (size_t)R * R * R, hvol = (size_t)R * R * half_pitch(R);
@@ -701,6 +713,7 @@ DpsrLayout layout_of(int B, int R) {
   L.pot = take((size_t)B * hvol * sizeof(float2));
   L.acc = take((size_t)B * sizeof(float));
   L.scal = take((size_t)B * sizeof(float2));
+  L.gtab = take((size_t)gauss_table_size(R) * sizeof(float));
   L.total = off;
   return L;
 }
@@ -742,7 +755,7 @@ unsigned persistent_grid(long long n_tiles, size_t smem_bytes) {
 
 // The five transform launches of one batch at R = 2^LOGR.
 template <int LOGR>
-int run_transforms_t(int B, float sig, float *raster, float2 *spec, float2 *pot, float *phi, cudaStream_t st) {
+int run_transforms_t(int B, float sig, float *raster, float2 *spec, float2 *pot, float *phi, float *gtab, cudaStream_t st) {
   using G = Geo<LOGR>;
   constexpr int R = G::R, H = R / 2 + 1;
   constexpr int KZA = R <= 128 ? 16 : 8;  // kz per tile of the axis passes (128 / 64 contiguous bytes per row)
@@ -770,8 +783,10 @@ int run_transforms_t(int B, float sig, float *raster, float2 *spec, float2 *pot,
   {
     const size_t smem = tw_bytes + 3 * KZS * line_bytes + 16 + 2 * (size_t)3 * R * KZS * sizeof(float2);
     if ((rc = opt_in_smem<solve_x_kernel<LOGR, KZS>>(smem))) return rc;
+    launch_k(gauss_table_kernel, dim3(ceil_div(gauss_table_size(R), 256)), dim3(256), 0, st, gtab, gauss_table_size(R), sig, R);
+    if ((rc = after_launch())) return rc;
     launch_k(solve_x_kernel<LOGR, KZS>, dim3(persistent_grid((long long)B * R * ceil_div(H, KZS), smem)), dim3(FFT_THREADS), smem,
-             st, (const float2 *)spec, pot, B, H, Hp, sig);
+             st, (const float2 *)spec, pot, B, H, Hp, (const float *)gtab);
     if ((rc = after_launch())) return rc;
   }
   if ((rc = opt_in_smem<fft_axis_kernel<LOGR, true, KZA>>(smem_axis))) return rc;
@@ -790,14 +805,14 @@ int run_transforms_t(int B, float sig, float *raster, float2 *spec, float2 *pot,
   return SLIDE_OK;
 }
 
-int run_transforms(int logR, int B, float sig, float *raster, float2 *spec, float2 *pot, float *phi, cudaStream_t st) {
+int run_transforms(int logR, int B, float sig, float *raster, float2 *spec, float2 *pot, float *phi, float *gtab, cudaStream_t st) {
   switch (logR) {
-    case 3: return run_transforms_t<3>(B, sig, raster, spec, pot, phi, st);
-    case 4: return run_transforms_t<4>(B, sig, raster, spec, pot, phi, st);
-    case 5: return run_transforms_t<5>(B, sig, raster, spec, pot, phi, st);
-    case 6: return run_transforms_t<6>(B, sig, raster, spec, pot, phi, st);
-    case 7: return run_transforms_t<7>(B, sig, raster, spec, pot, phi, st);
-    case 8: return run_transforms_t<8>(B, sig, raster, spec, pot, phi, st);
+    case 3: return run_transforms_t<3>(B, sig, raster, spec, pot, phi, gtab, st);
+    case 4: return run_transforms_t<4>(B, sig, raster, spec, pot, phi, gtab, st);
+    case 5: return run_transforms_t<5>(B, sig, raster, spec, pot, phi, gtab, st);
+    case 6: return run_transforms_t<6>(B, sig, raster, spec, pot, phi, gtab, st);
+    case 7: return run_transforms_t<7>(B, sig, raster, spec, pot, phi, gtab, st);
+    case 8: return run_transforms_t<8>(B, sig, raster, spec, pot, phi, gtab, st);
   }
   return SLIDE_ERR_UNSUPPORTED;
 }
@@ -857,7 +872,7 @@ int slide_dpsr_forward(const float *V, int ldv, const float *Nrm, int ldn, int B
   launch_k(splat_kernel, dim3(ceil_div(B * n, 128)), dim3(128), 0, st, V, ldv, Nrm, ldn, B, n, R, raster);
   if ((rc = after_launch())) return rc;
 
-  if ((rc = run_transforms(logR, B, sig, raster, spec, pot, phi, st))) return rc;
+  if ((rc = run_transforms(logR, B, sig, raster, spec, pot, phi, (float *)(ws + L.gtab), st))) return rc;
   if (!shift && !scale) return SLIDE_OK;
   if (shift) {
     launch_k(interp_sum_kernel, dim3(ceil_div(n, 256), B), dim3(256), 0, st, (const float *)phi, V, ldv, n, R, acc);
