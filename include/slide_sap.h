@@ -43,6 +43,24 @@ int slide_dpsr_workspace_bytes(int B, int res, size_t *bytes);
 int slide_dpsr_forward(const float *V, int ldv, const float *Nrm, int ldn, int B, int n, int res, float sig, int shift,
                        int scale, float *phi, void *workspace, size_t workspace_bytes, slide_stream_t stream);
 
+/* Iso-surface of an indicator grid: replaces measure.marching_cubes(psr_grid[i], level) in mc_from_psr
+ * (pointnet2/dpsr_utils/utils.py:246-287; scikit-image's Lewiner marching cubes on the CPU).  The level set is the same; the
+ * triangulation is not scikit-image's: cells are split into the six tetrahedra around their main diagonal (marching tetrahedra:
+ * no case table, no ambiguous cases, watertight by construction; vertices on grid / face-diagonal / body-diagonal edges at the
+ * linear crossing).  Output order is deterministic: vertex i = i-th crossing in (node, edge type) order, faces in (cell,
+ * tetrahedron) order, oriented with the normal from phi < level to phi >= level.
+ *   phi f32[res,res,res] (one grid), 2 <= res <= 256.
+ *   slide_mc_count: fills the workspace (slide_mc_workspace_bytes(res) bytes) and writes counts i32[2] = (n_vertices, n_faces)
+ *     -- a DEVICE pointer; read it back to size the outputs;
+ *   slide_mc_emit: verts f32[n_vertices,3] = index coordinates * vertex_scale (mc_from_psr divides by res: pass 1/res),
+ *     normals f32[n_vertices,3] or NULL = normalised numpy-style gradient of phi interpolated along the edge,
+ *     faces i32[n_faces,3]. */
+int slide_mc_workspace_bytes(int res, size_t *bytes);
+int slide_mc_count(const float *phi, int res, float level, void *workspace, size_t workspace_bytes, int *counts,
+                   slide_stream_t stream);
+int slide_mc_emit(const float *phi, int res, float level, const void *workspace, float vertex_scale, float *verts,
+                  float *normals, int *faces, slide_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@ SYMBOLS = [
     "slide_program_set_resident", "slide_program_use_resident", "slide_philox_normal_slice",
     # include/slide_sap.h
     "slide_sap_mirror_concat", "slide_sap_unit_cube", "slide_dpsr_workspace_bytes", "slide_dpsr_forward",
+    "slide_mc_workspace_bytes", "slide_mc_count", "slide_mc_emit",
 ]
 
 

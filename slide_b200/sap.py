@@ -3,13 +3,14 @@
 Mirrors the reference's interface for this stage:
 
   DPSR                      dpsr_utils/dpsr.py::DPSR (same constructor arguments, forward(V, N) -> phi)
+  mc_from_psr               dpsr_utils/utils.py::mc_from_psr (same arguments; a different, deterministic triangulation)
   SapReconstructor          what dpsr_evaluation.py::visualize_per_rank does per batch between loading the cloud and
                             marching cubes (:214-260): [mirror_and_concat] -> PointNet2CloudCondition(refine JSON) ->
                             network_output_to_dpsr_grid (point_upsample, shapenet_psr_normalize / scale, clamp, DPSR)
 
 torch is used for device memory and streams only; every computation is a kernel of libslide_b200.so and there is no
-fallback: a missing library raises.  Marching cubes (skimage.measure.marching_cubes on the CPU in the reference,
-dpsr_utils/utils.py:246-287) is outside this stage: the indicator grid is its input.
+fallback: a missing library raises.  mc_from_psr extracts the grids' zero level sets on the GPU (marching tetrahedra; the
+reference's skimage.measure.marching_cubes runs on the CPU, dpsr_utils/utils.py:246-287, and cannot be reproduced offline).
 """
 import ctypes
 
@@ -28,6 +29,9 @@ def _bind(l):
     l.slide_sap_unit_cube.argtypes = [vp, ci, ci, ci, ci, cf, vp, vp]
     l.slide_dpsr_workspace_bytes.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_size_t)]
     l.slide_dpsr_forward.argtypes = [vp, ci, vp, ci, ci, ci, ci, cf, ci, ci, vp, vp, ctypes.c_size_t, vp]
+    l.slide_mc_workspace_bytes.argtypes = [ci, ctypes.POINTER(ctypes.c_size_t)]
+    l.slide_mc_count.argtypes = [vp, ci, cf, vp, ctypes.c_size_t, vp, vp]
+    l.slide_mc_emit.argtypes = [vp, ci, cf, vp, cf, vp, vp, vp, vp]
     l._sap_bound = True
     return l
 
@@ -109,6 +113,42 @@ class DPSR(object):
         return out
 
     __call__ = forward
+
+
+def mc_from_psr(psr_grid, zero_level=0.0, real_scale=False, with_normals=True):
+    """dpsr_utils/utils.py::mc_from_psr: iso-surface meshes of a batch of indicator grids, on the GPU.
+    psr_grid (B,r,r,r) cuda f32 -> (verts, faces, normals): lists of B device tensors (V_i,3) f32 in [0,1) grid units
+    (index / r, or index / (r-1) with real_scale), (F_i,3) int32, (V_i,3) f32 (normalised gradient of the grid).
+    The level set is the reference's; the triangulation is marching tetrahedra, not scikit-image's Lewiner marching cubes
+    (include/slide_sap.h: slide_mc_count / slide_mc_emit), so vertex / face counts and order differ from the reference's."""
+    l = _bind(lib.load())
+    assert psr_grid.is_cuda and psr_grid.dtype == torch.float32 and psr_grid.dim() == 4
+    B, r = psr_grid.shape[0], psr_grid.shape[1]
+    assert psr_grid.shape[2] == r and psr_grid.shape[3] == r
+    grid = psr_grid.contiguous()
+    dev = grid.device
+    need = ctypes.c_size_t()
+    lib.check(l.slide_mc_workspace_bytes(r, ctypes.byref(need)), "slide_mc_workspace_bytes")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    counts = torch.zeros(2, dtype=torch.int32, device=dev)
+    scale = 1.0 / (r - 1) if real_scale else 1.0 / r
+    verts, faces, normals = [], [], []
+    with torch.cuda.device(dev):
+        for i in range(B):
+            g = grid[i]
+            lib.check(l.slide_mc_count(lib.ptr(g), r, float(zero_level), lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+                                       lib.ptr(counts), lib.stream_of(g)), "slide_mc_count")
+            nv, nf = (int(c) for c in counts.tolist())  # device -> host: the output sizes
+            v = torch.empty(nv, 3, device=dev, dtype=torch.float32)
+            n = torch.empty(nv, 3, device=dev, dtype=torch.float32) if with_normals else None
+            f = torch.empty(nf, 3, device=dev, dtype=torch.int32)
+            if nv:
+                lib.check(l.slide_mc_emit(lib.ptr(g), r, float(zero_level), lib.ptr(ws), float(scale), lib.ptr(v),
+                                          lib.ptr(n), lib.ptr(f), lib.stream_of(g)), "slide_mc_emit")
+            verts.append(v)
+            faces.append(f)
+            normals.append(n)
+    return verts, faces, normals
 
 
 class SapReconstructor(object):

@@ -62,3 +62,25 @@ def test_refine_lowering_matches_reference_golden(gold):
     # and the grid the oracle builds from the interpreter's output is the reference's grid
     phi, _, _ = sap_oracle.refine_to_grid(X[:1], torch.from_numpy(disp[:1]), (32, 32, 32), 2, 5, pc["output_scale_factor"])
     assert np.abs(phi.numpy() - gold["phi_r32"]).max() < 2e-4
+
+
+def test_mesh_oracle_properties():
+    """oracle/mesh_oracle.py (the checker of the GPU iso-surface kernels) on a sphere: closed, consistently oriented, genus 0,
+    area and radius right, normals outward.  (Parity with scikit-image is unpinned: not available offline.)"""
+    from oracle import mesh_oracle
+    R, c, rad = 24, np.array([11.3, 12.1, 11.7], dtype=np.float32), 7.4
+    g = np.arange(R, dtype=np.float32)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    phi = (np.sqrt((X - c[0]) ** 2 + (Y - c[1]) ** 2 + (Z - c[2]) ** 2) - rad).astype(np.float32)
+    v, n, f = mesh_oracle.extract(phi, 0.0)
+    assert mesh_oracle.mesh_checks(v, f) == dict(closed=True, oriented=True, euler=2)
+    r = np.sqrt(((v - c) ** 2).sum(1))
+    assert np.abs(r - rad).max() < 3.0 / (8 * rad) + 1e-3
+    p0, p1, p2 = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    cr = np.cross(p1 - p0, p2 - p0)
+    assert abs(0.5 * np.linalg.norm(cr, axis=1).sum() / (4 * np.pi * rad ** 2) - 1) < 1e-2
+    assert ((cr * ((p0 + p1 + p2) / 3 - c)).sum(1) > 0).all()
+    assert ((n * (v - c) / r[:, None]).sum(1)).min() > 0.999
+    # a grid without a crossing gives an empty mesh
+    v, n, f = mesh_oracle.extract(np.ones((6, 6, 6), dtype=np.float32), 0.0)
+    assert len(v) == 0 and len(f) == 0
