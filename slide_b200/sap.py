@@ -179,7 +179,9 @@ class SapReconstructor(object):
         self.dpsr = DPSR((r, r, r), sig=self.dc["psr_sigma"])
         self.n_fine = self.n_in * self.h["factor"]
 
-    def reconstruct(self, cloud, labels, perm=None):
+    def reconstruct(self, cloud, labels, perm=None, mesh=False):
+        """mesh=True: also extract the grids' zero level sets (mc_from_psr) -> out["verts"], out["faces"],
+        out["vert_normals"] (lists of B device tensors)."""
         B = self.B
         cloud = torch.as_tensor(cloud, dtype=torch.float32).to(self.device, non_blocking=True)
         assert cloud.shape == (B, self.n_points, 6 if self.include_normals or cloud.shape[2] == 6 else 3)
@@ -202,7 +204,10 @@ class SapReconstructor(object):
         phi = self.dpsr(pts, nrm)
         if lib.load().slide_tc_error():
             raise lib.SlideError("tcgen05 pipeline wait timed out (results invalid)")
-        return dict(phi=phi, points=pts, normals=nrm, refined=fine[:, :, :6])
+        out = dict(phi=phi, points=pts, normals=nrm, refined=fine[:, :, :6])
+        if mesh:
+            out["verts"], out["faces"], out["vert_normals"] = mc_from_psr(phi, zero_level=0.0)
+        return out
 
 
 def load_default(B, n_points=2048, seed=21, **kw):

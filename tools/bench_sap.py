@@ -83,6 +83,15 @@ def main():
     t1.record()
     torch.cuda.synchronize()
     e2e_ms = t0.elapsed_time(t1) / args.reps
+    # iso-surface meshes of the batch's grids (sap.mc_from_psr: one 8-byte read-back per grid sizes its outputs)
+    sap.mc_from_psr(out["phi"][:2])
+    torch.cuda.synchronize()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    verts, faces, _ = sap.mc_from_psr(out["phi"])
+    m1.record()
+    torch.cuda.synchronize()
+    mesh_ms = m0.elapsed_time(m1)
     R = rec.dpsr.res[0]
     peaks = {}
     try:
@@ -97,6 +106,8 @@ def main():
         "clouds_per_s": B / (total / 1e3), "ms": {"setup+mirror": ms[0], "refine_network": ms[1], "unit_cube": ms[2], "dpsr": ms[3]},
         "total_ms": total, "e2e_clouds_per_s": B / (e2e_ms / 1e3), "e2e_ms": e2e_ms,
         "e2e_h2d_bytes": int(cloud_host.numel() * 4), "e2e_d2h_bytes": int(host_phi.numel() * 4),
+        "mesh_ms": mesh_ms, "mesh_vertices_per_grid": int(sum(v.shape[0] for v in verts) / B),
+        "mesh_faces_per_grid": int(sum(f.shape[0] for f in faces) / B),
         "launches": launches, "finite": bool(torch.isfinite(phi).all().item()), "tc_error": int(lib.load().slide_tc_error()),
         "dpsr_roofline": {"bound": "hbm", "algorithmic_bytes": dbytes, "achieved": dbytes / (ms[3] / 1e3) / 1e9, "peak": hbm,
                           "unit": "GB/s", "frac": dbytes / (ms[3] / 1e3) / 1e9 / hbm}}))
