@@ -302,6 +302,10 @@ __device__ __forceinline__ Corners corners_of(const float *p, int R) {
     const float f = floorf(q);
     c.i0[d] = (int)f;
     c.i1[d] = (int)fmodf(ceilf(q), size);
+    // coordinates outside [0, 1) (the reference raises an index error there): wrap instead of touching memory outside the
+    // grid; no effect on valid input
+    if ((unsigned)c.i0[d] >= (unsigned)R) c.i0[d] = ((c.i0[d] % R) + R) % R;
+    if ((unsigned)c.i1[d] >= (unsigned)R) c.i1[d] = ((c.i1[d] % R) + R) % R;
     const float lo = __fmul_rn(f, cell), hi = __fmul_rn(__fadd_rn(f, 1.0f), cell);
     c.w0[d] = __fdiv_rn(fabsf(__fsub_rn(p[d], hi)), cell);  // low node <- distance to the opposite (high) corner
     c.w1[d] = __fdiv_rn(fabsf(__fsub_rn(p[d], lo)), cell);

@@ -106,3 +106,17 @@ def test_reconstructor_against_reference_golden(gold, backend, tol_disp, tol_phi
     want = sap_oracle.dpsr_forward(out["points"].cpu(), out["normals"].cpu().contiguous(), (128,) * 3, 2).numpy()
     assert _rel(out["phi"].cpu().numpy(), want) < 2e-4
     assert lib.load().slide_tc_error() == 0
+
+
+def test_dpsr_out_of_range_points_do_not_touch_foreign_memory():
+    """The reference raises an index error for coordinates outside [0, 1); this library wraps them periodically instead of
+    writing outside the grid.  Valid points are unaffected (the tests above); here: finite output, guard band intact."""
+    g = torch.Generator().manual_seed(2)
+    V = (torch.rand(1, 500, 3, generator=g) * 3 - 1).cuda()          # in [-1, 2)
+    N = torch.randn(1, 500, 3, generator=g).cuda()
+    buf = torch.full((1 + 2, 32, 32, 32), 7.0, device="cuda")          # guard grids before and after the output
+    out = buf[1:2]
+    sap.DPSR((32, 32, 32), sig=2, shift=False, scale=False)(V, N, out=out)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert bool((buf[0] == 7.0).all()) and bool((buf[2] == 7.0).all())
