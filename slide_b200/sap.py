@@ -210,10 +210,11 @@ class SapReconstructor(object):
         return out
 
 
-def load_default(B, n_points=2048, seed=21, **kw):
-    """SapReconstructor on the shipped symmetry refine JSON with seeded random weights of the reference's schema
-    (no checkpoints are reachable offline)."""
+def load_default(B, n_points=2048, seed=21, config="sap_refine", **kw):
+    """SapReconstructor on a shipped refine JSON with seeded random weights of the reference's schema (no checkpoints are
+    reachable offline).  config: "sap_refine" (mirrored input, normals given, 5 children per point) or "sap_refine_plain"
+    (no mirroring, normals estimated by the network, 10 children per point)."""
     from . import weights
-    cfg = weights.load_json("sap_refine.json")
-    sd = weights.random_state_dict(weights.load_json("schema_sap_refine.json"), seed)
+    cfg = weights.load_json(config + ".json")
+    sd = weights.random_state_dict(weights.load_json("schema_%s.json" % config), seed)
     return SapReconstructor(cfg, sd, B, n_points, **kw)

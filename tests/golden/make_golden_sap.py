@@ -130,6 +130,30 @@ def main():
         phi2 = sap_oracle.dpsr_forward(V, Nn, (128,) * 3, 2)
     assert torch.equal(phi, phi2)
     gold["edge_phi128_sub"] = phi[:, ::8, ::8, ::8].numpy()
+    # the shipped configuration without mirroring and without input normals ("zero_normal": the network estimates them):
+    # in_fea_dim 3, 10 children per point, X = [points, zeros] (dpsr_evaluation.py:231-233)
+    full2 = read_json_file(CFG.replace("s3_noise_0_symmetry", "s3_zero_normal_noise_0"))
+    pc2 = full2["pointnet_config"]
+    with open(os.path.join(CONF_OUT, "sap_refine_plain.json"), "w") as f:
+        json.dump({"pointnet_config": pc2, "dpsr_config": full2["dpsr_config"], "scale": full2["shapenet_psr_dataset_config"]["scale"],
+                   "include_normals": full2["shapenet_psr_dataset_config"].get("include_normals", True)}, f, indent=1, sort_keys=True)
+    net2 = PointNet2CloudCondition(copy.deepcopy(pc2)).eval()
+    schema2 = [[k, list(v.shape)] for k, v in net2.state_dict().items()]
+    with open(os.path.join(CONF_OUT, "schema_sap_refine_plain.json"), "w") as f:
+        json.dump(schema2, f, indent=1, sort_keys=True)
+    sd2 = weights.random_state_dict(schema2, 22)
+    net2.load_state_dict(sd2, strict=True)
+    X2 = torch.cat([cloud[:, :, :3], torch.zeros_like(cloud[:, :, :3])], dim=2)
+    with torch.no_grad():
+        disp_p = net2(X2, None, ts=None, label=label)
+        assert torch.equal(disp_p, ref_model.cloud_condition_net(X2, ref_model.Params(sd2), pc2, ts=None, label=label))
+        dpsr = DPSR(res=(16, 16, 16), sig=2)
+        phi_p, rp, rn = real_to_grid(X2, disp_p, dpsr, 1, pc2, last_dim_as_indicator=False, only_original_points_split=False,
+                                     explicit_normalize=True)
+        phi_p2, rp2, rn2 = sap_oracle.refine_to_grid(X2, disp_p, (16, 16, 16), 2, pc2["point_upsample_factor"],
+                                                     pc2["output_scale_factor"], indicator=False)
+    assert torch.equal(phi_p, phi_p2) and torch.equal(rp, rp2) and torch.equal(rn, rn2)
+    gold.update(plain_disp_rows8=disp_p[:, ::8].numpy(), plain_phi_r16=phi_p.numpy())
     np.savez_compressed(os.path.join(OUT, "golden_sap.npz"), **gold)
     print("wrote golden_sap.npz", {k: v.shape for k, v in gold.items()})
 

@@ -84,3 +84,26 @@ def test_mesh_oracle_properties():
     # a grid without a crossing gives an empty mesh
     v, n, f = mesh_oracle.extract(np.ones((6, 6, 6), dtype=np.float32), 0.0)
     assert len(v) == 0 and len(f) == 0
+
+
+def test_plain_refine_lowering_matches_reference_golden(gold):
+    """The shipped configuration without mirroring / input normals (in_fea_dim 3, 10 children per point)."""
+    cfg = weights.load_json("sap_refine_plain.json")
+    pc = cfg["pointnet_config"]
+    assert not cfg["include_normals"] and not cfg["dpsr_config"].get("mirror_before_upsampling")
+    sd = weights.random_state_dict(weights.load_json("schema_sap_refine_plain.json"), 22)
+    B, N = 2, 2048
+    b, h = engine.build_refine(pc, sd, B, N)
+    assert h["factor"] == 10 and h["F"] == 6
+    m = ir_exec.Machine(b)
+    engine.init_constants(m, h)
+    m.upload(h["labels"], gold["label"].astype(np.int32))
+    X = np.concatenate([gold["cloud"][:, :, :3], np.zeros_like(gold["cloud"][:, :, :3])], axis=2)
+    m.upload(h["x"], X.reshape(-1, 6))
+    m.run(*b.segments["setup"])
+    m.run(*b.segments["refine"])
+    disp = np.asarray(m.download(h["disp"])).reshape(B, N, 60)
+    assert np.abs(disp[:, ::8] - gold["plain_disp_rows8"]).max() < 5e-5 * np.abs(gold["plain_disp_rows8"]).max()
+    phi, _, _ = sap_oracle.refine_to_grid(torch.from_numpy(X), torch.from_numpy(disp), (16, 16, 16), 2, 10,
+                                          pc["output_scale_factor"], indicator=False)
+    assert np.abs(phi.numpy() - gold["plain_phi_r16"]).max() < 2e-4
