@@ -107,3 +107,31 @@ def test_plain_refine_lowering_matches_reference_golden(gold):
     phi, _, _ = sap_oracle.refine_to_grid(torch.from_numpy(X), torch.from_numpy(disp), (16, 16, 16), 2, 10,
                                           pc["output_scale_factor"], indicator=False)
     assert np.abs(phi.numpy() - gold["plain_phi_r16"]).max() < 2e-4
+
+
+@pytest.mark.parametrize("knob", ["SLIDE_PAIR_LITE", "SLIDE_HOIST_GEOMETRY", "SLIDE_FACTOR_GROUP"])
+def test_lowering_variants_agree(gold, knob, monkeypatch):
+    """The lowering's A/B knobs change the record list, not the function: folding the neighbour-coordinate term into U
+    (PAIR-lite), hoisting the coordinate-only records onto level 0's side branch, and the materialised (GROUP + GEMM) form of
+    the grouped convs all give the default lowering's output on the CPU interpreter."""
+    cfg = weights.load_json("sap_refine.json")
+    pc = cfg["pointnet_config"]
+    sd = weights.random_state_dict(weights.load_json("schema_sap_refine.json"), 21)
+    B, N = 1, 2048
+    X = sap_oracle.mirror_concat(torch.from_numpy(gold["cloud"][:1]), gold["perm"]).reshape(-1, 7).numpy()
+
+    def run():
+        b, h = engine.build_refine(pc, sd, B, 2 * N)
+        m = ir_exec.Machine(b)
+        engine.init_constants(m, h)
+        m.upload(h["labels"], gold["label"][:1].astype(np.int32))
+        m.upload(h["x"], X)
+        m.run(*b.segments["setup"])
+        m.run(*b.segments["refine"])
+        return np.array(m.download(h["disp"])), [(op[0], op[3]) for op in b.ops]
+
+    base, n_base = run()
+    monkeypatch.setenv(knob, "0")
+    alt, n_alt = run()
+    assert n_alt != n_base, "the knob did not change the lowering (record kinds / order)"
+    assert np.abs(alt - base).max() < 2e-5 * np.abs(base).max()
