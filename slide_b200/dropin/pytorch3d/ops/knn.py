@@ -36,15 +36,15 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, norm=2, K=1, version=-1, re
         # into the features, pointnet2_utils.py:506-517).  The kernel's distances carry no graph, so the backward is
         # attached here: grad_p1 = 2 (p1 - p2[idx]) g, grad_p2 = scatter of -2 (p1 - p2[idx]) g; forward values stay
         # the kernel's (bit-exact with the no-grad path).
-        dists = _KnnDists.apply(p1, p2, idx, dists, l2)
+        dists = _KnnDists.apply(p1, p2, idx, dists, l2, l1)
     return _KNN(dists=dists, idx=idx, knn=nn)
 
 
 class _KnnDists(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, p1, p2, idx, dists, lengths2):
+    def forward(ctx, p1, p2, idx, dists, lengths2, lengths1=None):
         ctx.save_for_backward(p1, p2, idx)
-        ctx.lengths2 = lengths2
+        ctx.lengths2, ctx.lengths1 = lengths2, lengths1
         return dists.clone()
 
     @staticmethod
@@ -54,6 +54,8 @@ class _KnnDists(torch.autograd.Function):
         D = p1.shape[2]
         if ctx.lengths2 is not None:  # padded neighbour slots (k >= lengths2) carry no gradient
             g = g * (torch.arange(K, device=g.device)[None, None, :] < ctx.lengths2[:, None, None]).to(g.dtype)
+        if ctx.lengths1 is not None:  # query rows beyond lengths1 are padding (dists 0, idx 0): no gradient either
+            g = g * (torch.arange(P1, device=g.device)[None, :, None] < ctx.lengths1[:, None, None]).to(g.dtype)
         nb = p2[:, :, None].expand(-1, -1, K, -1).gather(1, idx[:, :, :, None].expand(-1, -1, -1, D))
         diff = 2.0 * (p1[:, :, None, :] - nb) * g[:, :, :, None]            # (N,P1,K,D)
         g1 = diff.sum(2) if ctx.needs_input_grad[0] else None
@@ -61,7 +63,7 @@ class _KnnDists(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             g2 = torch.zeros_like(p2).scatter_add_(1, idx.reshape(N, P1 * K, 1).expand(-1, -1, D),
                                                    (-diff).reshape(N, P1 * K, D))
-        return g1, g2, None, None, None
+        return g1, g2, None, None, None, None
 
 
 def knn_gather(x, idx, lengths=None):

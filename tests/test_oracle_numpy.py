@@ -142,3 +142,28 @@ def test_masked_gather_and_ragged_p3d_fps():
     assert len(set(idx[0].tolist())) == 5
     assert (sel[1, 3:] == 0).all() and torch.equal(sel[0], pts[0][idx[0]])
     assert torch.equal(ops.masked_gather(pts, idx), sel)
+
+
+def test_dropin_knn_backward_matches_autograd():
+    """The drop-in knn_points attaches pytorch3d's gradient of `dists` w.r.t. p1 / p2 to the kernel's (graph-less) outputs
+    (group_knn feeds d2 and 1 / (d2 + 1e-8) into the features, pointnet2_utils.py:506-517).  The backward is plain torch,
+    so it is checked here on the CPU with the oracle's indices: against autograd through a differentiable restatement,
+    with ragged lengths (padded neighbour slots and padded query rows carry no gradient)."""
+    from slide_b200.dropin.pytorch3d.ops.knn import _KnnDists
+    p1, p2 = _rand((3, 6, 3), 21, -1, 1), _rand((3, 12, 3), 22, -1, 1)
+    go = _rand((3, 6, 4), 23, -1, 1)
+    for l1, l2 in ((None, None), (torch.tensor([6, 4, 1]), torch.tensor([12, 5, 2]))):
+        res = ops.knn_points(p1, p2, lengths1=l1, lengths2=l2, K=4)
+        a, b = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
+        out = _KnnDists.apply(a, b, res.idx, res.dists, l2, l1)
+        assert torch.equal(out, res.dists)              # forward values stay the kernel's
+        ga, gb = torch.autograd.grad(out, (a, b), go)
+        a2, b2 = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
+        nb = b2[:, :, None].expand(-1, -1, 4, -1).gather(1, res.idx[:, :, :, None].expand(-1, -1, -1, 3))
+        d = ((a2[:, :, None, :] - nb) ** 2).sum(-1)
+        valid = torch.ones(3, 6, 4)
+        if l1 is not None:
+            valid = valid * (torch.arange(4)[None, None, :] < l2[:, None, None]) * (torch.arange(6)[None, :, None] < l1[:, None, None])
+        wa, wb = torch.autograd.grad(d, (a2, b2), go * valid)
+        assert torch.allclose(ga, wa, atol=1e-6) and torch.allclose(gb, wb, atol=1e-6)
+        assert torch.allclose(d.detach() * valid, res.dists, atol=1e-6)
