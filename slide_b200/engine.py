@@ -180,13 +180,15 @@ def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0,
     return b, h
 
 
-def build_decode(decoder_cfgs, sd, B):
+def build_decode(decoder_cfgs, sd, B, n_keypoints=16):
+    """PointAutoencoder.decode for B shapes of n_keypoints sparse latent points (16 in the flagship configs; the reference
+    also ships 8- and 32-keypoint ablation configs, configs/shapenet_psr_configs/autoencoder_configs/{8,32}_keypoints)."""
     b = Builder(B)
-    kp = b.tensor("keypoint", 16, 3)
+    kp = b.tensor("keypoint", n_keypoints, 3)
     fdim = decoder_cfgs[1]["feature_mapper_setting"]  # noqa: F841  (documented: level-1 features feed level 2)
     P = nets.Params(sd)
     Fdim = sd["keypoint_encoder.fc_layer.weight"].shape[1] - 3
-    feat = b.tensor("feature", 16, Fdim)
+    feat = b.tensor("feature", n_keypoints, Fdim)
     labels = b.tensor("labels", 1, B, B=1, dtype="i32")
     b.begin_segment("decode")
     b.step_begin()
@@ -200,17 +202,17 @@ def build_decode(decoder_cfgs, sd, B):
     return b, h
 
 
-def build_encode(enc_cfg, kp_cfg, sd, B, n_points, sample_posterior=False):
-    """PointAutoencoder.encode for B clouds of n_points (xyz + normal) and their 16 keypoints."""
+def build_encode(enc_cfg, kp_cfg, sd, B, n_points, sample_posterior=False, n_keypoints=16):
+    """PointAutoencoder.encode for B clouds of n_points (xyz + normal) and their n_keypoints keypoints."""
     b = Builder(B)
     cloud = b.tensor("cloud", n_points, 3 + enc_cfg["in_fea_dim"])
-    kp = b.tensor("keypoint", 16, 3)
+    kp = b.tensor("keypoint", n_keypoints, 3)
     labels = b.tensor("labels", 1, B, B=1, dtype="i32")
     C1 = kp_cfg["architecture"]["feature_dim"][-1]
     C2 = kp_cfg["feature_mapper_setting"]["out_dim"]
     noises = None
     if sample_posterior:
-        noises = (b.tensor("noise1", 16, C1), b.tensor("noise2", 16, C2))
+        noises = (b.tensor("noise1", n_keypoints, C1), b.tensor("noise2", n_keypoints, C2))
     P = nets.Params(sd)
     b.begin_segment("encode")
     b.step_begin()
