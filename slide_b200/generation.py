@@ -8,7 +8,8 @@ with the same file names and npz keys, so that files written by either side load
   keypoint file (input) : points (B,16,3) [, label (B,), category, category_name, keypoint_feature (B,16,F),
                           keypoint_mask (B,16)]
   result file (output)  : points (B,P,3), normals (B,P,3), label (B,), category, category_name, timing (B,),
-                          keypoint (B,16,3) [, keypoint_feature (B,16,F)]
+                          keypoint (B,16,3) [, keypoint_feature (B,16,F)] [, gt_points (B,N,6) when the keypoints were
+                          sampled from known shapes, mesh_evaluation.py:86-98,140-142]
 What changes is where the time goes: position -> feature -> decode are chained on the device (no npz round trip
 between the reference's two scripts), a batch is copied to the host once, and under torch.distributed the per-rank
 clouds travel through one NCCL all-gather instead of per-rank files (the file-level gather is kept for drop-in use).
@@ -51,13 +52,15 @@ def result_file(save_dir, num_points, rank=0, world_size=1, ckpt_info=""):
 
 
 def pack_results(clouds, label, category, category_name, timing, keypoint=None, keypoint_feature=None,
-                 split_points_and_normals=True):
+                 split_points_and_normals=True, gt_points=None):
     """The result dict of evaluate_per_rank (mesh_evaluation.py:135-150)."""
     clouds = np.asarray(clouds, dtype=np.float32)
     result = {"points": clouds, "label": np.asarray(label), "category": list(category),
               "category_name": list(category_name), "timing": np.asarray(timing)}
     if keypoint is not None:
         result["keypoint"] = np.asarray(keypoint, dtype=np.float32)
+    if gt_points is not None:
+        result["gt_points"] = np.asarray(gt_points, dtype=np.float32)
     if keypoint_feature is not None:
         result["keypoint_feature"] = np.asarray(keypoint_feature, dtype=np.float32)
     if split_points_and_normals and clouds.shape[2] == 6:
@@ -68,18 +71,22 @@ def pack_results(clouds, label, category, category_name, timing, keypoint=None, 
 
 def generate_per_rank(pipe, keypoints, label, category=None, category_name=None, save_dir=None, ckpt_info="",
                       save_keypoint_feature=False, complete_x0=None, keypoint_mask=None,
-                      split_points_and_normals=True, rank=0, world_size=1):
+                      split_points_and_normals=True, rank=0, world_size=1, gt_points=None, keypoint_noise_magnitude=0.0):
     """evaluate_per_rank for task 'latent_keypoint_conditional_generation' with external keypoints: feature DDPM +
     decode for this rank's keypoints (any count: the tail batch is padded up to the pipeline's batch and trimmed).
 
     pipe: this process's SlidePipeline over its own keypoint slice (world=1; built with local_resampling=True when
     complete_x0 / keypoint_mask are given); rank / world_size only select the result file name, as in the reference
     where every rank samples its slice independently.  keypoints (n,16,3), label (n,) CPU tensors.
+    gt_points (n,N,6): the shapes the keypoints were sampled from (the reference's `test_external_keypoint=False` branch,
+    mesh_evaluation.py:86-98; `keypoints_from_shapes` below makes such keypoints); stored under `gt_points` as the
+    reference does (:140-142).  keypoint_noise_magnitude > 0: `keypoint + magnitude * torch.randn_like(keypoint)` per
+    batch on the device generator before sampling (:80-82,92-94); the noised keypoints are conditioned on and saved.
     Returns the result dict; writes it to the reference's file name when save_dir is given."""
     assert pipe.world == 1, "one independent pipeline per rank (see load_keypoint_file for the slicing)"
     n = keypoints.shape[0]
     Bl = pipe.Bl
-    clouds, feats, timing = [], [], []
+    clouds, feats, timing, used_kp = [], [], [], []
     for b0 in range(0, n, Bl):
         m = min(Bl, n - b0)
         pad = lambda t: torch.cat([t[b0:b0 + m], t[b0:b0 + 1].expand((Bl - m,) + tuple(t.shape[1:]))]) if m < Bl \
@@ -89,7 +96,13 @@ def generate_per_rank(pipe, keypoints, label, category=None, category_name=None,
         # reference never draws position-DDPM noise on this path (diffusion.py:373 is its first draw), so neither do we
         pipe.draw_host_inputs(pad(label), skip_position=True)
         pipe.stage_inputs()
-        out = pipe.sample_resident(keypoints=pad(keypoints).to(pipe.device),
+        kp_dev = keypoints[b0:b0 + m].to(pipe.device)
+        if keypoint_noise_magnitude > 0:
+            kp_dev = kp_dev + keypoint_noise_magnitude * torch.randn_like(kp_dev)  # the batch's real rows only
+        used_kp.append(kp_dev.cpu())
+        if m < Bl:
+            kp_dev = torch.cat([kp_dev, kp_dev[0:1].expand(Bl - m, -1, -1)])
+        out = pipe.sample_resident(keypoints=kp_dev,
                                    complete_x0=None if complete_x0 is None else pad(complete_x0),
                                    keypoint_mask=None if keypoint_mask is None else pad(keypoint_mask))
         host = out[:m].cpu()
@@ -98,13 +111,30 @@ def generate_per_rank(pipe, keypoints, label, category=None, category_name=None,
         clouds.append(host.numpy())
         feats.append(pipe.keypoint_feature[:m].cpu().numpy())
     result = pack_results(np.concatenate(clouds, axis=0), label.numpy(), category or [""] * n,
-                          category_name or [""] * n, timing, keypoint=keypoints.numpy(),
+                          category_name or [""] * n, timing, keypoint=torch.cat(used_kp).numpy(),
+                          gt_points=None if gt_points is None else np.asarray(gt_points),
                           keypoint_feature=np.concatenate(feats, axis=0) if save_keypoint_feature else None,
                           split_points_and_normals=split_points_and_normals)
     if save_dir is not None:
         os.makedirs(save_dir, exist_ok=True)
         np.savez(result_file(save_dir, pipe.dec.out_points, rank, world_size, ckpt_info), **result)
     return result
+
+
+def keypoints_from_shapes(points, num_keypoints=16, add_centroid=True):
+    """The keypoints of known shapes, as evaluate_per_rank makes them when ground truth is given
+    (mesh_evaluation.py:88-91 -> data_utils/points_sampling.py:156-187, random_subsample=False): farthest point sampling
+    over [centroid; points] from index 0 (add_centroid=True: the centroid is the first keypoint), or over the points from
+    a random start index per shape (pytorch3d's CPU-generator draws, as in the reference: random_start_point=not
+    add_centroid; the 8- / 32-keypoint ablation configs set add_centroid_to_keypoints false).
+    points (B,N,3) on the GPU -> (B,K,3)."""
+    from .pipeline import sample_keypoints
+    if add_centroid:
+        return sample_keypoints(points, K=num_keypoints)
+    from . import install_dropin
+    install_dropin()
+    from pytorch3d.ops import sample_farthest_points
+    return sample_farthest_points(points.contiguous(), K=num_keypoints, random_start_point=True)[0]
 
 
 def gather_generated_results(save_dir, world_size, num_points=2048, ckpt_info="", remove_rank_files=True):

@@ -164,6 +164,28 @@ def test_generation_driver_batches_pads_and_trims(tmp_path):
     assert np.array_equal(res["label"], label.numpy()) and len(res["timing"]) == n
     data = np.load(os.path.join(str(tmp_path), "shapenet_psr_generated_data_2048_pts.npz"))
     assert np.array_equal(data["keypoint"], kp.numpy())
+    assert "gt_points" not in data.files
+
+
+def test_generation_driver_known_shapes_and_keypoint_noise(tmp_path):
+    """evaluate_per_rank's `test_external_keypoint=False` branch (mesh_evaluation.py:86-98,140-142): the shapes the keypoints
+    came from travel into the result file as `gt_points`, and keypoint noise is `magnitude * randn_like` per batch on the
+    batch's real rows -- the noised keypoints are what the sampler sees and what is saved."""
+    n, Bl = 5, 2
+    kp = torch.arange(n * 16 * 3, dtype=torch.float32).reshape(n, 16, 3)
+    gt = torch.randn(n, 64, 6)
+    pipe = _FakePipe(Bl)
+    torch.manual_seed(7)
+    res = generation.generate_per_rank(pipe, kp, torch.zeros(n, dtype=torch.int64), save_dir=str(tmp_path), gt_points=gt,
+                                       keypoint_noise_magnitude=0.04)
+    torch.manual_seed(7)
+    want = torch.cat([kp[b0:b0 + Bl] + 0.04 * torch.randn_like(kp[b0:b0 + Bl]) for b0 in range(0, n, Bl)])
+    assert np.array_equal(res["keypoint"], want.numpy())                  # the reference's draws: (2,16,3), (2,16,3), (1,16,3)
+    assert np.array_equal(res["points"][:, :16], want.numpy())            # ... and they are what was conditioned on
+    assert np.array_equal(res["gt_points"], gt.numpy())
+    data = np.load(os.path.join(str(tmp_path), "shapenet_psr_generated_data_2048_pts.npz"))
+    assert sorted(data.files) == sorted(["points", "normals", "label", "category", "category_name", "timing", "keypoint",
+                                         "gt_points"])
 
 
 def test_position_sampler_matches_reference_golden(gs, pipeline_cfg):
