@@ -193,6 +193,10 @@ class SlidePipeline(object):
         draw_host_inputs are then this rank's (B/W,)."""
         assert global_batch % world == 0
         assert rng_scope in ("global", "rank")
+        if int(cfg.get("num_keypoints", 16)) != 16:
+            # the programs lower for the reference's 8- / 32-keypoint ablations too (engine.build_ddpm(n_points=),
+            # build_decode(n_keypoints=)); this orchestration (buffers, RNG slicing) is written for the 16-keypoint flagship
+            raise NotImplementedError("SlidePipeline drives the 16-keypoint configs; got num_keypoints=%r" % cfg["num_keypoints"])
         self.cfg, self.B, self.rank, self.world = cfg, global_batch, rank, world
         self.Bl = global_batch // world
         self.rng_scope = rng_scope
