@@ -108,3 +108,34 @@ def test_autoencoders_of_the_keypoint_ablations(kps, tag, ga, fams):
     want = ga[pre + "enc_mode"]
     got = m.download(h["out"]).numpy().reshape(want.shape)
     assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max())
+
+
+# ---------------------------------------------------------------------------------------------- random architectures
+@pytest.fixture(scope="module")
+def gr():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_random_archs.npz"))
+
+
+@pytest.mark.parametrize("i", range(10))
+def test_random_architectures_lower_like_the_reference(i, gr):
+    """Ten randomly drawn denoiser architectures (1-3 levels, with and without down-sampling, widths that are not multiples
+    of the GroupNorm group count, depths 2-3, K 3-8, input features 0-13, timestep / class widths 64 / 128 / 32) lowered and
+    interpreted against the REAL PointNet2CloudCondition's outputs (tests/golden/make_golden_random_archs.py)."""
+    import json
+    meta = json.loads(str(gr["meta_json"]))[i]
+    pc, n0 = meta["pointnet_config"], meta["n_points"]
+    sd = weights.random_state_dict(meta["schema"], meta["seed"])
+    d = weights.load_json("pipeline_airplane.json")["position_ddpm"]["diffusion_config"]
+    b, h = engine.build_ddpm(pc, sd, B, d["T"], engine.position_table(d["T"], d["beta_0"], d["beta_T"]), 0, n_points=n0,
+                             keep_cols=0, with_noise=False)
+    m = ir_exec.Machine(b)
+    engine.init_constants(m, h)
+    m.upload(h["labels"], gr["label"].astype(np.int32))
+    m.run_segment("setup")
+    for t in (999, 0):
+        m.upload(h["x"], gr["a%d_x" % i])
+        m.set_step(t + 1)
+        m.run_segment("forward")
+        want = gr["a%d_eps_t%d" % (i, t)]
+        eps = m.download(h["eps"]).numpy().reshape(want.shape)
+        assert np.abs(eps - want).max() < 2e-5 * max(1.0, np.abs(want).max()), (i, t)
