@@ -65,3 +65,61 @@ def test_feature_denoiser_is_refused(pipeline_cfg):
                              engine.latent_table(lat["standard_diffusion_config"]), 1, keep_cols=3,
                              resident=dict(cluster=4))
     assert h["resident_plans"] == [] and "shared memory" in h["resident_unsupported"]
+
+
+# ------------------------------------------------------------------------------------------ random 16-point architectures
+def _random16():
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gr = np.load(os.path.join(root, "tests", "golden", "golden_random_archs.npz"))
+    return gr, json.loads(str(gr["meta16_json"]))
+
+
+@pytest.mark.parametrize("i", range(6))
+@pytest.mark.parametrize("cluster", [2, 4])
+def test_random_architectures_compile_or_refuse(i, cluster, pipeline_cfg):
+    """Six randomly drawn 16-point denoisers (1-3 levels, widths 16-128 incl. non-multiples of the GroupNorm group count,
+    K 8 / 16, depths 2-3; tests/golden/make_golden_random_archs.py): the record program reproduces the REAL
+    PointNet2CloudCondition, and the sample-resident compiler either refuses the architecture loudly (the pipeline then keeps
+    the record executor) or emits plans whose simulation equals the record interpreter -- never a silently different result."""
+    from slide_b200 import weights
+    gr, metas = _random16()
+    meta = metas[i]
+    pc, n0 = meta["pointnet_config"], meta["n_points"]
+    sd = weights.random_state_dict(meta["schema"], meta["seed"])
+    d = pipeline_cfg["position_ddpm"]["diffusion_config"]
+    B = 2
+    b, h = engine.build_ddpm(pc, sd, B, 4, engine.position_table(d["T"], d["beta_0"], d["beta_T"]), 0, n_points=n0,
+                             resident=dict(cluster=cluster, precise=True))
+    m = ir_exec.Machine(b)
+    engine.init_constants(m, h)
+    m.upload(h["labels"], gr["label"].astype(np.int32))
+    m.run_segment("setup")
+    # the record program against the real module (timestep table of this 4-step program: t = 0 is its last row too)
+    m.upload(h["x"], gr["r%d_x" % i])
+    m.set_step(1)
+    m.run_segment("forward")
+    want = gr["r%d_eps_t0" % i]
+    eps = m.download(h["eps"]).numpy().reshape(want.shape)
+    assert np.abs(eps - want).max() < 2e-5 * max(1.0, np.abs(want).max())
+    if not h["resident_plans"]:
+        assert h["resident_unsupported"]          # refused with a reason
+        return
+    g = torch.Generator().manual_seed(3)
+    m.upload(h["x"], torch.randn(B * n0, 3, generator=g))
+    m.upload(h["noise"], torch.randn(h["noise"].rows, 3, generator=g))
+    m.set_step(3)
+    start = m.arena.copy()
+    for plan, seg in zip(h["resident_plans"], ("step", "forward")):
+        m.arena[:] = start
+        m.run_segment(seg)
+        want_x, want_eps = m.download(h["x"]).numpy().copy(), m.download(h["eps"]).numpy().copy()
+        hdr, rec = plan.pack()
+        assert int(hdr[0]["smem_floats"]) <= resident.SMEM_LIMIT_FLOATS
+        arena = start.copy()
+        resident_sim.ResidentSim(b, hdr, rec).run(arena)
+        m.arena[:] = arena
+        assert np.abs(m.download(h["x"]).numpy() - want_x).max() <= 1e-5 * np.abs(want_x).max()
+        if seg == "forward":
+            assert np.abs(m.download(h["eps"]).numpy() - want_eps).max() <= 1e-5 * np.abs(want_eps).max()
