@@ -113,6 +113,18 @@ def fast_position_schedule(method, length, schedule, kappa, dcfg):
 # ---------------------------------------------------------------------------------------------------
 # builders
 # ---------------------------------------------------------------------------------------------------
+def can_freeze_geometry(cfg, n_points=16):
+    """True when a denoiser's neighbour searches can be hoisted out of the step for frozen coordinates: no level of the
+    network down-samples (with down-sampling the FPS pick belongs to the step, nets._sa_geometry refuses to defer it).
+    All shipped denoisers qualify (npoint == the keypoint count on every level)."""
+    n = n_points
+    for npoint in cfg["architecture"]["npoint"]:
+        if n > npoint:
+            return False
+        n = min(n, npoint)
+    return True
+
+
 def build_ddpm(cfg, sd, B, T, table, mode, n_points=16, keep_cols=0, clamp=-1.0, with_noise=True,
                local_resampling=False, ts_values=None, resident=None, frozen_xyz=False):
     """One program = setup segment + step segment (+ forward-only segment) for a DDPM denoiser.

@@ -30,7 +30,8 @@ class DDPMSampler(object):
         frozen_xyz: None = automatic (the keypoint-conditional feature DDPM: the update leaves the coordinates alone) --
         the modules' neighbour searches run once per chain (refresh_geometry) instead of once per step."""
         self.B, self.T, self.mode = B, T, mode
-        self.frozen_xyz = (mode == 1 and keep_cols >= 3) if frozen_xyz is None else bool(frozen_xyz)
+        self.frozen_xyz = (mode == 1 and keep_cols >= 3 and engine.can_freeze_geometry(pointnet_cfg)) \
+            if frozen_xyz is None else bool(frozen_xyz)
         self.builder, self.h = engine.build_ddpm(pointnet_cfg, sd, B, T, table, mode, keep_cols=keep_cols, clamp=clamp,
                                                  local_resampling=local_resampling, ts_values=ts_values,
                                                  resident=resident if backend == "auto" else None,

@@ -129,3 +129,33 @@ def test_frozen_coordinates_hoist_the_neighbour_search(golden, pipeline_cfg):
             m.run_segment("step")
         out.append(np.array(m.download(h["x"])))
     assert np.array_equal(out[0], out[1])
+
+
+def test_automatic_geometry_hoist_only_without_down_sampling(golden, pipeline_cfg):
+    """DDPMSampler(frozen_xyz=None) hoists the neighbour searches only when engine.can_freeze_geometry says so: every
+    shipped denoiser qualifies; a custom feature denoiser that down-samples (FPS inside the step) keeps them in the step
+    instead of failing, and still reproduces the reference network."""
+    import copy
+    lat = pipeline_cfg["latent_ddpm"]
+    assert engine.can_freeze_geometry(lat["pointnet_config"]) and engine.can_freeze_geometry(pipeline_cfg["position_ddpm"]["pointnet_config"])
+    pc = copy.deepcopy(lat["pointnet_config"])
+    pc["architecture"]["npoint"] = [16, 8]      # the point counts change no parameter shape: same state dict
+    assert not engine.can_freeze_geometry(pc)
+    sd = common.state_dict("lat")
+    table = engine.latent_table(lat["standard_diffusion_config"])
+    with pytest.raises(NotImplementedError):
+        engine.build_ddpm(pc, sd, 2, 1000, table, 1, keep_cols=3, with_noise=False, frozen_xyz=True)
+    b, h = engine.build_ddpm(pc, sd, 2, 1000, table, 1, keep_cols=3, with_noise=False, frozen_xyz=False)
+    assert "geometry" not in b.segments
+    m = ir_exec.Machine(b)
+    common.init_machine(m, h, golden["label"])
+    m.run_segment("setup")
+    x = torch.from_numpy(golden["lat_x"])
+    m.upload(h["x"], x)
+    m.set_step(501)
+    m.run_segment("forward")
+    eps = m.download(h["eps"]).numpy().reshape(2, 16, -1)
+    with torch.no_grad():
+        want = ref_model.cloud_condition_net(x, ref_model.Params(sd), pc, ts=torch.ones(2) * 500,
+                                             label=torch.from_numpy(golden["label"]).long()).numpy()
+    assert np.abs(eps - want).max() < 2e-5 * max(1.0, np.abs(want).max())
