@@ -230,7 +230,12 @@ class Builder(object):
                                            "SB_STEP": self.step.off}, note="step_begin")
 
     def knn(self, q, ref, K, idx, d2=None, note=""):
-        assert q.B == ref.B == idx.B and idx.R == q.R and idx.C == K and K <= ref.R
+        assert q.B == ref.B == idx.B and idx.R == q.R and idx.C == K
+        if K > ref.R:
+            # pytorch3d pads the missing neighbours with index 0 / distance 0 and the reference's modules then treat them as
+            # real neighbours (group_knn, pointnet2_utils.py:497-524); no shipped config gets here (K = 8 <= 16 points)
+            raise NotImplementedError("%s: %d nearest neighbours among %d points (pytorch3d's zero-padded neighbours are "
+                                      "not lowered)" % (note or "knn", K, ref.R))
         self._emit("SLIDE_OP_KNN", {"KNN_Q": q.off, "KNN_LDQ": q.ld, "KNN_P1": q.R, "KNN_REF": ref.off,
                                     "KNN_LDR": ref.ld, "KNN_P2": ref.R, "KNN_K": K, "KNN_IDX": idx.off,
                                     "KNN_D2": d2.off if d2 is not None else -1, "KNN_B": q.B}, note=note)

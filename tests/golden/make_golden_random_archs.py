@@ -22,6 +22,7 @@ from oracle import ops, ref_model  # noqa: E402
 
 ops.install_reference_stubs()
 from models.pointnet2_with_pcld_condition import PointNet2CloudCondition  # noqa: E402
+from models.autoencoder import PointAutoencoder  # noqa: E402
 from slide_b200 import weights  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -73,6 +74,87 @@ def draw(rng, base):
     return pc, n0
 
 
+N_DECODERS = 4
+DEC_WIDTHS = [16, 24, 32, 40, 64]
+DEC_STARTS = [[1, 2], [3, 4], [5, 6]]
+
+
+def draw_decoders(rng, aec):
+    """A random three-level autoencoder decoder: keypoint count, up-sampling factors / level sizes, extractor depths, widths,
+    neighbour counts (K kept <= the coarsest level: pytorch3d's zero-padded neighbours are not lowered)."""
+    enc, decs = copy.deepcopy(aec["encoder"]), copy.deepcopy(aec["decoders"])
+    kps = rng.choice([8, 16, 32])
+    f1 = rng.choice([4, 8, 16])
+    n1 = kps * f1 // rng.choice([1, 2])
+    f2 = rng.choice([2, 4])
+    n2 = n1 * f2 // rng.choice([1, 2])
+    f3 = rng.choice([2, 4])
+    n3 = n2 * f3 // rng.choice([1, 2])
+    for dcfg, (f, n) in zip(decs, [(f1, n1), (f2, n2), (f3, n3)]):
+        dcfg["upsampling_setting"]["point_upsample_factor"] = f
+        dcfg["upsampling_setting"]["num_output_points"] = n
+    k0 = decs[0]
+    k0["architecture"]["npoint"] = [kps, kps]
+    k0["architecture"]["nsample"] = [min(rng.choice([8, 16]), kps)] * 2
+    k0["architecture"]["feature_dim"] = [rng.choice([16, 24, 32]) for _ in range(3)]
+    k0["feature_mapper_setting"]["out_dim"] = rng.choice([16, 24, 32])
+    k0["feature_mapper_setting"]["nsample"] = rng.choice([8, 32])
+    for n_in, dcfg in zip([kps, n1], decs[1:]):
+        a = dcfg["architecture"]
+        levels = rng.choice([2, 3])
+        npoint = [max(8, n_in // 2)]
+        for _ in range(levels - 1):
+            npoint.append(max(4, npoint[-1] // rng.choice([2, 4])))
+        a["npoint"], a["nsample"], a["radius"] = npoint, [rng.choice([8, 16]) for _ in range(levels)], [0] * levels
+        a["feature_dim"] = [rng.choice(DEC_WIDTHS) for _ in range(levels + 1)]
+        a["decoder_feature_dim"] = [rng.choice(DEC_WIDTHS) for _ in range(levels)] + [a["feature_dim"][-1]]
+        a["K"] = min(rng.choice([4, 8]), min(npoint))
+        a["mlp_depth"], a["decoder_mlp_depth"] = rng.choice([2, 3]), rng.choice([2, 3])
+        dcfg["feature_mapper_setting"]["out_dim"] = rng.choice(DEC_WIDTHS)
+        dcfg["feature_mapper_setting"]["nsample"] = rng.choice([4, 8])
+    return enc, decs, kps
+
+
+def decoder_family(gold, B, label):
+    aec = weights.load_json("pipeline_airplane.json")["autoencoder"]
+    rng = random.Random(1)
+    meta = []
+    for i in range(N_DECODERS):
+        enc, decs, kps = draw_decoders(rng, aec)
+        net = PointAutoencoder(copy.deepcopy(enc), copy.deepcopy(decs), apply_kl_regularization=True, kl_weight=1e-5).eval()
+        schema = [[k, list(v.shape)] for k, v in net.state_dict().items()]
+        sd = weights.random_state_dict(schema, 50 + i)
+        net.load_state_dict(sd, strict=True)
+        g = torch.Generator().manual_seed(i)
+        fdim = sd["keypoint_encoder.fc_layer.weight"].shape[1] - 3
+        kp = torch.rand(B, kps, 3, generator=g) - 0.5
+        feat = torch.randn(B, kps, fdim, generator=g)
+        starts = [torch.tensor(s) for s in DEC_STARTS]
+        it = iter(starts)
+        orig = ops.draw_start_indices
+        ops.draw_start_indices = lambda lengths: next(it)   # pin pytorch3d's CPU randint draws
+        with torch.no_grad():
+            out = net.decode(kp, feat, label=label)
+        ops.draw_start_indices = orig
+        with torch.no_grad():
+            out2, levels = ref_model.decode(kp, feat, ref_model.Params(sd), decs, label, start_idx_list=starts)
+        # ref_model.decode is bit-identical to the real module on most draws; where a layer shape sends torch's CPU GEMM down
+        # another accumulation order, FPS over near-coincident children picks other (equally valid) points and the clouds
+        # agree as point SETS only.  The intermediate level (which the real module does not return) is pinned only when
+        # the two are bit-identical.
+        exact = bool(torch.equal(out, out2))
+        dist = torch.cdist(out[:, :, :3].double(), out2[:, :, :3].double())
+        assert exact or float(torch.max(dist.min(1)[0].max(), dist.min(2)[0].max())) < 1e-3, \
+            "oracle/ref_model.decode deviates from the reference on decoder %d" % i
+        gold.update({"d%d_kp" % i: kp.numpy(), "d%d_feat" % i: feat.numpy(), "d%d_l1" % i: levels[1].numpy(),
+                     "d%d_out" % i: out.numpy()})
+        meta.append({"decoders": decs, "schema": schema, "n_keypoints": kps, "seed": 50 + i, "l1_pinned": exact})
+        print("d", i, "keypoints", kps, "levels", [tuple(l.shape[1:]) for l in levels],
+              [(d["architecture"]["npoint"], d["architecture"]["K"]) for d in decs[1:]])
+    gold["dec_starts"] = np.asarray(DEC_STARTS)
+    gold["meta_dec_json"] = np.array(json.dumps(meta, sort_keys=True, separators=(",", ":")))
+
+
 def main():
     base = weights.load_json("pipeline_airplane.json")["position_ddpm"]["pointnet_config"]
     gold = {}
@@ -80,6 +162,7 @@ def main():
     label = torch.tensor([0, 4])
     for prefix, count, drawer, seed in (("a", N_ARCHS, draw, 2), ("r", N_ARCHS_16, draw16, 5)):
         one_family(gold, prefix, count, drawer, random.Random(seed), base, B, label)
+    decoder_family(gold, B, label)
     gold["label"] = label.numpy()
     path = os.path.join(OUT, "golden_random_archs.npz")
     np.savez_compressed(path, **gold)

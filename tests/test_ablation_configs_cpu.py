@@ -139,3 +139,45 @@ def test_random_architectures_lower_like_the_reference(i, gr):
         want = gr["a%d_eps_t%d" % (i, t)]
         eps = m.download(h["eps"]).numpy().reshape(want.shape)
         assert np.abs(eps - want).max() < 2e-5 * max(1.0, np.abs(want).max()), (i, t)
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_random_decoders_lower_like_the_reference(i, gr):
+    """Four randomly drawn three-level autoencoder decoders (8 / 16 keypoints, other up-sampling factors and level sizes,
+    2-3 extractor levels, widths 16-64, K 4-8) against the REAL PointAutoencoder.decode; clouds compared as point sets (FPS
+    over near-coincident children is chaotic under fp32 re-association), the first level exactly where the generator
+    could pin it."""
+    import json
+    meta = json.loads(str(gr["meta_dec_json"]))[i]
+    kps = meta["n_keypoints"]
+    sd = weights.random_state_dict(meta["schema"], meta["seed"])
+    b, h = engine.build_decode(meta["decoders"], sd, B, n_keypoints=kps)
+    m = ir_exec.Machine(b)
+    engine.init_constants(m, h)
+    m.upload(h["labels"], gr["label"].astype(np.int32))
+    m.upload(h["keypoint"], gr["d%d_kp" % i])
+    m.upload(h["feature"], gr["d%d_feat" % i])
+    for t, s in zip(h["starts"], gr["dec_starts"]):
+        m.upload(t, s.astype(np.int32))
+    m.run_segment("setup")
+    m.run_segment("decode")
+    if meta["l1_pinned"]:
+        want_l1 = gr["d%d_l1" % i]
+        assert np.abs(m.download(h["levels"][1]).numpy().reshape(want_l1.shape) - want_l1).max() < 1e-6
+    want = gr["d%d_out" % i]
+    out = m.download(h["out"]).numpy().reshape(want.shape)
+    for s in range(B):
+        d = torch.cdist(torch.from_numpy(out[s, :, :3]).double(), torch.from_numpy(want[s, :, :3]).double())
+        assert max(float(d.min(1)[0].max()), float(d.min(0)[0].max())) < 2e-3
+
+
+def test_more_neighbours_than_points_is_refused(gr):
+    """pytorch3d pads kNN results with index 0 / distance 0 when K exceeds the cloud; the lowering does not reproduce that
+    and must say so instead of emitting a record the kernels reject."""
+    import copy
+    import json
+    meta = json.loads(str(gr["meta_dec_json"]))[0]
+    decs = copy.deepcopy(meta["decoders"])
+    decs[1]["architecture"]["K"] = 1 + min(decs[1]["architecture"]["npoint"])
+    with pytest.raises(NotImplementedError, match="nearest neighbours among"):
+        engine.build_decode(decs, weights.random_state_dict(meta["schema"], meta["seed"]), B, n_keypoints=meta["n_keypoints"])
