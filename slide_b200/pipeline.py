@@ -13,7 +13,6 @@ Noise is always drawn for the FULL batch and then sliced per rank, so results do
 There is no CPU or PyTorch fallback: every network op runs in libslide_b200.so; torch is used for device
 memory, RNG, streams and (multi-GPU) the NCCL all-gather.
 """
-import numpy as np
 import torch
 
 from . import engine, rng, weights

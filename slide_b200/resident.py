@@ -24,7 +24,7 @@ import os
 import numpy as np
 
 from . import program as P
-from .program import KIND, KIND_NAME, V
+from .program import KIND_NAME
 
 _HDR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "slide_resident.h")
 RCONST, RENUM, RV = P._parse_header(_HDR, r"SLIDE_R\w+")

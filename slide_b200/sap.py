@@ -14,7 +14,6 @@ reference's skimage.measure.marching_cubes runs on the CPU, dpsr_utils/utils.py:
 """
 import ctypes
 
-import numpy as np
 import torch
 
 from . import engine, lib
