@@ -64,3 +64,39 @@ def test_public_names_exist():
     from pytorch3d.ops import knn_points, knn_gather, sample_farthest_points  # noqa: F401
     from pytorch3d.ops.utils import masked_gather  # noqa: F401
     from pytorch3d.structures.pointclouds import Pointclouds  # noqa: F401
+
+
+def test_ext_argument_checks_fail_like_the_reference():
+    """The pybind functions reject CPU, non-contiguous and wrong-dtype tensors through CHECK_CONTIGUOUS / CHECK_IS_FLOAT /
+    CHECK_IS_INT (RuntimeError, _ext-src/include/utils.h:5-25) and have no CPU path ("CPU not supported", sampling.cpp:34).
+    The drop-in raises the same way, before any library call -- so this runs without a GPU."""
+    import pytest
+    import torch
+    slide_b200.install_dropin()
+    from pointnet2_ops import _ext
+    f = torch.zeros(2, 4, 8)
+    xyz = torch.zeros(2, 8, 3)
+    i2 = torch.zeros(2, 5, dtype=torch.int32)
+    i3 = torch.zeros(2, 5, 3, dtype=torch.int32)
+    w = torch.zeros(2, 5, 3)
+    calls = {
+        "gather_points": lambda **k: _ext.gather_points(k.get("a", f), k.get("i", i2)),
+        "gather_points_grad": lambda **k: _ext.gather_points_grad(k.get("a", torch.zeros(2, 4, 5)), k.get("i", i2), 8),
+        "furthest_point_sampling": lambda **k: _ext.furthest_point_sampling(k.get("a", xyz), 4),
+        "three_nn": lambda **k: _ext.three_nn(k.get("a", xyz), xyz),
+        "three_interpolate": lambda **k: _ext.three_interpolate(k.get("a", f), k.get("i", i3), w),
+        "three_interpolate_grad": lambda **k: _ext.three_interpolate_grad(k.get("a", torch.zeros(2, 4, 5)), k.get("i", i3), w, 8),
+        "ball_query": lambda **k: _ext.ball_query(k.get("a", xyz), xyz, 0.2, 4),
+        "group_points": lambda **k: _ext.group_points(k.get("a", f), k.get("i", i3)),
+        "group_points_grad": lambda **k: _ext.group_points_grad(k.get("a", torch.zeros(2, 4, 5, 3)), k.get("i", i3), 8),
+    }
+    for name, call in calls.items():
+        with pytest.raises(RuntimeError, match="CPU not supported|must be a CUDA tensor"):
+            call()                                                     # well-formed CPU tensors: no CPU path
+        with pytest.raises(RuntimeError, match="must be a float tensor"):
+            call(a=torch.zeros(2, 8, 3, dtype=torch.float64))          # wrong dtype of the first argument
+    for name in ("gather_points", "three_interpolate", "group_points"):
+        with pytest.raises(RuntimeError, match="must be an int tensor"):
+            calls[name](i=torch.zeros(2, 5, 3, dtype=torch.int64))     # the reference's kernels take int32 indices
+    with pytest.raises(RuntimeError, match="must be a contiguous tensor"):
+        _ext.furthest_point_sampling(torch.zeros(2, 3, 8).transpose(1, 2), 4)
