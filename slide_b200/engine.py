@@ -42,22 +42,41 @@ def latent_table(dcfg):
     extract() (diffusion.py:31-39) and exp(0.5*logvar) evaluated in fp32 like denoising_step (:88-92):
     [sqrt_recip_acp, sqrt_recipm1_acp, post_mean_coef1, post_mean_coef2, exp(0.5*logvar)]."""
     import torch
-    if dcfg["beta_schedule"] != "linear" or dcfg.get("model_var_type", "fixedsmall") != "fixedsmall":
-        raise NotImplementedError("only the linear / fixedsmall schedule of the shipped configs")
     T = dcfg["num_diffusion_timesteps"]
-    betas = np.linspace(dcfg["beta_start"], dcfg["beta_end"], T, dtype=np.float64)
-    alphas = 1.0 - betas
-    acp = np.cumprod(alphas, axis=0)
-    acp_prev = np.append(1.0, acp[:-1])
-    post_var = betas * (1.0 - acp_prev) / (1.0 - acp)
-    logvar = np.log(np.maximum(post_var, 1e-20))
-    tab = torch.zeros(T, 8)
-    tab[:, 0] = torch.tensor(np.sqrt(1.0 / acp)).float()
-    tab[:, 1] = torch.tensor(np.sqrt(1.0 / acp - 1)).float()
-    tab[:, 2] = torch.tensor(betas * np.sqrt(acp_prev) / (1.0 - acp)).float()
-    tab[:, 3] = torch.tensor((1.0 - acp_prev) * np.sqrt(alphas) / (1.0 - acp)).float()
-    tab[:, 4] = torch.exp(0.5 * torch.tensor(logvar).float())
+    betas = beta_schedule(dcfg["beta_schedule"], dcfg["beta_start"], dcfg["beta_end"], T)
+    var_type = dcfg.get("model_var_type", "fixedsmall")
+    with np.errstate(divide="ignore", invalid="ignore"):  # 'jsd' ends at beta = 1: the reference's tables hold inf there too
+        alphas = 1.0 - betas
+        acp = np.cumprod(alphas, axis=0)
+        acp_prev = np.append(1.0, acp[:-1])
+        post_var = betas * (1.0 - acp_prev) / (1.0 - acp)
+        if var_type == "fixedsmall":      # the shipped configs (diffusion.py:204-206)
+            logvar = np.log(np.maximum(post_var, 1e-20))
+        elif var_type == "fixedlarge":    # diffusion.py:201-203
+            logvar = np.log(np.append(post_var[1], betas[1:]))
+        else:
+            raise NotImplementedError("model_var_type %r (the reference knows fixedsmall / fixedlarge)" % var_type)
+        tab = torch.zeros(T, 8)
+        tab[:, 0] = torch.tensor(np.sqrt(1.0 / acp)).float()
+        tab[:, 1] = torch.tensor(np.sqrt(1.0 / acp - 1)).float()
+        tab[:, 2] = torch.tensor(betas * np.sqrt(acp_prev) / (1.0 - acp)).float()
+        tab[:, 3] = torch.tensor((1.0 - acp_prev) * np.sqrt(alphas) / (1.0 - acp)).float()
+        tab[:, 4] = torch.exp(0.5 * torch.tensor(logvar).float())
     return tab.numpy()
+
+
+def beta_schedule(name, beta_start, beta_end, T):
+    """get_beta_schedule (diffusion_utils/diffusion.py:12-28), float64.  Every shipped config is 'linear'; 'quad', 'const'
+    and 'jsd' are the reference's other working branches ('warmup10' / 'warmup50' call a helper the reference never defines)."""
+    if name == "linear":
+        return np.linspace(beta_start, beta_end, T, dtype=np.float64)
+    if name == "quad":
+        return np.linspace(beta_start ** 0.5, beta_end ** 0.5, T, dtype=np.float64) ** 2
+    if name == "const":
+        return beta_end * np.ones(T, dtype=np.float64)
+    if name == "jsd":  # 1/T, 1/(T-1), ..., 1
+        return 1.0 / np.linspace(T, 1, T, dtype=np.float64)
+    raise NotImplementedError(name)
 
 
 def _alpha_bar_fp32(T, beta_0, beta_T):

@@ -214,3 +214,41 @@ def test_position_sampler_matches_reference_golden(gs, pipeline_cfg):
         m.set_step(t)
         m.run(upd, 1)
     assert np.array_equal(m.download(h["x"]).reshape(B, 16, 3).numpy(), gs["pos_out"])
+
+
+@pytest.mark.parametrize("ci", range(6))
+def test_update_record_under_the_reference_s_other_schedules(ci, pipeline_cfg):
+    """engine.latent_table for get_beta_schedule 'quad' / 'const' / 'jsd', model_var_type 'fixedlarge' and other step counts /
+    beta ranges (no shipped config selects them) + the mode-1 update record: bit-exact against the REAL Diffusion class and
+    denoising_step (tests/golden/make_golden_schedules.py), including the inf / nan the reference itself produces at the
+    last 'jsd' step."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gsch = np.load(os.path.join(root, "tests", "golden", "golden_schedules.npz"))
+    case = json.loads(str(gsch["cases_json"]))[ci]
+    T, B = case["num_diffusion_timesteps"], 2
+    dcfg = dict(case, data_clamp_range=-1)
+    lat = pipeline_cfg["latent_ddpm"]
+    b, h = engine.build_ddpm(lat["pointnet_config"], common.state_dict("lat"), B, T, engine.latent_table(dcfg), 1, keep_cols=3)
+    upd = [i for i, op in enumerate(b.ops) if op[0] == KIND["SLIDE_OP_DDPM_UPDATE"]][0]
+    m = ir_exec.Machine(b)
+    x = torch.cat([torch.from_numpy(gsch["keypoint"]), torch.from_numpy(gsch["x"])[:, :, 3:]], dim=2)
+    nz = m.view(h["noise"]).reshape(T, B * 16, h["C"])
+    model = _stand_in(T)
+    for j, t in enumerate([T - 1, T // 2, 1, 0]):
+        m.upload(h["x"], x)
+        nz[t] = gsch["c%d_noise" % ci][j].reshape(B * 16, -1)
+        m.upload(h["eps"], model(x, torch.ones(B) * t))
+        m.set_step(t)
+        m.run(upd, 1)
+        got = m.download(h["x"]).reshape(B, 16, -1).numpy()
+        assert np.array_equal(got, gsch["c%d_out_t%d" % (ci, t)], equal_nan=True), (case, t)
+
+
+def test_unknown_schedules_are_refused():
+    with pytest.raises(NotImplementedError):
+        engine.beta_schedule("warmup10", 1e-4, 0.02, 10)     # NameError in the reference itself (undefined _warmup_beta)
+    with pytest.raises(NotImplementedError):
+        engine.latent_table(dict(beta_schedule="linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=10,
+                                 model_var_type="learned"))
